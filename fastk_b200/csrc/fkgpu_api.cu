@@ -1,0 +1,775 @@
+/*  fkgpu_api.cu -- C ABI (include/fastk_gpu.h) and host-side orchestration of the sm_100a kernels in
+ *  fkgpu_kernels.cuh.  One context = one GPU = one stream.  No CPU fallback anywhere: every entry point
+ *  either runs the CUDA path or returns an error.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <vector>
+#include <mutex>
+#include <algorithm>
+
+#include "fastk_gpu.h"
+#include "fkgpu_kernels.cuh"
+
+using namespace fk;
+
+static thread_local char g_err[1024] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{ va_list ap;
+  va_start(ap,fmt);
+  vsnprintf(g_err,sizeof(g_err),fmt,ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return set_err(FKGPU_E_CUDA,"%s failed at %s:%d: %s",#call,__FILE__,__LINE__,cudaGetErrorString(e_)); } while (0)
+
+struct DevBuf
+  { void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    { if (bytes <= cap) return 0;
+      if (p) cudaFree(p);
+      p = nullptr; cap = 0;
+      size_t want = bytes + (bytes >> 4) + 4096;
+      if (cudaMalloc(&p,want) != cudaSuccess)
+        { cudaGetLastError();
+          if (cudaMalloc(&p,bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return 1; }
+          want = bytes;
+        }
+      cap = want;
+      return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  };
+
+struct PinBuf
+  { void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    { if (bytes <= cap) return 0;
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      if (cudaMallocHost(&p,bytes + 4096) != cudaSuccess) { cudaGetLastError(); p = nullptr; return 1; }
+      cap = bytes + 4096;
+      return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  };
+
+#define CHUNK_BYTES (32u << 20)
+
+struct TidState
+  { char   *pin = nullptr;            /* pinned staging chunk                       */
+    size_t  fill = 0;
+    cudaEvent_t done = nullptr;       /* last async copy out of pin                 */
+    bool    inflight = false;
+    std::vector<std::pair<long long,long long> > chunks;   /* (device offset, bytes)            */
+    std::vector<long long> rstart;    /* device position of every read start        */
+    std::vector<int>       rlen;      /* read length (without terminator)           */
+    std::vector<char>      rcont;     /* 1 = this read continues the previous one (rem > 0 carry) */
+    int     carry = 0;                /* previous block ended with rem > 0          */
+  };
+
+struct fkgpu_ctx
+  { fkgpu_config cfg;
+    int  NW, kbytes;
+    cudaStream_t st = nullptr, cst = nullptr;
+    cudaEvent_t  ev[2*FKGPU_NSTAGES + 4];
+    float        ms[FKGPU_NSTAGES];
+    double       bytes[FKGPU_NSTAGES];
+    bool         used[FKGPU_NSTAGES];
+    long long    launches = 0;
+    int          sms = 148;
+
+    /* ingest */
+    std::mutex   mu;
+    std::vector<TidState> tids;
+    DevBuf       ascii;               /* device copy of the ingested blocks           */
+    long long    ascii_used = 0;
+    long long    nreads = 0, nbases = 0;
+    bool         finished = false;
+
+    /* device working set */
+    DevBuf seq, val, bufA, bufB, scnt, hist1, off1, cur1, off2, gstart, eall, epass, poff, bsum, ghist, misc, table;
+    DevBuf segs, child, pcl, sub_s, sub_e, sub_f, sub_ea, sub_ep, sub_off, sub_par, sub_base, rstart_d, prof_d;
+    PinBuf h_table, h_misc, h_prof, h_poff;
+    int64_t h_hist[FKGPU_HIST_BINS];
+
+    /* last result bookkeeping for profiles */
+    long long last_ndist = 0;
+  };
+
+/* ------------------------------------------------------------------------------------------------ */
+
+extern "C" int fkgpu_device_count(void)
+{ int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char *fkgpu_last_error(void) { return g_err; }
+
+extern "C" int fkgpu_record_bytes(int kmer) { return (kmer <= 32) ? 8 : 16; }
+
+extern "C" void fkgpu_packed_words(int64_t npos, int64_t *seq_words, int64_t *val_words)
+{ int64_t vw = (npos + 31) / 32;
+  if (val_words) *val_words = vw + FKGPU_PACK_PAD;
+  if (seq_words) *seq_words = 2*vw + FKGPU_PACK_PAD;
+}
+
+extern "C" int fkgpu_create(const fkgpu_config *cfg, fkgpu_ctx **out)
+{ if (cfg == NULL || out == NULL) return set_err(FKGPU_E_ARG,"fkgpu_create: NULL argument");
+  *out = NULL;
+  if (cfg->kmer < 1) return set_err(FKGPU_E_ARG,"fkgpu_create: k = %d must be positive",cfg->kmer);
+  if (cfg->kmer > FKGPU_MAX_K) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_create: k = %d > %d not supported",cfg->kmer,FKGPU_MAX_K);
+  if (cfg->do_table < 0 || cfg->bc_prefix < 0 || cfg->nthreads < 0)
+    return set_err(FKGPU_E_ARG,"fkgpu_create: negative option");
+  int ndev = fkgpu_device_count();
+  if (ndev <= 0) return set_err(FKGPU_E_NODEVICE,"fkgpu_create: no CUDA device available (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_err(FKGPU_E_ARG,"fkgpu_create: device %d out of range [0,%d)",cfg->device,ndev);
+  CU(cudaSetDevice(cfg->device));
+  fkgpu_ctx *c = new (std::nothrow) fkgpu_ctx();
+  if (c == NULL) return set_err(FKGPU_E_NOMEM,"fkgpu_create: out of host memory");
+  c->cfg = *cfg;
+  if (c->cfg.nthreads < 1) c->cfg.nthreads = 1;
+  c->NW = (cfg->kmer <= 32) ? 1 : 2;
+  c->kbytes = (2*cfg->kmer + 7) >> 3;
+  c->tids.resize(c->cfg.nthreads);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop,cfg->device));
+  c->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->st,cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->cst,cudaStreamNonBlocking));
+  for (auto &e : c->ev) CU(cudaEventCreate(&e));
+  memset(c->ms,0,sizeof(c->ms));
+  memset(c->bytes,0,sizeof(c->bytes));
+  memset(c->used,0,sizeof(c->used));
+  *out = c;
+  return FKGPU_OK;
+}
+
+extern "C" void fkgpu_destroy(fkgpu_ctx *c)
+{ if (c == NULL) return;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto &t : c->tids)
+    { if (t.pin) cudaFreeHost(t.pin);
+      if (t.done) cudaEventDestroy(t.done);
+    }
+  DevBuf *bufs[] = { &c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
+                     &c->eall,&c->epass,&c->poff,&c->bsum,&c->ghist,&c->misc,&c->table,&c->segs,&c->child,&c->pcl,
+                     &c->sub_s,&c->sub_e,&c->sub_f,&c->sub_ea,&c->sub_ep,&c->sub_off,&c->sub_par,&c->sub_base,
+                     &c->rstart_d,&c->prof_d };
+  for (auto b : bufs) b->release();
+  c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
+  for (auto &e : c->ev) cudaEventDestroy(e);
+  if (c->st) cudaStreamDestroy(c->st);
+  if (c->cst) cudaStreamDestroy(c->cst);
+  delete c;
+}
+
+extern "C" int fkgpu_reset(fkgpu_ctx *c)
+{ if (c == NULL) return set_err(FKGPU_E_ARG,"fkgpu_reset: NULL context");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaStreamSynchronize(c->cst));
+  CU(cudaStreamSynchronize(c->st));
+  for (auto &t : c->tids)
+    { t.fill = 0; t.inflight = false; t.chunks.clear(); t.rstart.clear(); t.rlen.clear(); t.rcont.clear(); t.carry = 0; }
+  c->ascii_used = 0; c->nreads = 0; c->nbases = 0; c->finished = false;
+  return FKGPU_OK;
+}
+
+extern "C" int64_t fkgpu_launch_count(fkgpu_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int fkgpu_stage_times(fkgpu_ctx *c, float *ms, double *bytes)
+{ if (c == NULL) return set_err(FKGPU_E_ARG,"fkgpu_stage_times: NULL context");
+  for (int i = 0; i < FKGPU_NSTAGES; i++)
+    { if (ms) ms[i] = c->ms[i];
+      if (bytes) bytes[i] = c->bytes[i];
+    }
+  return FKGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  ingest                                                                                           */
+
+static int ascii_reserve(fkgpu_ctx *c, long long need)      /* c->mu held */
+{ if ((size_t) need + 64 <= c->ascii.cap) return 0;
+  size_t want = std::max((size_t) need + 64, std::max(c->ascii.cap*2,(size_t) 256 << 20));
+  if (c->cfg.reserve_bases > 0)
+    want = std::max(want,(size_t) (c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20)));
+  void *np = nullptr;
+  if (cudaMalloc(&np,want) != cudaSuccess) { cudaGetLastError(); return 1; }
+  if (c->ascii.p)
+    { cudaStreamSynchronize(c->cst);
+      cudaMemcpy(np,c->ascii.p,(size_t) c->ascii_used,cudaMemcpyDeviceToDevice);
+      cudaFree(c->ascii.p);
+    }
+  c->ascii.p = np; c->ascii.cap = want;
+  return 0;
+}
+
+static int flush_tid(fkgpu_ctx *c, TidState &t)
+{ if (t.fill == 0) return FKGPU_OK;
+  long long off;
+  { std::lock_guard<std::mutex> lk(c->mu);
+    if (ascii_reserve(c,c->ascii_used + (long long) t.fill))
+      return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot grow the device read buffer to %lld bytes",c->ascii_used + (long long) t.fill);
+    off = c->ascii_used;
+    c->ascii_used += (long long) t.fill;
+    /* rebase the read starts of this chunk (they were recorded chunk-relative, tagged negative) */
+    CU(cudaMemcpyAsync((char *) c->ascii.p + off,t.pin,t.fill,cudaMemcpyHostToDevice,c->cst));
+    CU(cudaEventRecord(t.done,c->cst));
+  }
+  t.inflight = true;
+  t.chunks.push_back(std::make_pair(off,(long long) t.fill));
+  for (size_t i = t.rstart.size(); i-- > 0; )
+    { if (t.rstart[i] >= 0) break;
+      t.rstart[i] = off + (-(t.rstart[i]) - 1);
+    }
+  t.fill = 0;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int32_t *boff, int32_t nreads, int32_t rem)
+{ if (c == NULL || (nreads > 0 && (bases == NULL || boff == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_ingest: NULL argument");
+  if (tid < 0 || tid >= (int) c->tids.size()) return set_err(FKGPU_E_ARG,"fkgpu_ingest: tid %d out of range [0,%d)",tid,(int) c->tids.size());
+  if (c->finished) return set_err(FKGPU_E_STATE,"fkgpu_ingest: called after fkgpu_finish (use fkgpu_reset)");
+  if (nreads <= 0) return FKGPU_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  TidState &t = c->tids[tid];
+  if (t.pin == nullptr)
+    { if (cudaMallocHost((void **) &t.pin,CHUNK_BYTES) != cudaSuccess)
+        { cudaGetLastError(); return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot allocate pinned staging"); }
+      CU(cudaEventCreateWithFlags(&t.done,cudaEventDisableTiming));
+    }
+  const size_t len = (size_t) boff[nreads] - (size_t) boff[0];
+  if (len > CHUNK_BYTES) return set_err(FKGPU_E_ARG,"fkgpu_ingest: block of %zu bytes exceeds the %u byte staging chunk",len,CHUNK_BYTES);
+  if (t.fill + len > CHUNK_BYTES)
+    { int rc = flush_tid(c,t);
+      if (rc) return rc;
+    }
+  if (t.inflight && t.fill == 0)
+    { CU(cudaEventSynchronize(t.done));      /* the chunk is being reused: previous copy must be out */
+      t.inflight = false;
+    }
+  memcpy(t.pin + t.fill,bases + boff[0],len);
+  long long nb = 0;
+  for (int i = 0; i < nreads; i++)
+    { long long s = (long long) t.fill + (boff[i] - boff[0]);
+      int rl = boff[i+1] - boff[i] - 1;
+      t.rstart.push_back(-(s + 1));            /* chunk relative, fixed up at flush */
+      t.rlen.push_back(rl);
+      t.rcont.push_back((i == 0 && t.carry) ? 1 : 0);
+      nb += rl;
+    }
+  /* a continued read re-delivers its k-1 overlap; count it once (split.c:1046-1053) */
+  long long nr = nreads;
+  if (t.carry) { nr -= 1; nb -= (c->cfg.kmer - 1); }
+  t.carry = (rem > 0);
+  t.fill += len;
+  { std::lock_guard<std::mutex> lk(c->mu);
+    c->nreads += nr;
+    c->nbases += nb;
+  }
+  return FKGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  the counting pipeline                                                                            */
+
+struct Misc            /* small device-side scalars, one cudaMemcpy to read them all */
+  { u64 maxinst, ndistinct, total_pass;
+    u32 ovf_cnt, ticket;
+  };
+
+static void stage_begin(fkgpu_ctx *c, int s) { cudaEventRecord(c->ev[2*s],c->st); c->used[s] = true; }
+static void stage_end  (fkgpu_ctx *c, int s) { cudaEventRecord(c->ev[2*s+1],c->st); }
+
+static int ilog2_ceil(unsigned long long x) { int l = 0; while ((1ull << l) < x) l++; return l; }
+
+#define KCHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+    return set_err(FKGPU_E_CUDA,"kernel launch failed at %s:%d: %s",__FILE__,__LINE__,cudaGetErrorString(e_)); c->launches++; } while (0)
+
+static const u32 SC_CAP = 3072;      /* records one k_sortcount CTA can hold           */
+static const u32 SC_T   = 2048;      /* group packing target                           */
+
+struct ScLayout { u32 tab_off, srt_off, total; };
+static ScLayout sc_layout(int NW)
+{ ScLayout L;
+  u32 recb = (SC_CAP + 2) * 8 * NW;
+  u32 hmax = 1; while (hmax < SC_CAP + SC_CAP/4 + 1) hmax <<= 1;
+  u32 dmax = 1; while (dmax < SC_CAP) dmax <<= 1;
+  L.tab_off = (recb + 127) & ~127u;
+  L.srt_off = L.tab_off + hmax*4;
+  L.total   = L.srt_off + dmax*8;
+  return L;
+}
+
+template<int NW> static int run_large_scan(fkgpu_ctx *c, const u32 *in, long long n, u64 *out, u64 *total_dev)
+{ long long nb = (n + LS_CHUNK - 1) / LS_CHUNK;
+  if (nb == 0) nb = 1;
+  if (c->bsum.ensure((size_t) nb * 8)) return set_err(FKGPU_E_NOMEM,"scan: out of device memory");
+  k_lscan_reduce<<<(unsigned) nb,256,0,c->st>>>(in,n,(u64 *) c->bsum.p); KCHECK();
+  k_lscan_top<<<1,1024,0,c->st>>>((u64 *) c->bsum.p,nb,total_dev); KCHECK();
+  k_lscan_apply<<<(unsigned) nb,256,0,c->st>>>(in,n,(const u64 *) c->bsum.p,out); KCHECK();
+  return FKGPU_OK;
+}
+
+/*  Everything after "records are in bufA grouped by their top P1 bits, off1[] holds the group starts".
+ *  nub = upper bound on the record count used for sizing.                                           */
+template<int NW>
+static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fetch_table, fkgpu_result *res)
+{ typedef Key<NW> K;
+  const int nb1 = 1 << P1;
+  const long long m = (long long) nb1 << P2;           /* # fine buckets */
+  const long long gmax = nub / SC_T + 2;
+  const ScLayout L = sc_layout(NW);
+  Misc *d_misc = (Misc *) c->misc.p;
+
+  K *X = (K *) c->bufA.p, *Y = (K *) c->bufB.p;
+  const u64 *offs = (const u64 *) c->off1.p;
+
+  if (P2 > 0)
+    { if (c->off2.ensure((size_t) (m + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
+      stage_begin(c,FKGPU_ST_L2PART);
+      int grid = std::min(nb1,c->sms * 2);
+      size_t sm = (size_t) (1 << P2) * 4;
+      CU(cudaFuncSetAttribute(k_refine<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+      k_refine<NW><<<grid,REF_TPB,sm,c->st>>>(X,Y,(const u64 *) c->off1.p,nb1,P1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
+      stage_end(c,FKGPU_ST_L2PART);
+      offs = (const u64 *) c->off2.p;
+      std::swap(X,Y);
+    }
+  /* now: records in X, grouped into m fine buckets with starts offs[0..m]; Y is free */
+
+  if (c->gstart.ensure((size_t) (gmax + 2) * 8) || c->eall.ensure((size_t) gmax * 4) || c->epass.ensure((size_t) gmax * 4)
+      || c->poff.ensure((size_t) (gmax + 1) * 8) || c->scnt.ensure((size_t) (nub + 2) * 4))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (group arrays)");
+  u64 *gstart = (u64 *) c->gstart.p;
+  k_fill_u64<<<(unsigned) ((gmax + 1 + 255) / 256),256,0,c->st>>>(gstart,gmax + 1,offs + m); KCHECK();
+  k_groups<<<(unsigned) ((m + 1 + 255) / 256),256,0,c->st>>>(offs,m,SC_T,gstart,gmax); KCHECK();
+
+  stage_begin(c,FKGPU_ST_SORTCOUNT);
+  SortCountParams sp;
+  sp.in0 = X; sp.stage0 = Y; sp.in1 = Y; sp.stage1 = X;
+  sp.stage_cnt = (u32 *) c->scnt.p;
+  sp.starts = gstart; sp.ends = gstart + 1; sp.flags = NULL;
+  sp.e_all = (u32 *) c->eall.p; sp.e_pass = (u32 *) c->epass.p;
+  sp.g_hist = (u64 *) c->ghist.p; sp.g_maxinst = &d_misc->maxinst; sp.g_ndistinct = &d_misc->ndistinct;
+  if (c->segs.ensure((size_t) gmax * 4)) return set_err(FKGPU_E_NOMEM,"out of device memory (overflow list)");
+  sp.ovf_cnt = &d_misc->ovf_cnt; sp.ovf_list = (u32 *) c->segs.p; sp.ovf_cap = (u32) std::min<long long>(gmax,0x7fffffffll);
+  sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax;
+  sp.tab_off = L.tab_off; sp.srt_off = L.srt_off;
+  CU(cudaFuncSetAttribute(k_sortcount<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) L.total));
+  k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK();
+  stage_end(c,FKGPU_ST_SORTCOUNT);
+
+  /* first sync: overflow list + totals */
+  Misc hm;
+  CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+
+  /* ---- fallback for oversize groups (heavy repeats): host-driven MSD refinement ---------------- */
+  struct Sub { u64 s, e; u32 fl; u32 parent; };
+  std::vector<Sub> subs;
+  if (hm.ovf_cnt > 0)
+    { if (hm.ovf_cnt > sp.ovf_cap) return set_err(FKGPU_E_CUDA,"internal: overflow list truncated");
+      std::vector<u32> og(hm.ovf_cnt);
+      CU(cudaMemcpy(og.data(),c->segs.p,(size_t) hm.ovf_cnt * 4,cudaMemcpyDeviceToHost));
+      std::sort(og.begin(),og.end());
+      std::vector<Sub> work;
+      for (u32 g : og)
+        { u64 se[2];
+          CU(cudaMemcpy(se,gstart + g,16,cudaMemcpyDeviceToHost));
+          Sub w; w.s = se[0]; w.e = se[1]; w.fl = 0; w.parent = g;
+          work.push_back(w);
+        }
+      int guard = 0;
+      while (!work.empty())
+        { if (++guard > 40) return set_err(FKGPU_E_CUDA,"internal: refinement did not converge");
+          size_t ns = work.size();
+          std::vector<u64> hs(ns), he(ns); std::vector<u32> hf(ns);
+          for (size_t i = 0; i < ns; i++) { hs[i] = work[i].s; he[i] = work[i].e; hf[i] = work[i].fl; }
+          if (c->sub_s.ensure(ns*8) || c->sub_e.ensure(ns*8) || c->sub_f.ensure(ns*4) || c->child.ensure(ns*257*8) || c->pcl.ensure(ns*4))
+            return set_err(FKGPU_E_NOMEM,"out of device memory (refinement)");
+          CU(cudaMemcpyAsync(c->sub_s.p,hs.data(),ns*8,cudaMemcpyHostToDevice,c->st));
+          CU(cudaMemcpyAsync(c->sub_e.p,he.data(),ns*8,cudaMemcpyHostToDevice,c->st));
+          CU(cudaMemcpyAsync(c->sub_f.p,hf.data(),ns*4,cudaMemcpyHostToDevice,c->st));
+          k_autorefine<NW><<<(unsigned) ns,AR_TPB,0,c->st>>>(X,Y,(const u64 *) c->sub_s.p,(const u64 *) c->sub_e.p,
+                                                            (const u32 *) c->sub_f.p,(u64 *) c->child.p,(u32 *) c->pcl.p); KCHECK();
+          std::vector<u64> hc(ns*257); std::vector<u32> hp(ns);
+          CU(cudaMemcpyAsync(hc.data(),c->child.p,ns*257*8,cudaMemcpyDeviceToHost,c->st));
+          CU(cudaMemcpyAsync(hp.data(),c->pcl.p,ns*4,cudaMemcpyDeviceToHost,c->st));
+          CU(cudaStreamSynchronize(c->st));
+          std::vector<Sub> next;
+          for (size_t i = 0; i < ns; i++)
+            { if ((int) hp[i] >= 64*NW)
+                { Sub u = work[i]; u.fl |= ITEM_UNIFORM; subs.push_back(u); continue; }
+              for (int d = 0; d < 256; d++)
+                { u64 s = hc[i*257+d], e = hc[i*257+d+1];
+                  if (e == s) continue;
+                  Sub u; u.s = s; u.e = e; u.fl = work[i].fl ^ ITEM_ALTBUF; u.parent = work[i].parent;
+                  if (e - s <= SC_CAP) subs.push_back(u); else next.push_back(u);
+                }
+            }
+          work.swap(next);
+        }
+      std::sort(subs.begin(),subs.end(),[](const Sub &a, const Sub &b) { return a.s < b.s; });
+      size_t nsub = subs.size();
+      std::vector<u64> hs(nsub), he(nsub); std::vector<u32> hf(nsub), hpar(nsub);
+      for (size_t i = 0; i < nsub; i++) { hs[i] = subs[i].s; he[i] = subs[i].e; hf[i] = subs[i].fl; hpar[i] = subs[i].parent; }
+      if (c->sub_s.ensure(nsub*8) || c->sub_e.ensure(nsub*8) || c->sub_f.ensure(nsub*4) || c->sub_ea.ensure(nsub*4) || c->sub_ep.ensure(nsub*4)
+          || c->sub_off.ensure(nsub*8) || c->sub_par.ensure(nsub*4) || c->sub_base.ensure(nsub*8))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (refinement items)");
+      CU(cudaMemcpyAsync(c->sub_s.p,hs.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->sub_e.p,he.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->sub_f.p,hf.data(),nsub*4,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->sub_par.p,hpar.data(),nsub*4,cudaMemcpyHostToDevice,c->st));
+      SortCountParams sq = sp;
+      sq.starts = (const u64 *) c->sub_s.p; sq.ends = (const u64 *) c->sub_e.p; sq.flags = (const u32 *) c->sub_f.p;
+      sq.e_all = (u32 *) c->sub_ea.p; sq.e_pass = (u32 *) c->sub_ep.p; sq.nitems = (long long) nsub;
+      k_sortcount<NW><<<(unsigned) nsub,SC_TPB,L.total,c->st>>>(sq); KCHECK();
+      std::vector<u32> hep(nsub);
+      CU(cudaMemcpyAsync(hep.data(),c->sub_ep.p,nsub*4,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      if (hm.ovf_cnt != (u32) og.size()) return set_err(FKGPU_E_CUDA,"internal: refinement left oversize items");
+      /* per parent group: total of its sub-items goes into e_pass[parent]; each sub-item gets its base */
+      std::vector<u64> hbase(nsub);
+      size_t i = 0;
+      while (i < nsub)
+        { size_t j = i; u64 run = 0;
+          while (j < nsub && hpar[j] == hpar[i]) { hbase[j] = run; run += hep[j]; j++; }
+          u32 tot = (u32) run;
+          CU(cudaMemcpyAsync((u32 *) c->epass.p + hpar[i],&tot,4,cudaMemcpyHostToDevice,c->st));
+          CU(cudaStreamSynchronize(c->st));
+          i = j;
+        }
+      CU(cudaMemcpyAsync(c->sub_base.p,hbase.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
+    }
+
+  /* ---- table: scan the per-item pass counts, compact ------------------------------------------- */
+  res->ntable = 0; res->table = NULL; res->table_dev = NULL;
+  const int tw = c->kbytes + 2;
+  if (c->cfg.do_table > 0)
+    { stage_begin(c,FKGPU_ST_COMPACT);
+      int rc = run_large_scan<NW>(c,(const u32 *) c->epass.p,gmax,(u64 *) c->poff.p,&d_misc->total_pass);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      if (c->table.ensure((size_t) hm.total_pass * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of device memory (table of %llu entries)",hm.total_pass);
+      CompactParams cp;
+      cp.stage0 = Y; cp.stage1 = X; cp.stage_cnt = (const u32 *) c->scnt.p;
+      cp.starts = gstart; cp.flags = NULL; cp.e_all = (const u32 *) c->eall.p; cp.out_off = (const u64 *) c->poff.p;
+      cp.out = (uint8_t *) c->table.p; cp.nitems = gmax; cp.cutoff = (u32) c->cfg.do_table; cp.kbytes = c->kbytes;
+      int grid = c->sms * 8;
+      k_compact<NW><<<grid,256,0,c->st>>>(cp); KCHECK();
+      if (!subs.empty())
+        { size_t nsub = subs.size();
+          k_suboff<<<(unsigned) ((nsub + 255) / 256),256,0,c->st>>>((u64 *) c->sub_off.p,(const u32 *) c->sub_par.p,
+                                                                   (const u64 *) c->sub_base.p,(const u64 *) c->poff.p,(long long) nsub); KCHECK();
+          CompactParams cq = cp;
+          cq.starts = (const u64 *) c->sub_s.p; cq.flags = (const u32 *) c->sub_f.p; cq.e_all = (const u32 *) c->sub_ea.p;
+          cq.out_off = (const u64 *) c->sub_off.p; cq.nitems = (long long) nsub;
+          k_compact<NW><<<grid,256,0,c->st>>>(cq); KCHECK();
+        }
+      stage_end(c,FKGPU_ST_COMPACT);
+      res->ntable = (int64_t) hm.total_pass;
+      res->table_dev = (const uint8_t *) c->table.p;
+      if (fetch_table)
+        { if (c->h_table.ensure((size_t) hm.total_pass * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
+          CU(cudaMemcpyAsync(c->h_table.p,c->table.p,(size_t) hm.total_pass * tw,cudaMemcpyDeviceToHost,c->st));
+          res->table = (const uint8_t *) c->h_table.p;
+        }
+    }
+
+  /* ---- histogram + scalars --------------------------------------------------------------------- */
+  u64 ntot;
+  CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(&ntot,(const u64 *) c->off1.p + nb1,8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  res->hist = c->h_hist;
+  res->max_inst = (int64_t) hm.maxinst;
+  res->ndistinct = (int64_t) hm.ndistinct;
+  res->nkmers = (int64_t) ntot;
+  c->last_ndist = (long long) hm.ndistinct;
+  return FKGPU_OK;
+}
+
+static void make_kmask(int k, u32 *km)
+{ for (int m = 0; m < 4; m++)
+    { int lo = 32*m, hi = 32*(m+1);
+      if (hi <= 2*k) km[m] = 0xffffffffu;
+      else if (lo >= 2*k) km[m] = 0;
+      else km[m] = 0xffffffffu << (hi - 2*k);
+    }
+}
+
+static void choose_levels(long long nub, int *P1, int *P2)
+{ unsigned long long want = (unsigned long long) std::max<long long>(1,nub / 256);
+  int P = ilog2_ceil(want);
+  if (P > 23) P = 23;
+  *P1 = std::min(P,11);
+  *P2 = P - *P1;
+}
+
+static int prepare_common(fkgpu_ctx *c, long long nub, int P1)
+{ const int nb1 = 1 << P1;
+  const size_t rb = (size_t) 8 * c->NW;
+  if (c->bufA.ensure((size_t) (nub + 4) * rb) || c->bufB.ensure((size_t) (nub + 4) * rb))
+    return set_err(FKGPU_E_NOMEM,"out of device memory: two record buffers of %lld x %zu bytes",nub,rb);
+  if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8)
+      || c->ghist.ensure(FKGPU_HIST_BINS * 8) || c->misc.ensure(sizeof(Misc)))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (histograms)");
+  CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (nb1 + 1) * 8,c->st));
+  CU(cudaMemsetAsync(c->ghist.p,0,FKGPU_HIST_BINS * 8,c->st));
+  CU(cudaMemsetAsync(c->misc.p,0,sizeof(Misc),c->st));
+  return FKGPU_OK;
+}
+
+static void collect_times(fkgpu_ctx *c, fkgpu_result *res)
+{ for (int s = 0; s < FKGPU_NSTAGES; s++)
+    { c->ms[s] = 0;
+      if (c->used[s]) cudaEventElapsedTime(&c->ms[s],c->ev[2*s],c->ev[2*s+1]);
+    }
+  float tot = 0;
+  cudaEventElapsedTime(&tot,c->ev[2*FKGPU_NSTAGES],c->ev[2*FKGPU_NSTAGES+1]);
+  res->ms_pack = c->ms[FKGPU_ST_PACK];
+  res->ms_total = tot;
+  res->ms_count = tot - res->ms_pack;
+}
+
+template<int NW>
+static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res, bool own_total)
+{ int P1, P2;
+  choose_levels(npos,&P1,&P2);
+  int rc = prepare_common(c,npos,P1);
+  if (rc) return rc;
+  const int nb1 = 1 << P1;
+
+  ScanParams sp;
+  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
+  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+  sp.k = c->cfg.kmer; sp.pbits = P1;
+  make_kmask(c->cfg.kmer,sp.kmask);
+  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t smh = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4;
+  const size_t sms = smh + (size_t) nb1 * 8;
+  CU(cudaFuncSetAttribute(k_scan<NW,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
+  CU(cudaFuncSetAttribute(k_scan<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+
+  if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  if (ntiles > 0)
+    { stage_begin(c,FKGPU_ST_SCANHIST);
+      sp.hist = (u64 *) c->hist1.p; sp.out = NULL;
+      k_scan<NW,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); KCHECK();
+      stage_end(c,FKGPU_ST_SCANHIST);
+    }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,nb1); KCHECK();
+  if (ntiles > 0)
+    { stage_begin(c,FKGPU_ST_SCATTER);
+      sp.hist = (u64 *) c->cur1.p; sp.out = c->bufA.p;
+      k_scan<NW,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); KCHECK();
+      stage_end(c,FKGPU_ST_SCATTER);
+    }
+  rc = count_from_level1<NW>(c,npos,P1,P2,fetch_table,res);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  return FKGPU_OK;
+}
+
+static void init_result(fkgpu_ctx *c, fkgpu_result *res)
+{ memset(res,0,sizeof(*res));
+  res->kmer = c->cfg.kmer;
+  res->kmer_bytes = c->kbytes;
+  memset(c->used,0,sizeof(c->used));
+}
+
+extern "C" int fkgpu_count_packed(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                                  int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL || (npos > 0 && (d_seq == NULL || d_val == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_count_packed: NULL argument");
+  if (npos < 0) return set_err(FKGPU_E_ARG,"fkgpu_count_packed: negative length");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  res->nbases = npos;
+  int rc = (c->NW == 1) ? count_packed_t<1>(c,d_seq,d_val,npos,fetch_table,res,true)
+                        : count_packed_t<2>(c,d_seq,d_val,npos,fetch_table,res,true);
+  return rc;
+}
+
+extern "C" int fkgpu_pack_ascii_dev(fkgpu_ctx *c, const char *d_ascii, int64_t npos, uint32_t *d_seq, uint32_t *d_val)
+{ if (c == NULL || (npos > 0 && (d_ascii == NULL || d_seq == NULL || d_val == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_pack_ascii_dev: NULL argument");
+  CU(cudaSetDevice(c->cfg.device));
+  if (((uintptr_t) d_ascii & 15) != 0) return set_err(FKGPU_E_ARG,"fkgpu_pack_ascii_dev: input must be 16-byte aligned");
+  long long vw = (npos + 31) / 32;
+  if (vw > 0)
+    { k_pack_ascii<<<(unsigned) ((vw + 255) / 256),256,0,c->st>>>((const uint4 *) d_ascii,npos,d_seq,d_val,vw);
+      KCHECK();
+    }
+  CU(cudaMemsetAsync(d_seq + 2*vw,0,FKGPU_PACK_PAD * 4,c->st));
+  CU(cudaMemsetAsync(d_val + vw,0,FKGPU_PACK_PAD * 4,c->st));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL) return set_err(FKGPU_E_ARG,"fkgpu_finish: NULL argument");
+  if (c->finished) return set_err(FKGPU_E_STATE,"fkgpu_finish: already finished (use fkgpu_reset)");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  for (auto &t : c->tids)
+    { int rc = flush_tid(c,t);
+      if (rc) return rc;
+    }
+  CU(cudaStreamSynchronize(c->cst));
+  c->finished = true;
+  const long long npos = c->ascii_used;
+  res->nbases = c->nbases;
+  res->nreads = c->nreads;
+  int64_t sw, vw;
+  fkgpu_packed_words(npos,&sw,&vw);
+  if (c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (packed reads)");
+  { std::lock_guard<std::mutex> lk(c->mu);
+    if (ascii_reserve(c,npos + 64)) return set_err(FKGPU_E_NOMEM,"out of device memory (read buffer)");
+  }
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  stage_begin(c,FKGPU_ST_PACK);
+  int rc = fkgpu_pack_ascii_dev(c,(const char *) c->ascii.p,npos,(uint32_t *) c->seq.p,(uint32_t *) c->val.p);
+  if (rc) return rc;
+  if (c->cfg.bc_prefix > 0 || c->cfg.do_profile)
+    { /* read starts on the device, tid-major */
+      std::vector<long long> rs;
+      for (auto &t : c->tids) rs.insert(rs.end(),t.rstart.begin(),t.rstart.end());
+      if (c->rstart_d.ensure(rs.size()*8 + 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (read index)");
+      if (!rs.empty())
+        { CU(cudaMemcpyAsync(c->rstart_d.p,rs.data(),rs.size()*8,cudaMemcpyHostToDevice,c->st));
+          CU(cudaStreamSynchronize(c->st));
+          if (c->cfg.bc_prefix > 0)
+            { k_mask_prefix<<<(unsigned) ((rs.size() + 255) / 256),256,0,c->st>>>((const long long *) c->rstart_d.p,(long long) rs.size(),
+                                                                                  c->cfg.bc_prefix,npos,(u32 *) c->val.p);
+              KCHECK();
+            }
+        }
+    }
+  stage_end(c,FKGPU_ST_PACK);
+  rc = (c->NW == 1) ? count_packed_t<1>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false)
+                    : count_packed_t<2>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  multi-GPU stages                                                                                 */
+
+extern "C" int fkgpu_prefix_hist(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int bits, uint64_t *d_hist)
+{ if (c == NULL || d_hist == NULL || bits < 0 || bits > 11) return set_err(FKGPU_E_ARG,"fkgpu_prefix_hist: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const int nb1 = 1 << bits;
+  CU(cudaMemsetAsync(d_hist,0,(size_t) nb1 * 8,c->st));
+  ScanParams sp;
+  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
+  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+  sp.k = c->cfg.kmer; sp.pbits = bits; sp.hist = (u64 *) d_hist; sp.out = NULL;
+  make_kmask(c->cfg.kmer,sp.kmask);
+  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t smh = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4;
+  if (ntiles > 0)
+    { if (c->NW == 1)
+        { CU(cudaFuncSetAttribute(k_scan<1,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
+          k_scan<1,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); }
+      else
+        { CU(cudaFuncSetAttribute(k_scan<2,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
+          k_scan<2,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); }
+      KCHECK();
+    }
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_scatter_prefix(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int bits,
+                                    const uint64_t *d_hist, void *d_records, int64_t cap_records, uint64_t *d_offsets)
+{ if (c == NULL || d_hist == NULL || d_records == NULL || d_offsets == NULL || bits < 0 || bits > 11)
+    return set_err(FKGPU_E_ARG,"fkgpu_scatter_prefix: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const int nb1 = 1 << bits;
+  if (c->cur1.ensure((size_t) (nb1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) c->cur1.p,nb1); KCHECK();
+  u64 tot;
+  CU(cudaMemcpyAsync(&tot,d_offsets + nb1,8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if ((int64_t) tot > cap_records) return set_err(FKGPU_E_ARG,"fkgpu_scatter_prefix: %llu records exceed the capacity %lld",tot,(long long) cap_records);
+  ScanParams sp;
+  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
+  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+  sp.k = c->cfg.kmer; sp.pbits = bits; sp.hist = (u64 *) c->cur1.p; sp.out = d_records;
+  make_kmask(c->cfg.kmer,sp.kmask);
+  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t sms = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4 + (size_t) nb1 * 8;
+  if (ntiles > 0)
+    { if (c->NW == 1)
+        { CU(cudaFuncSetAttribute(k_scan<1,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+          k_scan<1,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); }
+      else
+        { CU(cudaFuncSetAttribute(k_scan<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+          k_scan<2,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); }
+      KCHECK();
+    }
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
+template<int NW>
+static int count_records_t(fkgpu_ctx *c, const void *d_records, long long n, int fetch_table, fkgpu_result *res)
+{ int P1, P2;
+  choose_levels(n,&P1,&P2);
+  int rc = prepare_common(c,n,P1);
+  if (rc) return rc;
+  const int nb1 = 1 << P1;
+  const size_t smh = (size_t) (nb1 + (nb1 & 1)) * 4;
+  const size_t sms = smh + (size_t) nb1 * 8;
+  const long long ntiles = (n + TP_TILE - 1) / TP_TILE;
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  if (ntiles > 0)
+    { stage_begin(c,FKGPU_ST_L2HIST);
+      k_tilepart<NW,false><<<(unsigned) ntiles,TP_TPB,smh,c->st>>>((const Key<NW> *) d_records,NULL,(u64) n,P1,(u64 *) c->hist1.p); KCHECK();
+      stage_end(c,FKGPU_ST_L2HIST);
+    }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,nb1); KCHECK();
+  if (ntiles > 0)
+    { stage_begin(c,FKGPU_ST_SCATTER);
+      CU(cudaFuncSetAttribute(k_tilepart<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<NW,true><<<(unsigned) ntiles,TP_TPB,sms,c->st>>>((const Key<NW> *) d_records,(Key<NW> *) c->bufA.p,(u64) n,P1,(u64 *) c->cur1.p); KCHECK();
+      stage_end(c,FKGPU_ST_SCATTER);
+    }
+  rc = count_from_level1<NW>(c,n,P1,P2,fetch_table,res);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_count_records(fkgpu_ctx *c, void *d_records, int64_t nrecords, int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL || nrecords < 0 || (nrecords > 0 && d_records == NULL))
+    return set_err(FKGPU_E_ARG,"fkgpu_count_records: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  return (c->NW == 1) ? count_records_t<1>(c,d_records,nrecords,fetch_table,res)
+                      : count_records_t<2>(c,d_records,nrecords,fetch_table,res);
+}
+
+extern "C" int fkgpu_profiles(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)
+{ (void) nreads; (void) off; (void) prof;
+  if (c == NULL) return set_err(FKGPU_E_ARG,"fkgpu_profiles: NULL context");
+  return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_profiles: not built yet");
+}

@@ -1,0 +1,897 @@
+/*  fkgpu_kernels.cuh -- sm_100a kernels of the FastK counting hot path.
+ *
+ *  Data model (all integer):
+ *    packed reads   seq: 16 bases / u32 word, first base in bits 31:30;  val: 32 positions / u32 word,
+ *                   MSB first, 1 = acgt.  Reads are concatenated with one invalid (terminator) position
+ *                   between them, so a k-mer window is legal iff its k val bits are all 1
+ *                   (restates split.c:1079-1086,1124-1129: short reads and non-acgt windows are dropped).
+ *    record         Key<NW>: NW 64-bit words, word 0 most significant, the canonical k-mer left aligned
+ *                   (bit 63 of w[0] = high bit of the first base), unused low bits 0.  Integer order of
+ *                   (w[0],w[1]) == bytewise order of the reference's KMER_BYTES key (count.c:473-510).
+ *
+ *  Pipeline (fkgpu_api.cu drives it):
+ *    k_scan<HIST>     reads -> histogram of the top P1 key bits               (replaces split.c scan + count.c:1406-1414)
+ *    k_scan<SCATTER>  reads -> records grouped by that prefix into buffer A   (replaces Distribute_Block/kmer_list_thread)
+ *    k_refine         one CTA per prefix bucket: MSD pass on the next P2 bits, A -> B, cursors in smem (MSDsort.c:129-261)
+ *    k_groups         packs consecutive fine buckets into <= C-record work groups
+ *    k_sortcount      one CTA per group: TMA bulk load -> smem hash count -> bitonic sort of the distinct keys
+ *                     -> run totals, histogram, staged (key,count)            (MSDsort.c:491-509 hist_kmers)
+ *    k_compact        staged entries -> [KMER_BYTES key][u16 count] records    (count.c:564-616 table_write_thread)
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fk {
+
+typedef unsigned long long u64;
+typedef uint32_t           u32;
+
+template<int NW> struct __align__(8 * NW) Key { u64 w[NW]; };
+
+template<int NW> __device__ __forceinline__ bool key_eq(const Key<NW> &a, const Key<NW> &b)
+{ bool e = true;
+#pragma unroll
+  for (int i = 0; i < NW; i++) e = e && (a.w[i] == b.w[i]);
+  return e;
+}
+template<int NW> __device__ __forceinline__ bool key_lt(const Key<NW> &a, const Key<NW> &b)
+{
+#pragma unroll
+  for (int i = 0; i < NW; i++)
+    { if (a.w[i] < b.w[i]) return true;
+      if (a.w[i] > b.w[i]) return false;
+    }
+  return false;
+}
+
+/* 64 key bits starting at bit position pos (0 = MSB of w[0]); zero filled past the end */
+template<int NW> __device__ __forceinline__ u64 key_bits64(const Key<NW> &a, int pos)
+{ if (NW == 1)
+    return (pos < 64) ? (a.w[0] << pos) : 0ull;
+  else
+    { if (pos == 0)  return a.w[0];
+      if (pos < 64)  return (a.w[0] << pos) | (a.w[NW > 1 ? 1 : 0] >> (64 - pos));
+      if (pos < 128) return a.w[NW > 1 ? 1 : 0] << (pos - 64);
+      return 0ull;
+    }
+}
+template<int NW> __device__ __forceinline__ u32 key_digit(const Key<NW> &a, int pos, int nbits)
+{ return (u32) (key_bits64<NW>(a,pos) >> (64 - nbits)); }
+
+/* reverse-complement the 16 bases of a packed word */
+__device__ __forceinline__ u32 rc32(u32 x)
+{ x = __brev(~x);
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+struct V96 { u32 a, b, c; };       /* 96 validity bits, MSB first */
+
+__device__ __forceinline__ V96 shl96(V96 v, int s)
+{ V96 r;
+  if (s >= 96) { r.a = r.b = r.c = 0; return r; }
+  if (s >= 64) { v.a = v.c; v.b = 0; v.c = 0; s -= 64; }
+  else if (s >= 32) { v.a = v.b; v.b = v.c; v.c = 0; s -= 32; }
+  r.a = __funnelshift_l(v.b,v.a,s);
+  r.b = __funnelshift_l(v.c,v.b,s);
+  r.c = v.c << s;
+  return r;
+}
+__device__ __forceinline__ V96 and96(V96 x, V96 y) { V96 r; r.a = x.a&y.a; r.b = x.b&y.b; r.c = x.c&y.c; return r; }
+
+/* bit j (MSB first) of the result = 1 iff positions j .. j+k-1 are all valid  (erosion by k) */
+__device__ __forceinline__ u32 window_ok(V96 v, int k)
+{ V96 acc; acc.a = acc.b = acc.c = 0xffffffffu;
+  V96 pw = v;
+  int m = 0, n = 1;
+  while (n <= k)
+    { if (k & n)
+        { acc = and96(acc,shl96(pw,m));
+          m += n;
+        }
+      pw = and96(pw,shl96(pw,n));
+      n <<= 1;
+    }
+  return acc.a;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+
+struct ScanParams
+  { const u32 *seq;          /* packed bases                                   */
+    const u32 *val;          /* validity bits                                  */
+    long long  npos;         /* # of positions                                 */
+    long long  nseqw;        /* # of real seq words (ceil(npos/16))            */
+    long long  nvalw;        /* # of real val words (ceil(npos/32))            */
+    int        k;
+    int        pbits;        /* P1                                             */
+    u32        kmask[4];     /* mask of the 2k key bits over four 32-bit words */
+    u64       *hist;         /* [2^P1]  HIST: += ; SCATTER: running cursors    */
+    void      *out;          /* SCATTER: record buffer                         */
+  };
+
+#define SCAN_TPB   256
+#define SCAN_PPT   32                       /* k-mer start positions per thread */
+#define SCAN_TILE  (SCAN_TPB*SCAN_PPT)
+#define SCAN_LHALO 4                        /* seq words kept left of the tile  */
+#define SCAN_SEQW  (SCAN_TILE/16 + SCAN_LHALO + 8)
+#define SCAN_VALW  (SCAN_TILE/32 + 4)
+
+/*  Per-thread window state: W = the 6 packed words covering the thread's 32 start positions and their
+ *  k-1 lookahead, R = the same bases reverse-complemented and reversed, aligned so that the k-mer starting
+ *  at local position j is the bit slice [2j, 2j+2k) of W and [62-2j, 62-2j+2k) of R.                      */
+struct Window { u32 W[6]; u32 R[6]; u32 ok; };
+
+__device__ __forceinline__ void load_window(Window &w, const u32 *s_seq, const u32 *s_val, int t, int k)
+{ const u32 *s = s_seq + SCAN_LHALO + 2*t;
+#pragma unroll
+  for (int i = 0; i < 6; i++) w.W[i] = s[i];
+  const int b  = 2*k + 30;            /* bit offset (from W[0]) of the slice that becomes R[0]   */
+  const int q0 = b >> 5, r = b & 31;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    w.R[i] = rc32(__funnelshift_l(s[q0-i+1],s[q0-i],r));
+  V96 v; v.a = s_val[t]; v.b = s_val[t+1]; v.c = s_val[t+2];
+  w.ok = window_ok(v,k);
+}
+
+/* canonical key words (32-bit, most significant first) of local k-mer J; NW32 = 2*NW */
+template<int NW32, int J>
+__device__ __forceinline__ void canon_kmer(const Window &w, const u32 *kmask, u32 *C)
+{ u32 F[NW32], G[NW32];
+  const int fq = (2*J) >> 5,      fr = (2*J) & 31;
+  const int gq = (62-2*J) >> 5,   gr = (62-2*J) & 31;
+#pragma unroll
+  for (int m = 0; m < NW32; m++)
+    { F[m] = __funnelshift_l(w.W[fq+m+1],w.W[fq+m],fr) & kmask[m];
+      G[m] = __funnelshift_l(w.R[gq+m+1],w.R[gq+m],gr) & kmask[m];
+    }
+  bool lt = false, dec = false;      /* lt = (G < F) decided at the first differing word */
+#pragma unroll
+  for (int m = 0; m < NW32; m++)
+    { if (!dec && F[m] != G[m]) { lt = (G[m] < F[m]); dec = true; } }
+#pragma unroll
+  for (int m = 0; m < NW32; m++) C[m] = lt ? G[m] : F[m];
+}
+
+template<int NW32, int J> struct KmerLoop
+{ template<class Fn> __device__ __forceinline__ static void run(const Window &w, const u32 *kmask, Fn &fn)
+  { if ((w.ok >> (31-J)) & 1u)
+      { u32 C[NW32];
+        canon_kmer<NW32,J>(w,kmask,C);
+        fn(J,C);
+      }
+    KmerLoop<NW32,J+1>::run(w,kmask,fn);
+  }
+};
+template<int NW32> struct KmerLoop<NW32,SCAN_PPT>
+{ template<class Fn> __device__ __forceinline__ static void run(const Window &, const u32 *, Fn &) {} };
+
+__device__ __forceinline__ void scan_load_tile(const ScanParams &p, long long tile, u32 *s_seq, u32 *s_val)
+{ const long long w0 = tile * (SCAN_TILE/16) - SCAN_LHALO;
+  for (int i = threadIdx.x; i < SCAN_SEQW; i += SCAN_TPB)
+    { long long g = w0 + i;
+      s_seq[i] = (g >= 0 && g < p.nseqw) ? __ldg(p.seq+g) : 0u;
+    }
+  const long long v0 = tile * (SCAN_TILE/32);
+  for (int i = threadIdx.x; i < SCAN_VALW; i += SCAN_TPB)
+    { long long g = v0 + i;
+      s_val[i] = (g < p.nvalw) ? __ldg(p.val+g) : 0u;
+    }
+}
+
+template<int NW, bool SCATTER>
+__global__ void __launch_bounds__(SCAN_TPB) k_scan(ScanParams p)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_seq  = s_dyn;
+  u32 *s_val  = s_seq + SCAN_SEQW;
+  u32 *s_hist = s_val + SCAN_VALW;                 /* [2^P1]              */
+  const int nb = 1 << p.pbits;
+  u64 *s_base = (u64 *) (s_hist + nb + (nb & 1));  /* [2^P1] SCATTER only */
+  constexpr int NW32 = 2*NW;
+  const int sh = 32 - p.pbits;
+
+  for (int i = threadIdx.x; i < nb; i += SCAN_TPB) s_hist[i] = 0;
+  scan_load_tile(p,blockIdx.x,s_seq,s_val);
+  __syncthreads();
+
+  Window w;
+  load_window(w,s_seq,s_val,threadIdx.x,p.k);
+  u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
+
+  if (!SCATTER)
+    { auto fn = [&](int, const u32 *C) { atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u); };
+      KmerLoop<NW32,0>::run(w,km,fn);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
+        { u32 c = s_hist[i];
+          if (c) atomicAdd(p.hist+i,(u64) c);
+        }
+    }
+  else
+    { u32 rk[SCAN_PPT/2];
+#pragma unroll
+      for (int i = 0; i < SCAN_PPT/2; i++) rk[i] = 0;
+      auto fa = [&](int j, const u32 *C)
+        { u32 r = atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u);
+          rk[j>>1] |= r << (16*(j&1));
+        };
+      KmerLoop<NW32,0>::run(w,km,fa);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
+        { u32 c = s_hist[i];
+          s_base[i] = c ? atomicAdd(p.hist+i,(u64) c) : 0ull;
+        }
+      __syncthreads();
+      Key<NW> *out = (Key<NW> *) p.out;
+      auto fb = [&](int j, const u32 *C)
+        { u32 d = p.pbits ? (C[0] >> sh) : 0u;
+          u32 r = (rk[j>>1] >> (16*(j&1))) & 0xffffu;
+          Key<NW> key;
+#pragma unroll
+          for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
+          out[s_base[d] + r] = key;
+        };
+      KmerLoop<NW32,0>::run(w,km,fb);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  ASCII -> packed.  One thread = 32 positions = 2 seq words + 1 val word.                          */
+
+__global__ void k_pack_ascii(const uint4 *ascii, long long npos, u32 *seq, u32 *val, long long nvalw)
+{ long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nvalw) return;
+  u32 s0 = 0, s1 = 0, v = 0;
+  long long base = t*32;
+#pragma unroll
+  for (int q = 0; q < 2; q++)
+    { uint4 x = make_uint4(0,0,0,0);
+      if (base + q*16 < npos) x = __ldg(ascii + t*2 + q);       /* buffer is padded to 32 bytes */
+      u32 wd[4] = { x.x, x.y, x.z, x.w };
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        { u32 c = (wd[i>>2] >> (8*(i&3))) & 0xffu;
+          u32 lc = c | 0x20u;
+          bool ok = (lc == 'a') | (lc == 'c') | (lc == 'g') | (lc == 't');
+          ok = ok && (base + q*16 + i < npos);
+          u32 code = ((c >> 1) ^ (c >> 2)) & 3u;
+          code = ok ? code : 0u;
+          if (q == 0) s0 |= code << (30 - 2*i); else s1 |= code << (30 - 2*i);
+          v |= (ok ? 1u : 0u) << (31 - (q*16 + i));
+        }
+    }
+  seq[2*t] = s0; seq[2*t+1] = s1; val[t] = v;
+}
+
+/*  -bc<n>: invalidate the first bc positions of every read (split.c:1075 s += BC_PREFIX).          */
+__global__ void k_mask_prefix(const long long *rstart, long long nreads, int bc, long long npos, u32 *val)
+{ long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nreads) return;
+  long long p = rstart[r];
+  for (int i = 0; i < bc && p + i < npos; i++)
+    atomicAnd(val + ((p+i) >> 5), ~(1u << (31 - ((p+i) & 31))));
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  Small utility kernels                                                                           */
+
+/* exclusive scan of a u64 array of n <= 8192 entries, one CTA; out[n] = total; optional copy to cur */
+__global__ void k_scan_small(const u64 *in, u64 *out, u64 *cur, int n)
+{ __shared__ u64 s_part[1024];
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per;
+  u64 sum = 0;
+  for (int i = b; i < b+per && i < n; i++) sum += in[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { u64 run = 0;
+      for (int i = 0; i < (int) blockDim.x; i++) { u64 x = s_part[i]; s_part[i] = run; run += x; }
+    }
+  __syncthreads();
+  u64 run = s_part[threadIdx.x];
+  for (int i = b; i < b+per && i < n; i++)
+    { u64 x = in[i]; out[i] = run; if (cur) cur[i] = run; run += x; }
+  if (threadIdx.x == blockDim.x-1) out[n] = run;
+}
+
+/* three-phase exclusive scan of u32 -> u64 for large n (chunk = 2048 per CTA, 256 threads x 8) */
+#define LS_CHUNK 2048
+__global__ void __launch_bounds__(256) k_lscan_reduce(const u32 *in, long long n, u64 *bsum)
+{ __shared__ u64 s_w[8];
+  long long base = (long long) blockIdx.x * LS_CHUNK;
+  u64 sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    { long long g = base + threadIdx.x*8 + i;
+      if (g < n) sum += in[g];
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu,sum,o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { u64 t = 0;
+      for (int i = 0; i < 8; i++) t += s_w[i];
+      bsum[blockIdx.x] = t;
+    }
+}
+__global__ void k_lscan_top(u64 *bsum, long long nb, u64 *total)
+{ /* single CTA, sequential over chunks of blockDim */
+  __shared__ u64 s_part[1024];
+  __shared__ u64 s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long b0 = 0; b0 < nb; b0 += blockDim.x)
+    { long long g = b0 + threadIdx.x;
+      u64 x = (g < nb) ? bsum[g] : 0;
+      s_part[threadIdx.x] = x;
+      __syncthreads();
+      /* Hillis-Steele inclusive scan */
+      for (int o = 1; o < (int) blockDim.x; o <<= 1)
+        { u64 y = (threadIdx.x >= (unsigned) o) ? s_part[threadIdx.x-o] : 0;
+          __syncthreads();
+          s_part[threadIdx.x] += y;
+          __syncthreads();
+        }
+      u64 incl = s_part[threadIdx.x];
+      u64 carry = s_carry;
+      if (g < nb) bsum[g] = carry + incl - x;
+      __syncthreads();
+      if (threadIdx.x == blockDim.x-1) s_carry = carry + incl;
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void __launch_bounds__(256) k_lscan_apply(const u32 *in, long long n, const u64 *bsum, u64 *out)
+{ __shared__ u64 s_w[8];
+  long long base = (long long) blockIdx.x * LS_CHUNK;
+  u32 x[8];
+  u64 sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    { long long g = base + threadIdx.x*8 + i;
+      x[i] = (g < n) ? in[g] : 0;
+      sum += x[i];
+    }
+  u64 incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    { u64 y = __shfl_up_sync(0xffffffffu,incl,o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  u64 woff = 0;
+  for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_w[i];
+  u64 run = bsum[blockIdx.x] + woff + incl - sum;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    { long long g = base + threadIdx.x*8 + i;
+      if (g < n) out[g] = run;
+      run += x[i];
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_refine: one CTA per level-1 bucket (persistent, ticketed).  MSD pass on bits [pos, pos+nbits):
+ *  histogram in smem, block scan, scatter with smem cursors (no global atomics).  Writes the child
+ *  start offsets off2[(b << nbits) + d].                                                            */
+
+#define REF_TPB 512
+
+template<int NW>
+__global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ src, Key<NW> *__restrict__ dst,
+                                                    const u64 *off1, int nb1, int pos, int nbits,
+                                                    u64 *off2, u32 *ticket)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_cnt = s_dyn;                 /* [2^nbits] */
+  __shared__ u32 s_warp[REF_TPB/32];
+  __shared__ int s_b;
+  const int nd = 1 << nbits;
+
+  for (;;)
+    { if (threadIdx.x == 0) s_b = (int) atomicAdd(ticket,1u);
+      __syncthreads();
+      const int b = s_b;
+      if (b >= nb1) break;
+      const u64 start = off1[b];
+      const u64 n = off1[b+1] - start;
+      for (int i = threadIdx.x; i < nd; i += REF_TPB) s_cnt[i] = 0;
+      __syncthreads();
+      const Key<NW> *in = src + start;
+      for (u64 i0 = 0; i0 < n; i0 += REF_TPB*4)
+        { Key<NW> r[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            { u64 i = i0 + u*REF_TPB + threadIdx.x;
+              if (i < n) r[u] = in[i];
+            }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            { u64 i = i0 + u*REF_TPB + threadIdx.x;
+              if (i < n) atomicAdd(&s_cnt[key_digit<NW>(r[u],pos,nbits)],1u);
+            }
+        }
+      __syncthreads();
+      /* block exclusive scan of s_cnt (nd <= 4096 -> <= 8 per thread) */
+      { const int per = (nd + REF_TPB - 1) / REF_TPB;
+        const int b0 = threadIdx.x * per;
+        u32 sum = 0;
+        for (int i = b0; i < b0+per && i < nd; i++) sum += s_cnt[i];
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+          { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+            if ((threadIdx.x & 31) >= o) incl += y;
+          }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u32 woff = 0;
+        for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_warp[i];
+        u32 run = woff + incl - sum;
+        for (int i = b0; i < b0+per && i < nd; i++)
+          { u32 c = s_cnt[i];
+            s_cnt[i] = run;
+            off2[((u64) b << nbits) + i] = start + run;
+            run += c;
+          }
+      }
+      __syncthreads();
+      Key<NW> *out = dst + start;
+      for (u64 i0 = 0; i0 < n; i0 += REF_TPB*4)
+        { Key<NW> r[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            { u64 i = i0 + u*REF_TPB + threadIdx.x;
+              if (i < n) r[u] = in[i];
+            }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            { u64 i = i0 + u*REF_TPB + threadIdx.x;
+              if (i < n)
+                { u32 ps = atomicAdd(&s_cnt[key_digit<NW>(r[u],pos,nbits)],1u);
+                  out[ps] = r[u];
+                }
+            }
+        }
+      if (b == nb1-1 && threadIdx.x == 0) off2[(u64) nb1 << nbits] = off1[nb1];
+      __syncthreads();
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  Tile-parallel histogram / partition of ONE flat record array on its top `nbits` bits (level 1 when
+ *  the input is records rather than reads: the multi-GPU path after the exchange).                   */
+
+#define TP_TPB 256
+#define TP_RPT 16
+#define TP_TILE (TP_TPB*TP_RPT)
+
+template<int NW, bool SCATTER>
+__global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__ src, Key<NW> *__restrict__ dst,
+                                                     u64 n, int nbits, u64 *hist)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_cnt = s_dyn;
+  const int nd = 1 << nbits;
+  u64 *s_base = (u64 *) (s_cnt + nd + (nd & 1));
+  for (int i = threadIdx.x; i < nd; i += TP_TPB) s_cnt[i] = 0;
+  __syncthreads();
+  const u64 t0 = (u64) blockIdx.x * TP_TILE;
+  Key<NW> r[TP_RPT];
+  u32 rk[TP_RPT/2];
+#pragma unroll
+  for (int u = 0; u < TP_RPT/2; u++) rk[u] = 0;
+#pragma unroll
+  for (int u = 0; u < TP_RPT; u++)
+    { u64 i = t0 + u*TP_TPB + threadIdx.x;
+      if (i < n) r[u] = src[i];
+    }
+#pragma unroll
+  for (int u = 0; u < TP_RPT; u++)
+    { u64 i = t0 + u*TP_TPB + threadIdx.x;
+      if (i < n)
+        { u32 rr = atomicAdd(&s_cnt[nbits ? key_digit<NW>(r[u],0,nbits) : 0u],1u);
+          rk[u>>1] |= rr << (16*(u&1));
+        }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nd; i += TP_TPB)
+    { u32 c = s_cnt[i];
+      if (SCATTER) s_base[i] = c ? atomicAdd(hist+i,(u64) c) : 0ull;
+      else if (c) atomicAdd(hist+i,(u64) c);
+    }
+  if (!SCATTER) return;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < TP_RPT; u++)
+    { u64 i = t0 + u*TP_TPB + threadIdx.x;
+      if (i < n)
+        { u32 d = nbits ? key_digit<NW>(r[u],0,nbits) : 0u;
+          dst[s_base[d] + ((rk[u>>1] >> (16*(u&1))) & 0xffffu)] = r[u];
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_groups: gstart[g] = smallest fine-bucket start >= g*T  (so group g = [gstart[g], gstart[g+1]))  */
+
+__global__ void k_fill_u64(u64 *a, long long n, const u64 *value)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = *value;
+}
+
+__global__ void k_groups(const u64 *off, long long m /* # of buckets; off[m] = N */, u32 T, u64 *gstart, long long gmax)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > m) return;
+  u64 s = off[i];
+  long long glo = (i == 0) ? 0 : (long long) (off[i-1] / T) + 1;
+  long long ghi = (long long) (s / T);
+  if (i == 0) glo = 0;
+  for (long long g = glo; g <= ghi && g <= gmax; g++)
+    gstart[g] = s;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_sortcount: one CTA per work item [start, end) of <= cap records.                               */
+
+#define SC_TPB 256
+#define SC_EMPTY 0xffffffffu
+#define SC_PAD   0xffffffffffffffffull
+#define SC_SMALLHIST 256
+
+#define ITEM_UNIFORM 1u      /* every record of the item holds the same key                  */
+#define ITEM_ALTBUF  2u      /* item lives in the alternate buffer (input/staging swapped)    */
+
+struct SortCountParams
+  { const void *in0;  void *stage0;      /* default: read in0, stage into stage0              */
+    const void *in1;  void *stage1;      /* ITEM_ALTBUF: read in1, stage into stage1          */
+    u32        *stage_cnt;               /* count of staged entry, indexed like the stage     */
+    const u64  *starts; const u64 *ends; /* item record ranges                                */
+    const u32  *flags;                   /* per item, may be NULL                             */
+    u32        *e_all;                   /* out: # distinct keys of the item                  */
+    u32        *e_pass;                  /* out: # of them with count >= cutoff               */
+    u64        *g_hist;                  /* [32768]                                           */
+    u64        *g_maxinst;
+    u64        *g_ndistinct;
+    u32        *ovf_cnt; u32 *ovf_list; u32 ovf_cap;
+    u32         cap;                     /* C                                                 */
+    u32         tab_off, srt_off;        /* byte offsets of the hash table / sort array in smem */
+    u32         cutoff;
+    long long   nitems;
+  };
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{ asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_LOOP:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra WAIT_DONE;\n\t"
+    "bra WAIT_LOOP;\n\t"
+    "WAIT_DONE:\n\t}"
+    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template<int NW> __device__ __forceinline__ u32 key_hash(const Key<NW> &a)
+{ u64 h = a.w[0] * 0x9E3779B97F4A7C15ull;
+  if (NW > 1) h ^= a.w[NW > 1 ? 1 : 0] * 0xC2B2AE3D27D4EB4Full;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  return (u32) (h >> 32);
+}
+
+template<int NW>
+__global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
+{ extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ u64 s_bar;
+  __shared__ u32 s_D, s_pass, s_or[2*NW];
+  __shared__ u32 s_hist[SC_SMALLHIST];
+
+  const long long g = blockIdx.x;
+  if (g >= p.nitems) return;
+  const u64 r0 = p.starts[g], r1 = p.ends[g];
+  const u64 n64 = r1 - r0;
+  const u32 fl = p.flags ? p.flags[g] : 0u;
+  const Key<NW> *in    = (const Key<NW> *) ((fl & ITEM_ALTBUF) ? p.in1 : p.in0);
+  Key<NW>       *stage = (Key<NW> *) ((fl & ITEM_ALTBUF) ? p.stage1 : p.stage0);
+
+  if (n64 == 0)
+    { if (threadIdx.x == 0) { p.e_all[g] = 0; p.e_pass[g] = 0; }
+      return;
+    }
+  if (fl & ITEM_UNIFORM)
+    { /* all n records equal: one entry, count n (saturating; MSDsort.c:498-504) */
+      if (threadIdx.x == 0)
+        { u32 c = (n64 >= 0x7fffull) ? 0x7fffu : (u32) n64;
+          stage[r0] = in[r0];
+          p.stage_cnt[r0] = c;
+          atomicAdd(p.g_hist + c,1ull);
+          if (n64 >= 0x7fffull) atomicAdd(p.g_maxinst,n64);
+          atomicAdd(p.g_ndistinct,1ull);
+          p.e_all[g] = 1;
+          p.e_pass[g] = (c >= p.cutoff) ? 1u : 0u;
+        }
+      return;
+    }
+  if (n64 > p.cap)
+    { if (threadIdx.x == 0)
+        { u32 s = atomicAdd(p.ovf_cnt,1u);
+          if (s < p.ovf_cap) p.ovf_list[s] = (u32) g;
+          p.e_all[g] = 0; p.e_pass[g] = 0;
+        }
+      return;
+    }
+  const u32 n = (u32) n64;
+
+  /* smem carve-up: records | hash table (2*pow2) | sort keys */
+  Key<NW> *rec   = (Key<NW> *) s_raw;
+  u32      H     = 128; while (H < n + (n >> 2) + 1) H <<= 1;     /* load <= 0.8 even if all keys differ */
+  u32     *table = (u32 *) (s_raw + p.tab_off);
+  u64     *srt   = (u64 *) (s_raw + p.srt_off);
+
+  /* TMA bulk load of the item (16-byte granules) */
+  const u64 a0 = (NW == 1) ? (r0 & ~1ull) : r0;
+  const u64 a1 = (NW == 1) ? ((r1 + 1) & ~1ull) : r1;
+  const u32 shift = (u32) (r0 - a0);
+  const u32 bytes = (u32) ((a1 - a0) * sizeof(Key<NW>));
+  if (threadIdx.x == 0)
+    { mbar_init(&s_bar,1);
+      s_D = 0; s_pass = 0;
+    }
+  if (threadIdx.x < 2*NW) s_or[threadIdx.x] = 0;
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += SC_TPB) s_hist[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { mbar_expect_tx(&s_bar,bytes);
+      tma_bulk_g2s(rec,in + a0,bytes,&s_bar);
+    }
+  for (u32 i = threadIdx.x; i < H; i += SC_TPB) table[i] = SC_EMPTY;
+  mbar_wait(&s_bar,0);
+  __syncthreads();
+  rec += shift;
+
+  /* hash count: table slot = (owner record index << 16) | multiplicity */
+  { const Key<NW> k0 = rec[0];
+    u32 orw[2*NW];
+#pragma unroll
+    for (int m = 0; m < 2*NW; m++) orw[m] = 0;
+    for (u32 i = threadIdx.x; i < n; i += SC_TPB)
+      { const Key<NW> key = rec[i];
+#pragma unroll
+        for (int m = 0; m < NW; m++)
+          { u64 x = key.w[m] ^ k0.w[m];
+            orw[2*m] |= (u32) (x >> 32); orw[2*m+1] |= (u32) x;
+          }
+        u32 h = key_hash<NW>(key) & (H-1);
+        for (;;)
+          { u32 cur = ((volatile u32 *) table)[h];
+            if (cur == SC_EMPTY)
+              { u32 old = atomicCAS(&table[h],SC_EMPTY,(i << 16) | 1u);
+                if (old == SC_EMPTY) break;
+                cur = old;
+              }
+            if (key_eq<NW>(rec[cur >> 16],key))
+              { atomicAdd(&table[h],1u);
+                break;
+              }
+            h = (h+1) & (H-1);
+          }
+      }
+#pragma unroll
+    for (int m = 0; m < 2*NW; m++)
+      { u32 x = __reduce_or_sync(0xffffffffu,orw[m]);
+        if ((threadIdx.x & 31) == 0 && x) atomicOr(&s_or[m],x);
+      }
+  }
+  __syncthreads();
+
+  /* common prefix length of the item's keys -> sort on the 32 bits that follow it */
+  int pc = 0;
+  { bool done = false;
+#pragma unroll
+    for (int m = 0; m < 2*NW; m++)
+      if (!done)
+        { u32 x = s_or[m];
+          if (x) { pc += __clz(x); done = true; }
+          else pc += 32;
+        }
+    if (pc > 64*NW - 32) pc = 64*NW - 32;
+  }
+
+  /* gather the distinct keys */
+  for (u32 s = threadIdx.x; s < H; s += SC_TPB)
+    { u32 v = table[s];
+      if (v != SC_EMPTY)
+        { u32 ps = atomicAdd(&s_D,1u);
+          u64 pre = key_bits64<NW>(rec[v >> 16],pc) >> 32;
+          srt[ps] = (pre << 32) | v;
+        }
+    }
+  __syncthreads();
+  const u32 D = s_D;
+  u32 D2 = 1; while (D2 < D) D2 <<= 1;
+  for (u32 i = D + threadIdx.x; i < D2; i += SC_TPB) srt[i] = SC_PAD;
+  __syncthreads();
+
+  /* bitonic sort of srt[0..D2) by (32-bit prefix, then full key) */
+  for (u32 kk = 2; kk <= D2; kk <<= 1)
+    for (u32 j = kk >> 1; j > 0; j >>= 1)
+      { for (u32 t = threadIdx.x; t < (D2 >> 1); t += SC_TPB)
+          { u32 i = ((t & ~(j-1)) << 1) | (t & (j-1));
+            u32 l = i | j;
+            u64 a = srt[i], b = srt[l];
+            bool up = ((i & kk) == 0);
+            bool gt;                                   /* a > b ? */
+            if ((a >> 32) != (b >> 32)) gt = (a >> 32) > (b >> 32);
+            else if (a == SC_PAD || b == SC_PAD) gt = (a == SC_PAD) && (b != SC_PAD);
+            else gt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
+            if (gt == up) { srt[i] = b; srt[l] = a; }
+          }
+        __syncthreads();
+      }
+
+  /* emit: staged (key,count), histogram */
+  u32 npass = 0;
+  for (u32 q = threadIdx.x; q < D; q += SC_TPB)
+    { u32 v = (u32) srt[q];
+      u32 c = v & 0xffffu;
+      stage[r0 + q] = rec[v >> 16];
+      p.stage_cnt[r0 + q] = c;
+      if (c < SC_SMALLHIST) atomicAdd(&s_hist[c],1u);
+      else atomicAdd(p.g_hist + c,1ull);          /* c <= cap < 32767: never saturates here */
+      npass += (c >= p.cutoff) ? 1u : 0u;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) npass += __shfl_xor_sync(0xffffffffu,npass,o);
+  if ((threadIdx.x & 31) == 0 && npass) atomicAdd(&s_pass,npass);
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += SC_TPB)
+    { u32 c = s_hist[i];
+      if (c) atomicAdd(p.g_hist + i,(u64) c);
+    }
+  if (threadIdx.x == 0)
+    { p.e_all[g] = D;
+      p.e_pass[g] = s_pass;
+      atomicAdd(p.g_ndistinct,(u64) D);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_autorefine: fallback for oversize items.  One CTA per segment: finds the common prefix length of the
+ *  segment's keys, then does one 8-bit MSD pass right after it, src -> dst (same offsets).  child[s*257+d]
+ *  receives the child start offsets (257th = end), pcl[s] the prefix length (>= 64*NW means "all equal").  */
+
+#define AR_TPB 512
+template<int NW>
+__global__ void __launch_bounds__(AR_TPB) k_autorefine(const void *buf0, void *buf1, const u64 *sstart, const u64 *send,
+                                                       const u32 *sflags, u64 *child, u32 *pcl)
+{ __shared__ u32 s_cnt[256];
+  __shared__ u32 s_or[2*NW];
+  const int s = blockIdx.x;
+  const u64 start = sstart[s], n = send[s] - start;
+  const bool alt = (sflags[s] & ITEM_ALTBUF) != 0;
+  const Key<NW> *in = (const Key<NW> *) (alt ? buf1 : buf0) + start;
+  Key<NW>      *out = (Key<NW> *) (alt ? (void *) buf0 : buf1) + start;
+  if (threadIdx.x < 256) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 2*NW) s_or[threadIdx.x] = 0;
+  __syncthreads();
+  const Key<NW> k0 = in[0];
+  u32 orw[2*NW];
+#pragma unroll
+  for (int m = 0; m < 2*NW; m++) orw[m] = 0;
+  for (u64 i = threadIdx.x; i < n; i += AR_TPB)
+    { Key<NW> key = in[i];
+#pragma unroll
+      for (int m = 0; m < NW; m++)
+        { u64 x = key.w[m] ^ k0.w[m];
+          orw[2*m] |= (u32) (x >> 32); orw[2*m+1] |= (u32) x;
+        }
+    }
+#pragma unroll
+  for (int m = 0; m < 2*NW; m++)
+    { u32 x = __reduce_or_sync(0xffffffffu,orw[m]);
+      if ((threadIdx.x & 31) == 0 && x) atomicOr(&s_or[m],x);
+    }
+  __syncthreads();
+  int pc = 0;
+  { bool done = false;
+#pragma unroll
+    for (int m = 0; m < 2*NW; m++)
+      if (!done)
+        { u32 x = s_or[m];
+          if (x) { pc += __clz(x); done = true; }
+          else pc += 32;
+        }
+  }
+  if (threadIdx.x == 0) pcl[s] = (u32) pc;
+  if (pc >= 64*NW)
+    { if (threadIdx.x == 0) { child[(u64) s*257] = start; child[(u64) s*257+256] = start + n; }
+      return;
+    }
+  for (u64 i = threadIdx.x; i < n; i += AR_TPB)
+    atomicAdd(&s_cnt[key_digit<NW>(in[i],pc,8)],1u);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { u32 run = 0;
+      for (int d = 0; d < 256; d++)
+        { u32 c = s_cnt[d];
+          s_cnt[d] = run;
+          child[(u64) s*257 + d] = start + run;
+          run += c;
+        }
+      child[(u64) s*257 + 256] = start + n;
+    }
+  __syncthreads();
+  for (u64 i = threadIdx.x; i < n; i += AR_TPB)
+    { Key<NW> key = in[i];
+      u32 ps = atomicAdd(&s_cnt[key_digit<NW>(key,pc,8)],1u);
+      out[ps] = key;
+    }
+}
+
+__global__ void k_suboff(u64 *out_off, const u32 *parent, const u64 *base, const u64 *poff, long long n)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out_off[i] = poff[parent[i]] + base[i];
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_compact: staged entries of every item -> table records [kbytes key][u16 LE count], count >= cutoff.
+ *  One warp per item, grid-stride.                                                                   */
+
+struct CompactParams
+  { const void *stage0; const void *stage1;
+    const u32  *stage_cnt;
+    const u64  *starts;
+    const u32  *flags;
+    const u32  *e_all;
+    const u64  *out_off;        /* per item: index of its first table record */
+    uint8_t    *out;
+    long long   nitems;
+    u32         cutoff;
+    int         kbytes;
+  };
+
+template<int NW>
+__global__ void __launch_bounds__(256) k_compact(CompactParams p)
+{ const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  const int tw = p.kbytes + 2;
+  for (long long g = (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < p.nitems; g += nwarps)
+    { const u32 D = p.e_all[g];
+      if (D == 0) continue;
+      const u32 fl = p.flags ? p.flags[g] : 0u;
+      const Key<NW> *stage = (const Key<NW> *) ((fl & ITEM_ALTBUF) ? p.stage1 : p.stage0) + p.starts[g];
+      const u32 *cnt = p.stage_cnt + p.starts[g];
+      u64 o = p.out_off[g];
+      for (u32 q0 = 0; q0 < D; q0 += 32)
+        { u32 q = q0 + lane;
+          u32 c = (q < D) ? cnt[q] : 0u;
+          bool keep = (q < D) && (c >= p.cutoff);
+          u32 m = __ballot_sync(0xffffffffu,keep);
+          if (keep)
+            { Key<NW> key = stage[q];
+              uint8_t *e = p.out + (o + __popc(m & ((1u << lane) - 1u))) * (u64) tw;
+              for (int b = 0; b < p.kbytes; b++)
+                e[b] = (uint8_t) (key.w[b >> 3] >> (56 - 8*(b & 7)));
+              e[p.kbytes]   = (uint8_t) (c & 0xffu);
+              e[p.kbytes+1] = (uint8_t) (c >> 8);
+            }
+          o += __popc(m);
+        }
+    }
+}
+
+}  // namespace fk

@@ -1,0 +1,204 @@
+"""ctypes binding of include/fastk_gpu.h.  Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libfastk_gpu.so")
+
+HIST_BINS = 32768
+NSTAGES = 8
+STAGES = ["pack", "scan_hist", "scan_scatter", "l1_hist_records", "refine", "sortcount", "compact", "profile"]
+PACK_PAD = 16
+
+
+class FkgpuError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("kmer", C.c_int32), ("do_table", C.c_int32), ("do_profile", C.c_int32),
+                ("bc_prefix", C.c_int32), ("device", C.c_int32), ("nthreads", C.c_int32),
+                ("reserve_bases", C.c_int64)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("kmer", C.c_int32), ("kmer_bytes", C.c_int32),
+                ("nbases", C.c_int64), ("nreads", C.c_int64), ("nkmers", C.c_int64), ("ndistinct", C.c_int64),
+                ("hist", C.POINTER(C.c_int64)), ("max_inst", C.c_int64),
+                ("ntable", C.c_int64), ("table", C.POINTER(C.c_uint8)), ("table_dev", C.c_void_p),
+                ("ms_pack", C.c_float), ("ms_count", C.c_float), ("ms_total", C.c_float)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libfastk_gpu.so and declare every prototype of include/fastk_gpu.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FkgpuError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    lib = C.CDLL(p)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.fkgpu_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.fkgpu_create.restype = C.c_int
+    lib.fkgpu_destroy.argtypes = [vp]
+    lib.fkgpu_destroy.restype = None
+    lib.fkgpu_reset.argtypes = [vp]
+    lib.fkgpu_reset.restype = C.c_int
+    lib.fkgpu_last_error.argtypes = []
+    lib.fkgpu_last_error.restype = C.c_char_p
+    lib.fkgpu_device_count.argtypes = []
+    lib.fkgpu_device_count.restype = C.c_int
+    lib.fkgpu_ingest.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(i32), i32, i32]
+    lib.fkgpu_ingest.restype = C.c_int
+    lib.fkgpu_finish.argtypes = [vp, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_finish.restype = C.c_int
+    lib.fkgpu_profiles.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(i64)), C.POINTER(C.POINTER(C.c_uint16))]
+    lib.fkgpu_profiles.restype = C.c_int
+    lib.fkgpu_packed_words.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
+    lib.fkgpu_packed_words.restype = None
+    lib.fkgpu_pack_ascii_dev.argtypes = [vp, vp, i64, vp, vp]
+    lib.fkgpu_pack_ascii_dev.restype = C.c_int
+    lib.fkgpu_count_packed.argtypes = [vp, vp, vp, i64, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_count_packed.restype = C.c_int
+    lib.fkgpu_record_bytes.argtypes = [C.c_int]
+    lib.fkgpu_record_bytes.restype = C.c_int
+    lib.fkgpu_prefix_hist.argtypes = [vp, vp, vp, i64, C.c_int, vp]
+    lib.fkgpu_prefix_hist.restype = C.c_int
+    lib.fkgpu_scatter_prefix.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, i64, vp]
+    lib.fkgpu_scatter_prefix.restype = C.c_int
+    lib.fkgpu_count_records.argtypes = [vp, vp, i64, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_count_records.restype = C.c_int
+    lib.fkgpu_launch_count.argtypes = [vp]
+    lib.fkgpu_launch_count.restype = i64
+    lib.fkgpu_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    lib.fkgpu_stage_times.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
+           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
+           "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
+           "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_stage_times"]
+
+
+class FkResult:
+    """Host-side copy of an fkgpu_result (numpy arrays own their data)."""
+
+    def __init__(self, r, copy_table=True):
+        self.kmer = r.kmer
+        self.kmer_bytes = r.kmer_bytes
+        self.nbases, self.nreads = r.nbases, r.nreads
+        self.nkmers, self.ndistinct = r.nkmers, r.ndistinct
+        self.max_inst = r.max_inst
+        self.hist = np.ctypeslib.as_array(r.hist, shape=(HIST_BINS,)).copy()
+        self.ntable = r.ntable
+        self.table_dev = r.table_dev
+        tw = r.kmer_bytes + 2
+        if copy_table and r.ntable > 0 and bool(r.table):
+            self.table = np.ctypeslib.as_array(r.table, shape=(r.ntable * tw,)).copy().reshape(r.ntable, tw)
+        else:
+            self.table = None
+        self.ms_pack, self.ms_count, self.ms_total = r.ms_pack, r.ms_count, r.ms_total
+
+
+class FastKGPU:
+    """One context = one GPU.  Mirrors the stages the reference's driver sequences (FastK.c:498-540):
+    ingest() <-> Distribute_Block, finish() <-> Sorting, profiles() <-> Merge_Profiles."""
+
+    def __init__(self, k=40, table_cutoff=0, profile=False, bc_prefix=0, device=0, nthreads=1, reserve_bases=0):
+        self.lib = load_library()
+        cfg = _Config(k, table_cutoff, 1 if profile else 0, bc_prefix, device, nthreads, reserve_bases)
+        h = C.c_void_p()
+        rc = self.lib.fkgpu_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise FkgpuError(f"fkgpu_create -> {rc}: {self.lib.fkgpu_last_error().decode()}")
+        self.h = h
+        self.k = k
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise FkgpuError(f"{what} -> {rc}: {self.lib.fkgpu_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fkgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._chk(self.lib.fkgpu_reset(self.h), "fkgpu_reset")
+
+    def ingest(self, bases: bytes, boff, tid=0, rem=0):
+        """bases/boff exactly as in a DATA_BLOCK (FastK.h:87-98)."""
+        boff = np.ascontiguousarray(boff, dtype=np.int32)
+        n = len(boff) - 1
+        self._chk(self.lib.fkgpu_ingest(self.h, tid, bases, boff.ctypes.data_as(C.POINTER(C.c_int32)), n, rem),
+                  "fkgpu_ingest")
+
+    def ingest_ptr(self, bases_ptr, boff_ptr, nreads, tid=0, rem=0):
+        self._chk(self.lib.fkgpu_ingest(self.h, tid, C.cast(bases_ptr, C.c_char_p),
+                                        C.cast(boff_ptr, C.POINTER(C.c_int32)), nreads, rem), "fkgpu_ingest")
+
+    def finish(self, fetch_table=True, copy_table=True):
+        r = _Result()
+        self._chk(self.lib.fkgpu_finish(self.h, 1 if fetch_table else 0, C.byref(r)), "fkgpu_finish")
+        return FkResult(r, copy_table)
+
+    def packed_words(self, npos):
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.fkgpu_packed_words(npos, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def pack_ascii_dev(self, d_ascii_ptr, npos, d_seq_ptr, d_val_ptr):
+        self._chk(self.lib.fkgpu_pack_ascii_dev(self.h, d_ascii_ptr, npos, d_seq_ptr, d_val_ptr), "fkgpu_pack_ascii_dev")
+
+    def count_packed(self, d_seq_ptr, d_val_ptr, npos, fetch_table=False, copy_table=True):
+        r = _Result()
+        self._chk(self.lib.fkgpu_count_packed(self.h, d_seq_ptr, d_val_ptr, npos, 1 if fetch_table else 0, C.byref(r)),
+                  "fkgpu_count_packed")
+        return FkResult(r, copy_table)
+
+    def prefix_hist(self, d_seq_ptr, d_val_ptr, npos, bits, d_hist_ptr):
+        self._chk(self.lib.fkgpu_prefix_hist(self.h, d_seq_ptr, d_val_ptr, npos, bits, d_hist_ptr), "fkgpu_prefix_hist")
+
+    def scatter_prefix(self, d_seq_ptr, d_val_ptr, npos, bits, d_hist_ptr, d_rec_ptr, cap, d_off_ptr):
+        self._chk(self.lib.fkgpu_scatter_prefix(self.h, d_seq_ptr, d_val_ptr, npos, bits, d_hist_ptr, d_rec_ptr, cap,
+                                                d_off_ptr), "fkgpu_scatter_prefix")
+
+    def count_records(self, d_rec_ptr, n, fetch_table=False, copy_table=True):
+        r = _Result()
+        self._chk(self.lib.fkgpu_count_records(self.h, d_rec_ptr, n, 1 if fetch_table else 0, C.byref(r)),
+                  "fkgpu_count_records")
+        return FkResult(r, copy_table)
+
+    def launch_count(self):
+        return int(self.lib.fkgpu_launch_count(self.h))
+
+    def stage_times(self):
+        ms = (C.c_float * NSTAGES)()
+        by = (C.c_double * NSTAGES)()
+        self._chk(self.lib.fkgpu_stage_times(self.h, ms, by), "fkgpu_stage_times")
+        return {STAGES[i]: float(ms[i]) for i in range(NSTAGES)}
+
+    def profiles(self):
+        n = C.c_int64()
+        off = C.POINTER(C.c_int64)()
+        prof = C.POINTER(C.c_uint16)()
+        self._chk(self.lib.fkgpu_profiles(self.h, C.byref(n), C.byref(off), C.byref(prof)), "fkgpu_profiles")
+        offs = np.ctypeslib.as_array(off, shape=(n.value + 1,)).copy()
+        tot = int(offs[-1])
+        p = np.ctypeslib.as_array(prof, shape=(max(tot, 1),))[:tot].copy()
+        return offs, p

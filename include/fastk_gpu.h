@@ -1,0 +1,155 @@
+/*  fastk_gpu.h -- C ABI of libfastk_gpu.so, the B200 (sm_100a) replacement for FastK's k-mer counting
+ *  hot path.  Plain C: opaque handle, plain pointers and sizes, no torch / C++ types.
+ *
+ *  What it replaces in the reference (paths relative to the FastK source tree):
+ *     split.c    Distribute_Block / Split_Kmers   (split.c:1016-1393, 1407-1713)   -> fkgpu_ingest
+ *     count.c    Sorting                          (count.c:1202-1914)              -> fkgpu_finish
+ *     MSDsort.c  Supermer_Sort / Weighted_Kmer_Sort (MSDsort.c:458-544)            -> kernels behind fkgpu_finish
+ *     LSDsort.c  LSD_Sort                         (LSDsort.c:115-271)              -> kernels behind fkgpu_finish
+ *     merge.c    Merge_Profiles                   (merge.c:761-1006)               -> fkgpu_profiles
+ *  What stays on the host and calls this library: io.c (Scan_All_Input -> Distribute_Block callback,
+ *  io.c:2659-2699), table.c (Merge_Tables consumes [KMER_BYTES key][u16 count] runs, table.c:382-394),
+ *  libfastk.c (file readers) and the FastK.c driver.  INTEGRATION.md shows the shim.
+ *
+ *  Error convention: every entry point returns 0 on success, a negative FKGPU_E_* code otherwise;
+ *  fkgpu_last_error() gives the message.  The reference's convention (message on stderr, then
+ *  Clean_Exit(1), FastK.c:181-221) is applied by the host shim, not in here.
+ *
+ *  There is NO CPU fallback: without a CUDA device fkgpu_create fails with FKGPU_E_NODEVICE.
+ */
+#ifndef FASTK_GPU_H
+#define FASTK_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FKGPU_OK             0
+#define FKGPU_E_NODEVICE    -1    /* no CUDA device / driver                                  */
+#define FKGPU_E_CUDA        -2    /* a CUDA runtime call or kernel failed                     */
+#define FKGPU_E_ARG         -3    /* bad argument (k out of range, NULL pointer, bad tid ...)  */
+#define FKGPU_E_NOMEM       -4    /* host or device allocation failed                         */
+#define FKGPU_E_STATE       -5    /* call out of order (e.g. ingest after finish)             */
+#define FKGPU_E_UNSUPPORTED -6    /* k > FKGPU_MAX_K                                          */
+
+#define FKGPU_MAX_K        64     /* packed key = 1 or 2 64-bit words                         */
+#define FKGPU_HIST_BINS    32768  /* bins 1..32767 used; 32767 = ">= 32767" (MSDsort.c:498)   */
+
+typedef struct fkgpu_ctx fkgpu_ctx;
+
+/*  Mirrors the option globals the replaced stages read (FastK.h:34-83). */
+typedef struct
+  { int32_t  kmer;          /* KMER        -k          1 .. FKGPU_MAX_K                         */
+    int32_t  do_table;      /* DO_TABLE    -t<cutoff>  0 = no table, else emit counts >= cutoff */
+    int32_t  do_profile;    /* DO_PROFILE  -p          keep reads on the device for fkgpu_profiles */
+    int32_t  bc_prefix;     /* BC_PREFIX   -bc<n>      ignore first n bases of every read       */
+    int32_t  device;        /* CUDA device ordinal                                             */
+    int32_t  nthreads;      /* # of distinct tid values that will call fkgpu_ingest (ITHREADS)  */
+    int64_t  reserve_bases; /* hint: total bases expected (0 = grow as needed)                 */
+  } fkgpu_config;
+
+/*  Result of fkgpu_finish / fkgpu_count_packed.  All pointers are owned by the context and stay
+ *  valid until the next finish/reset/destroy.  table = ntable records of (kmer_bytes + 2) bytes:
+ *  [kmer_bytes big-endian 2-bit packed canonical k-mer, unused low bits 0][u16 LE count saturated at 32767],
+ *  strictly increasing by key -- exactly the record stream table.c:382-394 reads from its L-files.      */
+typedef struct
+  { int32_t        kmer;
+    int32_t        kmer_bytes;        /* (2k+7)>>3, FastK.c:419                                  */
+    int64_t        nbases;            /* bases ingested (terminators excluded)                   */
+    int64_t        nreads;            /* reads ingested                                          */
+    int64_t        nkmers;            /* valid k-mer instances counted                           */
+    int64_t        ndistinct;         /* distinct canonical k-mers                               */
+    const int64_t *hist;              /* host, [FKGPU_HIST_BINS]; hist[c] = # distinct k-mers with count c */
+    int64_t        max_inst;          /* sum of true counts of k-mers with count >= 32767        */
+    int64_t        ntable;            /* # of table records (count >= do_table); 0 if !do_table  */
+    const uint8_t *table;             /* host (pinned) copy of the table records, NULL if !do_table or not fetched */
+    const uint8_t *table_dev;         /* device copy of the same records                         */
+    float          ms_pack;           /* device time of the stages, CUDA events, for -v reporting */
+    float          ms_count;
+    float          ms_total;
+  } fkgpu_result;
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+
+int  fkgpu_create (const fkgpu_config *cfg, fkgpu_ctx **out);
+void fkgpu_destroy(fkgpu_ctx *ctx);
+int  fkgpu_reset  (fkgpu_ctx *ctx);             /* forget ingested reads and results, keep buffers */
+const char *fkgpu_last_error(void);              /* thread-local message of the last failing call  */
+int  fkgpu_device_count(void);                   /* # of CUDA devices, 0 if none                   */
+
+/* ---- host-buffer path: what the reference's io.c callback binds to --------------------------------
+ *  fkgpu_ingest replaces  void Distribute_Block(DATA_BLOCK *block, int tid)  (FastK.h:123):
+ *    bases  = block->bases   concatenation of 0-terminated reads (FastK.h:92)
+ *    boff   = block->boff    read i is bases+boff[i], boff[nreads] = total bytes (FastK.h:93)
+ *    nreads = block->nreads
+ *    rem    = block->rem     > 0: the last read continues in this tid's next block with a k-1 overlap
+ *  Thread-safe for distinct tid; the block is copied before return (io.c reuses it immediately,
+ *  io.c:552,565).  Reads of one tid keep their order; global read order is tid-major.             */
+int  fkgpu_ingest(fkgpu_ctx *ctx, int tid, const char *bases, const int32_t *boff, int32_t nreads, int32_t rem);
+
+/*  fkgpu_finish replaces  void Sorting(char *path, char *root)  (count.c:1202): uploads what was
+ *  ingested, runs the device pipeline, fills res.  fetch_table != 0 also copies the table to
+ *  pinned host memory (res->table).                                                               */
+int  fkgpu_finish(fkgpu_ctx *ctx, int fetch_table, fkgpu_result *res);
+
+/*  Count profiles (replaces count.c:817-1181 + merge.c:761-1006).  Valid after fkgpu_finish when
+ *  do_profile was set.  For global read r (tid-major order), prof[off[r] .. off[r+1]) are the
+ *  counts (saturated at 32767, 0 where the k-mer covers a non-acgt base) at each k-mer start of
+ *  the read after its bc prefix; a read shorter than k has an empty range.  Pointers are pinned
+ *  host memory owned by the context.                                                             */
+int  fkgpu_profiles(fkgpu_ctx *ctx, int64_t *nreads, const int64_t **off, const uint16_t **prof);
+
+/* ---- device-resident path (bench "value", multi-GPU stages) --------------------------------------
+ *  Packed read stream: position i of the concatenated reads (one terminator position between reads)
+ *    seq word i>>4 , bits 31-2*(i&15) .. 30-2*(i&15)   = base code a,c,g,t = 0..3
+ *    val word i>>5 , bit  31-(i&31)                    = 1 iff position i holds an acgt base
+ *  Both arrays must be followed by FKGPU_PACK_PAD zero words.                                      */
+#define FKGPU_PACK_PAD 16
+
+/*  ASCII (device or host memory) -> packed stream on the device; d_seq/d_val sized by fkgpu_packed_words. */
+void fkgpu_packed_words(int64_t npos, int64_t *seq_words, int64_t *val_words);
+int  fkgpu_pack_ascii_dev(fkgpu_ctx *ctx, const char *d_ascii, int64_t npos, uint32_t *d_seq, uint32_t *d_val);
+
+/*  Whole counting pipeline over a packed stream already resident in HBM.  */
+int  fkgpu_count_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                        int fetch_table, fkgpu_result *res);
+
+/*  Multi-GPU stages (one process per GPU; the exchange itself is done by the caller, e.g. NCCL
+ *  all-to-all via torch.distributed -- see fastk_b200/multigpu.py):
+ *   1. fkgpu_prefix_hist:   histogram of the top `bits` key bits of every valid canonical k-mer
+ *                           (d_hist: 2^bits uint64 on the device, overwritten).
+ *   2. fkgpu_scatter_prefix: writes every canonical k-mer as a 16-byte (k > 32) or 8-byte record,
+ *                           grouped by that prefix, into d_records (capacity cap_records); d_offsets
+ *                           (2^bits + 1 uint64, device) receives the group starts.
+ *   3. fkgpu_count_records: sort / count / histogram / table over an arbitrary record array (e.g. the
+ *                           records received from the peers).  Keys outside are not filtered.      */
+int  fkgpu_record_bytes(int kmer);
+int  fkgpu_prefix_hist(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                       int bits, uint64_t *d_hist);
+int  fkgpu_scatter_prefix(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                          int bits, const uint64_t *d_hist, void *d_records, int64_t cap_records,
+                          uint64_t *d_offsets);
+int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int fetch_table, fkgpu_result *res);
+
+/*  Instrumentation for bench.py: # of kernel launches issued by this context so far, and the
+ *  accumulated CUDA-event time / algorithmic bytes of the dominant kernel family (final sort+count). */
+int64_t fkgpu_launch_count(fkgpu_ctx *ctx);
+int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double *bytes /*[FKGPU_NSTAGES]*/);
+#define FKGPU_NSTAGES 8
+/* stage ids */
+#define FKGPU_ST_PACK      0
+#define FKGPU_ST_SCANHIST  1
+#define FKGPU_ST_SCATTER   2
+#define FKGPU_ST_L2HIST    3
+#define FKGPU_ST_L2PART    4
+#define FKGPU_ST_SORTCOUNT 5
+#define FKGPU_ST_COMPACT   6
+#define FKGPU_ST_PROFILE   7
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded reads.
+Bit-exact bar: histogram, max_inst, and the [key][count] table records must be identical."""
+import numpy as np
+import pytest
+
+from fastk_b200 import FastKGPU
+from fastk_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(reads, k, cutoff=1, bc=0, nthreads=1, block_bytes=1_000_000):
+    g = FastKGPU(k=k, table_cutoff=cutoff, bc_prefix=bc, nthreads=nthreads)
+    try:
+        for i, (bases, boff) in enumerate(synth.blocks(reads, max_bytes=block_bytes)):
+            g.ingest(bases, boff.astype(np.int32), tid=i % nthreads)
+        return g.finish(fetch_table=True)
+    finally:
+        g.close()
+
+
+def check(oracle_lib, reads, k, cutoff=1, bc=0, nthreads=1):
+    want = oracle_lib.count(reads, k, bc_prefix=bc, cutoff=cutoff)
+    got = run_gpu(reads, k, cutoff=cutoff, bc=bc, nthreads=nthreads)
+    assert got.nkmers == want["nkmers"]
+    assert got.ndistinct == want["ndistinct"]
+    assert got.max_inst == want["max_inst"]
+    assert np.array_equal(got.hist[1:], want["hist"][1:])
+    assert got.ntable == len(want["table"])
+    if got.ntable:
+        assert np.array_equal(got.table, want["table"])
+    return got
+
+
+@pytest.mark.parametrize("k", [40, 21, 63, 32, 33, 64, 7])
+def test_config1_1k_reads(oracle_lib, k):
+    genome = synth.random_genome(20_000, 11)
+    reads = synth.sample_reads(genome, 1000, 150, 0.005, 12)
+    check(oracle_lib, reads, k)
+
+
+def test_edge_cases(oracle_lib):
+    genome = synth.random_genome(5_000, 3)
+    reads = synth.sample_reads(genome, 300, 120, 0.01, 4, n_rate=0.01, lower_rate=0.3, len_jitter=100)
+    reads += [b"", b"A", b"ACGT" * 9 + b"ACG", b"N" * 200, b"acgtn" * 50, b"A" * 500, b"AC" * 300,
+              b"ACGTACGTAC" * 30, b"T" * 40, b"G" * 39]
+    check(oracle_lib, reads, 40)
+    check(oracle_lib, reads, 21, cutoff=2)
+    check(oracle_lib, reads, 40, bc=10)
+
+
+def test_saturation_known_answer(oracle_lib):
+    """40 000 copies of a 45-mer + 3 copies of its first 42 bases + 32 767 copies of a 50-mer."""
+    rng = np.random.default_rng(5)
+    a = bytes(b"ACGT"[x] for x in rng.integers(0, 4, 45))
+    b = bytes(b"ACGT"[x] for x in rng.integers(0, 4, 50))
+    reads = [a] * 40000 + [a[:42]] * 3 + [b] * 32767
+    got = check(oracle_lib, reads, 40)
+    assert got.hist[32767] == 17
+    assert got.max_inst == 3 * 40003 + 3 * 40000 + 11 * 32767
+    assert (got.table[:, -2].astype(int) | (got.table[:, -1].astype(int) << 8) == 32767).all()
+
+
+def test_medium_30x(oracle_lib):
+    genome = synth.random_genome(200_000, 21)
+    reads = synth.sample_reads(genome, 40_000, 150, 0.002, 22)
+    check(oracle_lib, reads, 40, nthreads=4)
+    check(oracle_lib, reads, 21, cutoff=4, nthreads=3)
+
+
+def test_long_reads_hifi_like(oracle_lib):
+    genome = synth.random_genome(300_000, 31)
+    reads = synth.sample_reads(genome, 400, 15_000, 0.001, 32)
+    check(oracle_lib, reads, 40)
+    check(oracle_lib, reads, 63)
+
+
+def test_repeats_force_refinement(oracle_lib):
+    """Heavy repeats: oversize work groups take the host-driven MSD refinement path."""
+    rng = np.random.default_rng(9)
+    unit = bytes(b"ACGT"[x] for x in rng.integers(0, 4, 300))
+    reads = [unit * 3] * 3000 + synth.sample_reads(synth.random_genome(50_000, 1), 2000, 150, 0.01, 2)
+    check(oracle_lib, reads, 40)
+    check(oracle_lib, reads, 25)
