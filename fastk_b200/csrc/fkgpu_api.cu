@@ -94,7 +94,7 @@ struct fkgpu_ctx
     bool         finished = false;
 
     /* device working set */
-    DevBuf seq, val, bufA, bufB, scnt, hist1, off1, cur1, off2, gstart, eall, epass, poff, bsum, ghist, misc, table;
+    DevBuf ctah, ctao, seq, val, bufA, bufB, scnt, hist1, off1, cur1, off2, gstart, eall, epass, poff, bsum, ghist, misc, table;
     DevBuf segs, child, pcl, sub_s, sub_e, sub_f, sub_ea, sub_ep, sub_off, sub_par, sub_base, rstart_d, prof_d;
     PinBuf h_table, h_misc, h_prof, h_poff;
     int64_t h_hist[FKGPU_HIST_BINS];
@@ -160,7 +160,7 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
     { if (t.pin) cudaFreeHost(t.pin);
       if (t.done) cudaEventDestroy(t.done);
     }
-  DevBuf *bufs[] = { &c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
+  DevBuf *bufs[] = { &c->ctah,&c->ctao,&c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
                      &c->eall,&c->epass,&c->poff,&c->bsum,&c->ghist,&c->misc,&c->table,&c->segs,&c->child,&c->pcl,
                      &c->sub_s,&c->sub_e,&c->sub_f,&c->sub_ea,&c->sub_ep,&c->sub_off,&c->sub_par,&c->sub_base,
                      &c->rstart_d,&c->prof_d };
@@ -296,10 +296,10 @@ static int ilog2_ceil(unsigned long long x) { int l = 0; while ((1ull << l) < x)
 #define KCHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
     return set_err(FKGPU_E_CUDA,"kernel launch failed at %s:%d: %s",__FILE__,__LINE__,cudaGetErrorString(e_)); c->launches++; } while (0)
 
-static const u32 SC_CAP = 3072;      /* records one k_sortcount CTA can hold           */
-static const u32 SC_T   = 2048;      /* group packing target                           */
+static const u32 SC_CAP = 2048;      /* records one k_sortcount CTA can hold           */
+static const u32 SC_T   = 1024;      /* group packing target (fine buckets up to SC_CAP-SC_T+1 never overflow) */
 
-struct ScLayout { u32 tab_off, srt_off, total; };
+struct ScLayout { u32 tab_off, srt_off, srt2_off, total; };
 static ScLayout sc_layout(int NW)
 { ScLayout L;
   u32 recb = (SC_CAP + 2) * 8 * NW;
@@ -308,6 +308,7 @@ static ScLayout sc_layout(int NW)
   L.tab_off = (recb + 127) & ~127u;
   L.srt_off = L.tab_off + hmax*4;
   L.total   = L.srt_off + dmax*8;
+  L.srt2_off = dmax/2;
   return L;
 }
 
@@ -339,7 +340,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
     { if (c->off2.ensure((size_t) (m + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
       stage_begin(c,FKGPU_ST_L2PART);
       int grid = std::min(nb1,c->sms * 2);
-      size_t sm = (size_t) (1 << P2) * 4;
+      size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(K) + (size_t) (1 << P2) * 4;
       CU(cudaFuncSetAttribute(k_refine<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
       k_refine<NW><<<grid,REF_TPB,sm,c->st>>>(X,Y,(const u64 *) c->off1.p,nb1,P1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
       stage_end(c,FKGPU_ST_L2PART);
@@ -365,7 +366,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   if (c->segs.ensure((size_t) gmax * 4)) return set_err(FKGPU_E_NOMEM,"out of device memory (overflow list)");
   sp.ovf_cnt = &d_misc->ovf_cnt; sp.ovf_list = (u32 *) c->segs.p; sp.ovf_cap = (u32) std::min<long long>(gmax,0x7fffffffll);
   sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax;
-  sp.tab_off = L.tab_off; sp.srt_off = L.srt_off;
+  sp.tab_off = L.tab_off; sp.srt_off = L.srt_off; sp.srt2_off = L.srt2_off;
   CU(cudaFuncSetAttribute(k_sortcount<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) L.total));
   k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK();
   stage_end(c,FKGPU_ST_SORTCOUNT);
@@ -516,8 +517,10 @@ static void choose_levels(long long nub, int *P1, int *P2)
 { unsigned long long want = (unsigned long long) std::max<long long>(1,nub / 256);
   int P = ilog2_ceil(want);
   if (P > 23) P = 23;
-  *P1 = std::min(P,11);
-  *P2 = P - *P1;
+  int p1max = 11;
+  { const char *e = getenv("FKGPU_P1"); if (e) p1max = std::max(1,std::min(11,atoi(e))); }
+  *P1 = std::min(P,p1max);
+  *P2 = std::min(13,P - *P1);
 }
 
 static int prepare_common(fkgpu_ctx *c, long long nub, int P1)
@@ -546,6 +549,81 @@ static void collect_times(fkgpu_ctx *c, fkgpu_result *res)
   res->ms_count = tot - res->ms_pack;
 }
 
+
+/*  geometry of the persistent scan: the same (grid, tiles-per-CTA) must be used by HIST and SCATTER */
+struct ScanGeom { long long ntiles, tpc; int grid; size_t smh, sms; };
+static ScanGeom scan_geom(fkgpu_ctx *c, long long npos, int P1)
+{ ScanGeom g;
+  const int nb1 = 1 << P1;
+  g.ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  long long want = (long long) c->sms * 4;
+  g.grid = (int) std::max<long long>(1,std::min<long long>(g.ntiles,want));
+  g.tpc = (g.ntiles + g.grid - 1) / std::max(1,g.grid);
+  if (g.tpc < 1) g.tpc = 1;
+  g.grid = (int) std::max<long long>(1,(g.ntiles + g.tpc - 1) / g.tpc);
+  g.smh = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4;
+  g.sms = g.smh + (size_t) nb1 * 8;
+  return g;
+}
+
+static void fill_scan_params(fkgpu_ctx *c, ScanParams &sp, const u32 *d_seq, const u32 *d_val, long long npos, int P1, const ScanGeom &g)
+{ sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
+  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+  sp.k = c->cfg.kmer; sp.pbits = P1;
+  make_kmask(c->cfg.kmer,sp.kmask);
+  sp.ntiles = g.ntiles; sp.tpc = g.tpc;
+  sp.cta_hist = (u32 *) c->ctah.p; sp.cta_off = (const u64 *) c->ctao.p; sp.off1 = NULL; sp.out = NULL;
+}
+
+/*  reads -> per-bucket totals in d_total[2^P1] (u64).  Leaves the per-CTA offsets in c->ctao for the scatter. */
+template<int NW>
+static int scan_hist(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int P1, u64 *d_total)
+{ const int nb1 = 1 << P1;
+  ScanGeom g = scan_geom(c,npos,P1);
+  if (c->ctah.ensure((size_t) g.grid * nb1 * 4) || c->ctao.ensure((size_t) g.grid * nb1 * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (per-CTA histograms)");
+  ScanParams sp;
+  fill_scan_params(c,sp,d_seq,d_val,npos,P1,g);
+  if (g.ntiles == 0)
+    { CU(cudaMemsetAsync(d_total,0,(size_t) nb1 * 8,c->st));
+      return FKGPU_OK;
+    }
+  CU(cudaFuncSetAttribute(k_scan<NW,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) g.smh));
+  k_scan<NW,false><<<g.grid,SCAN_TPB,g.smh,c->st>>>(sp); KCHECK();
+  k_colscan<<<(nb1 + 127) / 128,128,0,c->st>>>((const u32 *) c->ctah.p,(u64 *) c->ctao.p,d_total,g.grid,nb1); KCHECK();
+  return FKGPU_OK;
+}
+
+template<int NW>
+static int scan_scatter(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int P1, const u64 *d_off1, void *d_out)
+{ ScanGeom g = scan_geom(c,npos,P1);
+  if (g.ntiles == 0) return FKGPU_OK;
+  ScanParams sp;
+  fill_scan_params(c,sp,d_seq,d_val,npos,P1,g);
+  sp.off1 = d_off1; sp.out = d_out;
+  const int nb1 = 1 << P1;
+  static int variant = -1;
+  if (variant < 0) { const char *e = getenv("FKGPU_SCAT"); variant = e ? atoi(e) : 1; }
+  if (variant == 2)
+    { CU(cudaFuncSetAttribute(k_scan<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) g.sms));
+      k_scan<NW,true><<<g.grid,SCAN_TPB,g.sms,c->st>>>(sp); KCHECK();
+    }
+  else
+    { if (c->cur1.ensure((size_t) (nb1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (cursors)");
+      CU(cudaMemcpyAsync(c->cur1.p,d_off1,(size_t) nb1 * 8,cudaMemcpyDeviceToDevice,c->st));
+      sp.cursor = (u64 *) c->cur1.p;
+      if (variant == 1)
+        { CU(cudaFuncSetAttribute(k_scatter_tile<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) g.sms));
+          k_scatter_tile<NW><<<(unsigned) g.ntiles,SCAN_TPB,g.sms,c->st>>>(sp); KCHECK();
+        }
+      else
+        { size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW) * 4;
+          k_scatter_atomic<NW><<<(unsigned) g.ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
+        }
+    }
+  return FKGPU_OK;
+}
+
 template<int NW>
 static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res, bool own_total)
 { int P1, P2;
@@ -554,31 +632,16 @@ static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long
   if (rc) return rc;
   const int nb1 = 1 << P1;
 
-  ScanParams sp;
-  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
-  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
-  sp.k = c->cfg.kmer; sp.pbits = P1;
-  make_kmask(c->cfg.kmer,sp.kmask);
-  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
-  const size_t smh = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4;
-  const size_t sms = smh + (size_t) nb1 * 8;
-  CU(cudaFuncSetAttribute(k_scan<NW,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
-  CU(cudaFuncSetAttribute(k_scan<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-
   if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
-  if (ntiles > 0)
-    { stage_begin(c,FKGPU_ST_SCANHIST);
-      sp.hist = (u64 *) c->hist1.p; sp.out = NULL;
-      k_scan<NW,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); KCHECK();
-      stage_end(c,FKGPU_ST_SCANHIST);
-    }
-  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,nb1); KCHECK();
-  if (ntiles > 0)
-    { stage_begin(c,FKGPU_ST_SCATTER);
-      sp.hist = (u64 *) c->cur1.p; sp.out = c->bufA.p;
-      k_scan<NW,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); KCHECK();
-      stage_end(c,FKGPU_ST_SCATTER);
-    }
+  stage_begin(c,FKGPU_ST_SCANHIST);
+  rc = scan_hist<NW>(c,d_seq,d_val,npos,P1,(u64 *) c->hist1.p);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SCANHIST);
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) NULL,nb1); KCHECK();
+  stage_begin(c,FKGPU_ST_SCATTER);
+  rc = scan_scatter<NW>(c,d_seq,d_val,npos,P1,(const u64 *) c->off1.p,c->bufA.p);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SCATTER);
   rc = count_from_level1<NW>(c,npos,P1,P2,fetch_table,res);
   if (rc) return rc;
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
@@ -674,56 +737,28 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
 extern "C" int fkgpu_prefix_hist(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int bits, uint64_t *d_hist)
 { if (c == NULL || d_hist == NULL || bits < 0 || bits > 11) return set_err(FKGPU_E_ARG,"fkgpu_prefix_hist: bad argument");
   CU(cudaSetDevice(c->cfg.device));
-  const int nb1 = 1 << bits;
-  CU(cudaMemsetAsync(d_hist,0,(size_t) nb1 * 8,c->st));
-  ScanParams sp;
-  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
-  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
-  sp.k = c->cfg.kmer; sp.pbits = bits; sp.hist = (u64 *) d_hist; sp.out = NULL;
-  make_kmask(c->cfg.kmer,sp.kmask);
-  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
-  const size_t smh = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4;
-  if (ntiles > 0)
-    { if (c->NW == 1)
-        { CU(cudaFuncSetAttribute(k_scan<1,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
-          k_scan<1,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); }
-      else
-        { CU(cudaFuncSetAttribute(k_scan<2,false>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smh));
-          k_scan<2,false><<<(unsigned) ntiles,SCAN_TPB,smh,c->st>>>(sp); }
-      KCHECK();
-    }
+  int rc = (c->NW == 1) ? scan_hist<1>(c,d_seq,d_val,npos,bits,(u64 *) d_hist) : scan_hist<2>(c,d_seq,d_val,npos,bits,(u64 *) d_hist);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(c->st));
   return FKGPU_OK;
 }
 
+/*  must follow fkgpu_prefix_hist on the same (d_seq, d_val, npos, bits): it reuses the per-CTA regions computed there;
+ *  d_hist = this rank's own histogram as returned by fkgpu_prefix_hist.                                              */
 extern "C" int fkgpu_scatter_prefix(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int bits,
                                     const uint64_t *d_hist, void *d_records, int64_t cap_records, uint64_t *d_offsets)
 { if (c == NULL || d_hist == NULL || d_records == NULL || d_offsets == NULL || bits < 0 || bits > 11)
     return set_err(FKGPU_E_ARG,"fkgpu_scatter_prefix: bad argument");
   CU(cudaSetDevice(c->cfg.device));
   const int nb1 = 1 << bits;
-  if (c->cur1.ensure((size_t) (nb1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
-  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) c->cur1.p,nb1); KCHECK();
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) NULL,nb1); KCHECK();
   u64 tot;
   CU(cudaMemcpyAsync(&tot,d_offsets + nb1,8,cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
   if ((int64_t) tot > cap_records) return set_err(FKGPU_E_ARG,"fkgpu_scatter_prefix: %llu records exceed the capacity %lld",tot,(long long) cap_records);
-  ScanParams sp;
-  sp.seq = d_seq; sp.val = d_val; sp.npos = npos;
-  sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
-  sp.k = c->cfg.kmer; sp.pbits = bits; sp.hist = (u64 *) c->cur1.p; sp.out = d_records;
-  make_kmask(c->cfg.kmer,sp.kmask);
-  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
-  const size_t sms = (size_t) (SCAN_SEQW + SCAN_VALW + nb1 + (nb1 & 1)) * 4 + (size_t) nb1 * 8;
-  if (ntiles > 0)
-    { if (c->NW == 1)
-        { CU(cudaFuncSetAttribute(k_scan<1,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-          k_scan<1,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); }
-      else
-        { CU(cudaFuncSetAttribute(k_scan<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-          k_scan<2,true><<<(unsigned) ntiles,SCAN_TPB,sms,c->st>>>(sp); }
-      KCHECK();
-    }
+  int rc = (c->NW == 1) ? scan_scatter<1>(c,d_seq,d_val,npos,bits,(const u64 *) d_offsets,d_records)
+                        : scan_scatter<2>(c,d_seq,d_val,npos,bits,(const u64 *) d_offsets,d_records);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(c->st));
   return FKGPU_OK;
 }

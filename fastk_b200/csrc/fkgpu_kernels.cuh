@@ -106,7 +106,11 @@ struct ScanParams
     int        k;
     int        pbits;        /* P1                                             */
     u32        kmask[4];     /* mask of the 2k key bits over four 32-bit words */
-    u64       *hist;         /* [2^P1]  HIST: += ; SCATTER: running cursors    */
+    long long  ntiles, tpc;  /* # of tiles, tiles per CTA                      */
+    u32       *cta_hist;     /* HIST out: [grid][2^P1]                         */
+    const u64 *cta_off;      /* SCATTER in: [grid][2^P1] offset of the CTA's region inside each bucket */
+    const u64 *off1;         /* SCATTER in: bucket starts                      */
+    u64       *cursor;       /* scatter variants 1/3: running global cursors (init = bucket starts) */
     void      *out;          /* SCATTER: record buffer                         */
   };
 
@@ -180,60 +184,138 @@ __device__ __forceinline__ void scan_load_tile(const ScanParams &p, long long ti
     }
 }
 
+/*  Persistent: CTA c owns the contiguous tile range [c*tpc, (c+1)*tpc).  HIST accumulates its private
+ *  histogram in smem and stores it (no atomics); k_colscan turns the per-CTA histograms into per-CTA output
+ *  regions inside every bucket; SCATTER then needs only smem cursors: one pass, no global atomics.          */
 template<int NW, bool SCATTER>
 __global__ void __launch_bounds__(SCAN_TPB) k_scan(ScanParams p)
 { extern __shared__ u32 s_dyn[];
   u32 *s_seq  = s_dyn;
   u32 *s_val  = s_seq + SCAN_SEQW;
-  u32 *s_hist = s_val + SCAN_VALW;                 /* [2^P1]              */
+  u32 *s_hist = s_val + SCAN_VALW;                 /* [2^P1] counts                    */
   const int nb = 1 << p.pbits;
-  u64 *s_base = (u64 *) (s_hist + nb + (nb & 1));  /* [2^P1] SCATTER only */
+  u64 *s_base = (u64 *) (s_hist + nb + (nb & 1));  /* [2^P1] region starts, SCATTER only */
   constexpr int NW32 = 2*NW;
   const int sh = 32 - p.pbits;
+  const long long t0 = (long long) blockIdx.x * p.tpc;
+  long long t1 = t0 + p.tpc; if (t1 > p.ntiles) t1 = p.ntiles;
 
+  for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
+    { s_hist[i] = 0;
+      if (SCATTER) s_base[i] = p.off1[i] + p.cta_off[(u64) blockIdx.x * nb + i];
+    }
+  u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
+  Key<NW> *out = (Key<NW> *) p.out;
+
+  for (long long t = t0; t < t1; t++)
+    { __syncthreads();
+      scan_load_tile(p,t,s_seq,s_val);
+      __syncthreads();
+      Window w;
+      load_window(w,s_seq,s_val,threadIdx.x,p.k);
+      if (!SCATTER)
+        { auto fn = [&](int, const u32 *C) { atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u); };
+          KmerLoop<NW32,0>::run(w,km,fn);
+        }
+      else
+        { auto fb = [&](int, const u32 *C)
+            { u32 d = p.pbits ? (C[0] >> sh) : 0u;
+              u32 r = atomicAdd(&s_hist[d],1u);
+              Key<NW> key;
+#pragma unroll
+              for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
+              out[s_base[d] + r] = key;
+            };
+          KmerLoop<NW32,0>::run(w,km,fb);
+        }
+    }
+  if (!SCATTER)
+    { __syncthreads();
+      for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
+        p.cta_hist[(u64) blockIdx.x * nb + i] = s_hist[i];
+    }
+}
+
+/*  Scatter variant 1: one tile per CTA, two compute passes; pass A ranks the tile's k-mers in smem, one global
+ *  atomic per (tile, non-empty bucket) reserves a run at the bucket's shared frontier, pass B writes.          */
+template<int NW>
+__global__ void __launch_bounds__(SCAN_TPB) k_scatter_tile(ScanParams p)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_seq  = s_dyn;
+  u32 *s_val  = s_seq + SCAN_SEQW;
+  u32 *s_hist = s_val + SCAN_VALW;
+  const int nb = 1 << p.pbits;
+  u64 *s_base = (u64 *) (s_hist + nb + (nb & 1));
+  constexpr int NW32 = 2*NW;
+  const int sh = 32 - p.pbits;
   for (int i = threadIdx.x; i < nb; i += SCAN_TPB) s_hist[i] = 0;
   scan_load_tile(p,blockIdx.x,s_seq,s_val);
   __syncthreads();
-
   Window w;
   load_window(w,s_seq,s_val,threadIdx.x,p.k);
   u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
+  u32 rk[SCAN_PPT/2];
+#pragma unroll
+  for (int i = 0; i < SCAN_PPT/2; i++) rk[i] = 0;
+  auto fa = [&](int j, const u32 *C)
+    { u32 r = atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u);
+      rk[j>>1] |= r << (16*(j&1));
+    };
+  KmerLoop<NW32,0>::run(w,km,fa);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
+    { u32 c = s_hist[i];
+      s_base[i] = c ? atomicAdd(p.cursor+i,(u64) c) : 0ull;
+    }
+  __syncthreads();
+  Key<NW> *out = (Key<NW> *) p.out;
+  auto fb = [&](int j, const u32 *C)
+    { u32 d = p.pbits ? (C[0] >> sh) : 0u;
+      u32 r = (rk[j>>1] >> (16*(j&1))) & 0xffffu;
+      Key<NW> key;
+#pragma unroll
+      for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
+      out[s_base[d] + r] = key;
+    };
+  KmerLoop<NW32,0>::run(w,km,fb);
+}
 
-  if (!SCATTER)
-    { auto fn = [&](int, const u32 *C) { atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u); };
-      KmerLoop<NW32,0>::run(w,km,fn);
-      __syncthreads();
-      for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
-        { u32 c = s_hist[i];
-          if (c) atomicAdd(p.hist+i,(u64) c);
-        }
-    }
-  else
-    { u32 rk[SCAN_PPT/2];
+/*  Scatter variant 3: single pass, one global atomic (with return) per k-mer on the bucket's shared frontier. */
+template<int NW>
+__global__ void __launch_bounds__(SCAN_TPB) k_scatter_atomic(ScanParams p)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_seq  = s_dyn;
+  u32 *s_val  = s_seq + SCAN_SEQW;
+  constexpr int NW32 = 2*NW;
+  const int sh = 32 - p.pbits;
+  scan_load_tile(p,blockIdx.x,s_seq,s_val);
+  __syncthreads();
+  Window w;
+  load_window(w,s_seq,s_val,threadIdx.x,p.k);
+  u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
+  Key<NW> *out = (Key<NW> *) p.out;
+  auto fb = [&](int, const u32 *C)
+    { u32 d = p.pbits ? (C[0] >> sh) : 0u;
+      u64 ps = atomicAdd(p.cursor + d,1ull);
+      Key<NW> key;
 #pragma unroll
-      for (int i = 0; i < SCAN_PPT/2; i++) rk[i] = 0;
-      auto fa = [&](int j, const u32 *C)
-        { u32 r = atomicAdd(&s_hist[p.pbits ? (C[0] >> sh) : 0u],1u);
-          rk[j>>1] |= r << (16*(j&1));
-        };
-      KmerLoop<NW32,0>::run(w,km,fa);
-      __syncthreads();
-      for (int i = threadIdx.x; i < nb; i += SCAN_TPB)
-        { u32 c = s_hist[i];
-          s_base[i] = c ? atomicAdd(p.hist+i,(u64) c) : 0ull;
-        }
-      __syncthreads();
-      Key<NW> *out = (Key<NW> *) p.out;
-      auto fb = [&](int j, const u32 *C)
-        { u32 d = p.pbits ? (C[0] >> sh) : 0u;
-          u32 r = (rk[j>>1] >> (16*(j&1))) & 0xffffu;
-          Key<NW> key;
-#pragma unroll
-          for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
-          out[s_base[d] + r] = key;
-        };
-      KmerLoop<NW32,0>::run(w,km,fb);
+      for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
+      out[ps] = key;
+    };
+  KmerLoop<NW32,0>::run(w,km,fb);
+}
+
+/*  per bucket d: total[d] = sum_c cta_hist[c][d];  cta_off[c][d] = sum_{c' < c} cta_hist[c'][d]             */
+__global__ void k_colscan(const u32 *cta_hist, u64 *cta_off, u64 *total, int ncta, int nb)
+{ int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nb) return;
+  u64 run = 0;
+  for (int c = 0; c < ncta; c++)
+    { u32 x = cta_hist[(u64) c * nb + d];
+      cta_off[(u64) c * nb + d] = run;
+      run += x;
     }
+  total[d] = run;
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -379,17 +461,51 @@ __global__ void __launch_bounds__(256) k_lscan_apply(const u32 *in, long long n,
  *  histogram in smem, block scan, scatter with smem cursors (no global atomics).  Writes the child
  *  start offsets off2[(b << nbits) + d].                                                            */
 
-#define REF_TPB 512
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{ asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_LOOP:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra WAIT_DONE;\n\t"
+    "bra WAIT_LOOP;\n\t"
+    "WAIT_DONE:\n\t}"
+    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+
+#define REF_TPB   256
+#define REF_TB    1024                     /* records per smem stage                 */
+#define REF_ST    4                        /* stages in flight (TMA bulk copies)      */
+#define REF_SLOT  (REF_TB + 2)             /* slot stride in records (8-byte keys may start odd) */
 
 template<int NW>
 __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ src, Key<NW> *__restrict__ dst,
                                                     const u64 *off1, int nb1, int pos, int nbits,
                                                     u64 *off2, u32 *ticket)
-{ extern __shared__ u32 s_dyn[];
-  u32 *s_cnt = s_dyn;                 /* [2^nbits] */
+{ extern __shared__ __align__(128) unsigned char s_raw[];
+  Key<NW> *sbuf = (Key<NW> *) s_raw;
+  u32 *s_cnt = (u32 *) (s_raw + (size_t) REF_ST * REF_SLOT * sizeof(Key<NW>));     /* [2^nbits] */
+  __shared__ u64 s_full[REF_ST];
   __shared__ u32 s_warp[REF_TPB/32];
   __shared__ int s_b;
   const int nd = 1 << nbits;
+  u32 q = 0;                            /* running tile sequence number of this CTA (slot = q % ST, parity = q / ST) */
+
+  if (threadIdx.x == 0)
+    for (int i = 0; i < REF_ST; i++) mbar_init(&s_full[i],1);
+  __syncthreads();
 
   for (;;)
     { if (threadIdx.x == 0) s_b = (int) atomicAdd(ticket,1u);
@@ -398,62 +514,77 @@ __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ 
       if (b >= nb1) break;
       const u64 start = off1[b];
       const u64 n = off1[b+1] - start;
+      const u32 shift = (NW == 1) ? (u32) (start & 1ull) : 0u;
+      const u64 ntl = (n + REF_TB - 1) / REF_TB;
       for (int i = threadIdx.x; i < nd; i += REF_TPB) s_cnt[i] = 0;
       __syncthreads();
-      const Key<NW> *in = src + start;
-      for (u64 i0 = 0; i0 < n; i0 += REF_TPB*4)
-        { Key<NW> r[4];
+
+      for (int pass = 0; pass < 2; pass++)
+        { auto issue = [&](u64 t, u32 qq)
+            { u64 r0 = start + t * REF_TB;
+              u64 cnt = n - t * REF_TB; if (cnt > REF_TB) cnt = REF_TB;
+              u64 a0 = r0 - shift;
+              u64 len = cnt + shift; if (NW == 1) len = (len + 1) & ~1ull;
+              u32 bytes = (u32) (len * sizeof(Key<NW>));
+              u32 sl = qq % REF_ST;
+              mbar_expect_tx(&s_full[sl],bytes);
+              tma_bulk_g2s(sbuf + (size_t) sl * REF_SLOT,src + a0,bytes,&s_full[sl]);
+            };
+          if (threadIdx.x == 0)
+            for (u64 t = 0; t < ntl && t < REF_ST; t++) issue(t,q + (u32) t);
+          for (u64 t = 0; t < ntl; t++)
+            { const u32 sl = q % REF_ST;
+              mbar_wait(&s_full[sl],(q / REF_ST) & 1u);
+              const Key<NW> *tile = sbuf + (size_t) sl * REF_SLOT + shift;
+              u64 cnt = n - t * REF_TB; if (cnt > REF_TB) cnt = REF_TB;
+              if (pass == 0)
+                {
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            { u64 i = i0 + u*REF_TPB + threadIdx.x;
-              if (i < n) r[u] = in[i];
-            }
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            { u64 i = i0 + u*REF_TPB + threadIdx.x;
-              if (i < n) atomicAdd(&s_cnt[key_digit<NW>(r[u],pos,nbits)],1u);
-            }
-        }
-      __syncthreads();
-      /* block exclusive scan of s_cnt (nd <= 4096 -> <= 8 per thread) */
-      { const int per = (nd + REF_TPB - 1) / REF_TPB;
-        const int b0 = threadIdx.x * per;
-        u32 sum = 0;
-        for (int i = b0; i < b0+per && i < nd; i++) sum += s_cnt[i];
-        u32 incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-          { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
-            if ((threadIdx.x & 31) >= o) incl += y;
-          }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        u32 woff = 0;
-        for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_warp[i];
-        u32 run = woff + incl - sum;
-        for (int i = b0; i < b0+per && i < nd; i++)
-          { u32 c = s_cnt[i];
-            s_cnt[i] = run;
-            off2[((u64) b << nbits) + i] = start + run;
-            run += c;
-          }
-      }
-      __syncthreads();
-      Key<NW> *out = dst + start;
-      for (u64 i0 = 0; i0 < n; i0 += REF_TPB*4)
-        { Key<NW> r[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            { u64 i = i0 + u*REF_TPB + threadIdx.x;
-              if (i < n) r[u] = in[i];
-            }
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            { u64 i = i0 + u*REF_TPB + threadIdx.x;
-              if (i < n)
-                { u32 ps = atomicAdd(&s_cnt[key_digit<NW>(r[u],pos,nbits)],1u);
-                  out[ps] = r[u];
+                  for (int u = 0; u < REF_TB/REF_TPB; u++)
+                    { u32 i = u*REF_TPB + threadIdx.x;
+                      if (i < cnt) atomicAdd(&s_cnt[key_digit<NW>(tile[i],pos,nbits)],1u);
+                    }
                 }
+              else
+                { Key<NW> *out = dst + start;
+#pragma unroll
+                  for (int u = 0; u < REF_TB/REF_TPB; u++)
+                    { u32 i = u*REF_TPB + threadIdx.x;
+                      if (i < cnt)
+                        { Key<NW> r = tile[i];
+                          u32 ps = atomicAdd(&s_cnt[key_digit<NW>(r,pos,nbits)],1u);
+                          out[ps] = r;
+                        }
+                    }
+                }
+              __syncthreads();
+              if (threadIdx.x == 0 && t + REF_ST < ntl) issue(t + REF_ST,q + REF_ST);
+              q++;
+            }
+          if (pass == 0)
+            { /* block exclusive scan of s_cnt; publish the child starts */
+              const int per = (nd + REF_TPB - 1) / REF_TPB;
+              const int b0 = threadIdx.x * per;
+              u32 sum = 0;
+              for (int i = b0; i < b0+per && i < nd; i++) sum += s_cnt[i];
+              u32 incl = sum;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1)
+                { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+                  if ((threadIdx.x & 31) >= o) incl += y;
+                }
+              if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+              __syncthreads();
+              u32 woff = 0;
+              for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_warp[i];
+              u32 run = woff + incl - sum;
+              for (int i = b0; i < b0+per && i < nd; i++)
+                { u32 c = s_cnt[i];
+                  s_cnt[i] = run;
+                  off2[((u64) b << nbits) + i] = start + run;
+                  run += c;
+                }
+              __syncthreads();
             }
         }
       if (b == nb1-1 && threadIdx.x == 0) off2[(u64) nb1 << nbits] = off1[nb1];
@@ -540,6 +671,7 @@ __global__ void k_groups(const u64 *off, long long m /* # of buckets; off[m] = N
 #define SC_EMPTY 0xffffffffu
 #define SC_PAD   0xffffffffffffffffull
 #define SC_SMALLHIST 256
+#define SC_RANKMAX   256     /* <= this many distinct keys: rank by counting instead of the bitonic network */
 
 #define ITEM_UNIFORM 1u      /* every record of the item holds the same key                  */
 #define ITEM_ALTBUF  2u      /* item lives in the alternate buffer (input/staging swapped)    */
@@ -558,32 +690,10 @@ struct SortCountParams
     u32        *ovf_cnt; u32 *ovf_list; u32 ovf_cap;
     u32         cap;                     /* C                                                 */
     u32         tab_off, srt_off;        /* byte offsets of the hash table / sort array in smem */
+    u32         srt2_off;                /* entries: second sort array inside srt (>= SC_RANKMAX free) */
     u32         cutoff;
     long long   nitems;
   };
-
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
-{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
-{ asm volatile(
-    "{\n\t.reg .pred p;\n\t"
-    "WAIT_LOOP:\n\t"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-    "@p bra WAIT_DONE;\n\t"
-    "bra WAIT_LOOP;\n\t"
-    "WAIT_DONE:\n\t}"
-    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 template<int NW> __device__ __forceinline__ u32 key_hash(const Key<NW> &a)
 { u64 h = a.w[0] * 0x9E3779B97F4A7C15ull;
@@ -723,9 +833,32 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   __syncthreads();
   const u32 D = s_D;
   u32 D2 = 1; while (D2 < D) D2 <<= 1;
-  for (u32 i = D + threadIdx.x; i < D2; i += SC_TPB) srt[i] = SC_PAD;
-  __syncthreads();
+  if (D > SC_RANKMAX)
+    { for (u32 i = D + threadIdx.x; i < D2; i += SC_TPB) srt[i] = SC_PAD;
+      __syncthreads();
+    }
 
+  const u64 *fin = srt;
+  if (D <= SC_RANKMAX)
+    { /* few distinct keys (the common, high-coverage case): rank by counting, no barriers */
+      u64 *srt2 = srt + p.srt2_off;
+      for (u32 e = threadIdx.x; e < D; e += SC_TPB)
+        { const u64 a = srt[e];
+          const u32 pa = (u32) (a >> 32);
+          u32 rank = 0;
+          for (u32 j = 0; j < D; j++)
+            { const u64 b = srt[j];
+              const u32 pb = (u32) (b >> 32);
+              bool lt = pb < pa;
+              if (pb == pa && j != e) lt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
+              rank += lt ? 1u : 0u;
+            }
+          srt2[rank] = a;
+        }
+      fin = srt2;
+      __syncthreads();
+    }
+  else
   /* bitonic sort of srt[0..D2) by (32-bit prefix, then full key) */
   for (u32 kk = 2; kk <= D2; kk <<= 1)
     for (u32 j = kk >> 1; j > 0; j >>= 1)
@@ -746,7 +879,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   /* emit: staged (key,count), histogram */
   u32 npass = 0;
   for (u32 q = threadIdx.x; q < D; q += SC_TPB)
-    { u32 v = (u32) srt[q];
+    { u32 v = (u32) fin[q];
       u32 c = v & 0xffffu;
       stage[r0 + q] = rec[v >> 16];
       p.stage_cnt[r0 + q] = c;
