@@ -99,7 +99,9 @@ struct fkgpu_ctx
     PinBuf h_table, h_misc, h_prof, h_poff;
     int64_t h_hist[FKGPU_HIST_BINS];
 
-    /* last result bookkeeping for profiles */
+    /* profile lookup table built by finish when cfg.do_profile */
+    DevBuf eprof, qoff, pkeys, pcnts, pidx, praw, pout, psrc, pdst, plen;
+    long long ptab_n = 0; int ptab_B = 0; long long last_npos = 0;
     long long last_ndist = 0;
   };
 
@@ -163,7 +165,7 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
   DevBuf *bufs[] = { &c->ctah,&c->ctao,&c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
                      &c->eall,&c->epass,&c->poff,&c->bsum,&c->ghist,&c->misc,&c->table,&c->segs,&c->child,&c->pcl,
                      &c->sub_s,&c->sub_e,&c->sub_f,&c->sub_ea,&c->sub_ep,&c->sub_off,&c->sub_par,&c->sub_base,
-                     &c->rstart_d,&c->prof_d };
+                     &c->rstart_d,&c->prof_d,&c->eprof,&c->qoff,&c->pkeys,&c->pcnts,&c->pidx,&c->praw,&c->pout,&c->psrc,&c->pdst,&c->plen };
   for (auto b : bufs) b->release();
   c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -180,6 +182,16 @@ extern "C" int fkgpu_reset(fkgpu_ctx *c)
   for (auto &t : c->tids)
     { t.fill = 0; t.inflight = false; t.chunks.clear(); t.rstart.clear(); t.rlen.clear(); t.rcont.clear(); t.carry = 0; }
   c->ascii_used = 0; c->nreads = 0; c->nbases = 0; c->finished = false;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_read_counts(fkgpu_ctx *c, int64_t *per_tid)
+{ if (c == NULL || per_tid == NULL) return set_err(FKGPU_E_ARG,"fkgpu_read_counts: NULL argument");
+  for (size_t t = 0; t < c->tids.size(); t++)
+    { long long n = 0;
+      for (char x : c->tids[t].rcont) n += (x == 0);
+      per_tid[t] = n;
+    }
   return FKGPU_OK;
 }
 
@@ -379,6 +391,8 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   /* ---- fallback for oversize groups (heavy repeats): host-driven MSD refinement ---------------- */
   struct Sub { u64 s, e; u32 fl; u32 parent; };
   std::vector<Sub> subs;
+  std::vector<u32> sub_par_h, sub_eall_h;
+  std::vector<u64> sub_base_pass;
   if (hm.ovf_cnt > 0)
     { if (hm.ovf_cnt > sp.ovf_cap) return set_err(FKGPU_E_CUDA,"internal: overflow list truncated");
       std::vector<u32> og(hm.ovf_cnt);
@@ -437,7 +451,9 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       sq.e_all = (u32 *) c->sub_ea.p; sq.e_pass = (u32 *) c->sub_ep.p; sq.nitems = (long long) nsub;
       k_sortcount<NW><<<(unsigned) nsub,SC_TPB,L.total,c->st>>>(sq); KCHECK();
       std::vector<u32> hep(nsub);
+      sub_eall_h.resize(nsub); sub_par_h = hpar;
       CU(cudaMemcpyAsync(hep.data(),c->sub_ep.p,nsub*4,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaMemcpyAsync(sub_eall_h.data(),c->sub_ea.p,nsub*4,cudaMemcpyDeviceToHost,c->st));
       CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
       CU(cudaStreamSynchronize(c->st));
       if (hm.ovf_cnt != (u32) og.size()) return set_err(FKGPU_E_CUDA,"internal: refinement left oversize items");
@@ -452,7 +468,51 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
           CU(cudaStreamSynchronize(c->st));
           i = j;
         }
-      CU(cudaMemcpyAsync(c->sub_base.p,hbase.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
+      sub_base_pass = hbase;
+    }
+
+  /* ---- -p: compact ALL distinct k-mers into the lookup table used by fkgpu_profiles ------------------- */
+  c->ptab_n = 0;
+  if (c->cfg.do_profile)
+    { if (c->eprof.ensure((size_t) gmax * 4) || c->qoff.ensure((size_t) (gmax + 1) * 8))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (profile table offsets)");
+      CU(cudaMemcpyAsync(c->eprof.p,c->eall.p,(size_t) gmax * 4,cudaMemcpyDeviceToDevice,c->st));
+      const size_t nsub = subs.size();
+      std::vector<u64> hb(nsub);
+      for (size_t i = 0; i < nsub; )
+        { size_t j = i; u64 run = 0;
+          while (j < nsub && sub_par_h[j] == sub_par_h[i]) { hb[j] = run; run += sub_eall_h[j]; j++; }
+          u32 tot = (u32) run;
+          CU(cudaMemcpyAsync((u32 *) c->eprof.p + sub_par_h[i],&tot,4,cudaMemcpyHostToDevice,c->st));
+          CU(cudaStreamSynchronize(c->st));
+          i = j;
+        }
+      int rc = run_large_scan<NW>(c,(const u32 *) c->eprof.p,gmax,(u64 *) c->qoff.p,&d_misc->total_pass);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      const u64 U = hm.total_pass;
+      int B = ilog2_ceil(U + 1) - 2; if (B < 8) B = 8; if (B > 26) B = 26;
+      if (c->pkeys.ensure((size_t) (U + 1) * sizeof(K)) || c->pcnts.ensure((size_t) (U + 1) * 2) || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %llu k-mers)",U);
+      CompactParams cp;
+      cp.stage0 = Y; cp.stage1 = X; cp.stage_cnt = (const u32 *) c->scnt.p;
+      cp.starts = gstart; cp.flags = NULL; cp.e_all = (const u32 *) c->eall.p; cp.out_off = (const u64 *) c->qoff.p;
+      cp.out = NULL; cp.nitems = gmax; cp.cutoff = 0; cp.kbytes = c->kbytes;
+      k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cp,(K *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
+      if (nsub > 0)
+        { if (c->sub_base.ensure(nsub*8) || c->sub_off.ensure(nsub*8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+          CU(cudaMemcpyAsync(c->sub_base.p,hb.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
+          k_suboff<<<(unsigned) ((nsub + 255) / 256),256,0,c->st>>>((u64 *) c->sub_off.p,(const u32 *) c->sub_par.p,
+                                                                   (const u64 *) c->sub_base.p,(const u64 *) c->qoff.p,(long long) nsub); KCHECK();
+          CompactParams cq = cp;
+          cq.starts = (const u64 *) c->sub_s.p; cq.flags = (const u32 *) c->sub_f.p; cq.e_all = (const u32 *) c->sub_ea.p;
+          cq.out_off = (const u64 *) c->sub_off.p; cq.nitems = (long long) nsub;
+          k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cq,(K *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
+          CU(cudaStreamSynchronize(c->st));       /* hb is about to go out of scope */
+        }
+      k_build_index<NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const K *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
+      c->ptab_n = (long long) U; c->ptab_B = B;
     }
 
   /* ---- table: scan the per-item pass counts, compact ------------------------------------------- */
@@ -473,6 +533,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       k_compact<NW><<<grid,256,0,c->st>>>(cp); KCHECK();
       if (!subs.empty())
         { size_t nsub = subs.size();
+          CU(cudaMemcpyAsync(c->sub_base.p,sub_base_pass.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
           k_suboff<<<(unsigned) ((nsub + 255) / 256),256,0,c->st>>>((u64 *) c->sub_off.p,(const u32 *) c->sub_par.p,
                                                                    (const u64 *) c->sub_base.p,(const u64 *) c->poff.p,(long long) nsub); KCHECK();
           CompactParams cq = cp;
@@ -697,6 +758,7 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
   CU(cudaStreamSynchronize(c->cst));
   c->finished = true;
   const long long npos = c->ascii_used;
+  c->last_npos = npos;
   res->nbases = c->nbases;
   res->nreads = c->nreads;
   int64_t sw, vw;
@@ -713,7 +775,9 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
   if (c->cfg.bc_prefix > 0 || c->cfg.do_profile)
     { /* read starts on the device, tid-major */
       std::vector<long long> rs;
-      for (auto &t : c->tids) rs.insert(rs.end(),t.rstart.begin(),t.rstart.end());
+      for (auto &t : c->tids)
+        for (size_t i = 0; i < t.rstart.size(); i++)
+          if (!t.rcont[i]) rs.push_back(t.rstart[i]);
       if (c->rstart_d.ensure(rs.size()*8 + 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (read index)");
       if (!rs.empty())
         { CU(cudaMemcpyAsync(c->rstart_d.p,rs.data(),rs.size()*8,cudaMemcpyHostToDevice,c->st));
@@ -803,8 +867,60 @@ extern "C" int fkgpu_count_records(fkgpu_ctx *c, void *d_records, int64_t nrecor
                       : count_records_t<2>(c,d_records,nrecords,fetch_table,res);
 }
 
+template<int NW>
+static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)
+{ const long long npos = c->last_npos;
+  const int k = c->cfg.kmer, bc = c->cfg.bc_prefix;
+  /* pieces in tid-major order; a continuation piece (rem carry) extends the previous read */
+  std::vector<long long> src, dst; std::vector<int> len; std::vector<int64_t> offs;
+  long long run = 0;
+  for (auto &t : c->tids)
+    for (size_t i = 0; i < t.rstart.size(); i++)
+      { const int b = t.rcont[i] ? 0 : bc;
+        int pl = t.rlen[i] - b - k + 1; if (pl < 0) pl = 0;
+        if (!t.rcont[i]) offs.push_back(run);
+        src.push_back(t.rstart[i] + b); dst.push_back(run); len.push_back(pl);
+        run += pl;
+      }
+  offs.push_back(run);
+  const size_t np = src.size();
+  if (c->praw.ensure((size_t) (npos + 64) * 2) || c->pout.ensure((size_t) (run + 2) * 2) || c->psrc.ensure(np*8 + 8) || c->pdst.ensure(np*8 + 8)
+      || c->plen.ensure(np*4 + 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (profiles of %lld positions)",npos);
+  if (c->h_prof.ensure((size_t) (run + 2) * 2) || c->h_poff.ensure(offs.size() * 8))
+    return set_err(FKGPU_E_NOMEM,"out of pinned host memory (profiles)");
+  stage_begin(c,FKGPU_ST_PROFILE);
+  ProfileParams q;
+  ScanGeom g = scan_geom(c,npos,0);
+  fill_scan_params(c,q.sp,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,0,g);
+  q.keys = c->pkeys.p; q.cnts = (const uint16_t *) c->pcnts.p; q.idx = (const u64 *) c->pidx.p; q.B = c->ptab_B;
+  q.raw = (uint16_t *) c->praw.p;
+  if (g.ntiles > 0)
+    { size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW) * 4;
+      k_profile<NW><<<(unsigned) g.ntiles,SCAN_TPB,sm,c->st>>>(q); KCHECK();
+    }
+  if (np > 0)
+    { CU(cudaMemcpyAsync(c->psrc.p,src.data(),np*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->pdst.p,dst.data(),np*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->plen.p,len.data(),np*4,cudaMemcpyHostToDevice,c->st));
+      k_gather_profile<<<c->sms * 8,256,0,c->st>>>((const uint16_t *) c->praw.p,(const long long *) c->psrc.p,(const long long *) c->pdst.p,
+                                                  (const int *) c->plen.p,(long long) np,(uint16_t *) c->pout.p); KCHECK();
+    }
+  stage_end(c,FKGPU_ST_PROFILE);
+  if (run > 0) CU(cudaMemcpyAsync(c->h_prof.p,c->pout.p,(size_t) run * 2,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  cudaEventElapsedTime(&c->ms[FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE+1]);
+  memcpy(c->h_poff.p,offs.data(),offs.size()*8);
+  *nreads = (int64_t) offs.size() - 1;
+  *off = (const int64_t *) c->h_poff.p;
+  *prof = (const uint16_t *) c->h_prof.p;
+  return FKGPU_OK;
+}
+
 extern "C" int fkgpu_profiles(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)
-{ (void) nreads; (void) off; (void) prof;
-  if (c == NULL) return set_err(FKGPU_E_ARG,"fkgpu_profiles: NULL context");
-  return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_profiles: not built yet");
+{ if (c == NULL || nreads == NULL || off == NULL || prof == NULL) return set_err(FKGPU_E_ARG,"fkgpu_profiles: NULL argument");
+  if (!c->cfg.do_profile) return set_err(FKGPU_E_STATE,"fkgpu_profiles: the context was created without do_profile");
+  if (!c->finished) return set_err(FKGPU_E_STATE,"fkgpu_profiles: call fkgpu_finish first");
+  CU(cudaSetDevice(c->cfg.device));
+  return (c->NW == 1) ? profiles_t<1>(c,nreads,off,prof) : profiles_t<2>(c,nreads,off,prof);
 }

@@ -1027,4 +1027,98 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
     }
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/*  Count profiles (-p).  The finished distinct-k-mer table (all counts, no cutoff) is compacted into
+ *  (keys[], cnts[]) with a 2^B-slot prefix index; k_profile re-scans the packed reads and looks every
+ *  canonical k-mer up -- the reference's "relative profile" sort-merge-join idea (count.c:675-792)
+ *  turned into an indexed lookup.  Result: one u16 per read position (0 where no legal k-mer starts).  */
+
+template<int NW>
+__global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<NW> *keys, uint16_t *cnts)
+{ const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  for (long long g = (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < p.nitems; g += nwarps)
+    { const u32 D = p.e_all[g];
+      if (D == 0) continue;
+      const u32 fl = p.flags ? p.flags[g] : 0u;
+      const Key<NW> *stage = (const Key<NW> *) ((fl & ITEM_ALTBUF) ? p.stage1 : p.stage0) + p.starts[g];
+      const u32 *cnt = p.stage_cnt + p.starts[g];
+      const u64 o = p.out_off[g];
+      for (u32 q = lane; q < D; q += 32)
+        { keys[o+q] = stage[q];
+          cnts[o+q] = (uint16_t) cnt[q];
+        }
+    }
+}
+
+template<int NW>
+__global__ void k_build_index(const Key<NW> *keys, u64 n, int B, u64 *idx)
+{ u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const u64 slots = 1ull << B;
+  u64 lo = (i == 0) ? 0 : (keys[i-1].w[0] >> (64-B)) + 1;
+  u64 hi = (i == n) ? slots : (keys[i].w[0] >> (64-B));
+  for (u64 s = lo; s <= hi && s <= slots; s++) idx[s] = i;
+}
+
+struct ProfileParams
+  { ScanParams   sp;
+    const void  *keys; const uint16_t *cnts; const u64 *idx; int B;
+    uint16_t    *raw;            /* [npos] */
+  };
+
+template<int NW>
+__global__ void __launch_bounds__(SCAN_TPB) k_profile(ProfileParams q)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_seq = s_dyn;
+  u32 *s_val = s_seq + SCAN_SEQW;
+  constexpr int NW32 = 2*NW;
+  const ScanParams &p = q.sp;
+  scan_load_tile(p,blockIdx.x,s_seq,s_val);
+  __syncthreads();
+  Window w;
+  load_window(w,s_seq,s_val,threadIdx.x,p.k);
+  u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
+  const Key<NW> *keys = (const Key<NW> *) q.keys;
+  const long long p0 = (long long) blockIdx.x * SCAN_TILE + (long long) threadIdx.x * SCAN_PPT;
+  u32 res[SCAN_PPT/2];
+#pragma unroll
+  for (int i = 0; i < SCAN_PPT/2; i++) res[i] = 0;
+  auto fn = [&](int j, const u32 *C)
+    { Key<NW> key;
+#pragma unroll
+      for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
+      const u64 s = key.w[0] >> (64 - q.B);
+      u64 lo = q.idx[s], hi = q.idx[s+1];
+      u32 c = 0;
+      while (lo < hi)
+        { u64 mid = (lo + hi) >> 1;
+          Key<NW> t = keys[mid];
+          if (key_eq<NW>(t,key)) { c = q.cnts[mid]; break; }
+          if (key_lt<NW>(t,key)) lo = mid+1; else hi = mid;
+        }
+      res[j>>1] |= c << (16*(j&1));
+    };
+  KmerLoop<NW32,0>::run(w,km,fn);
+  if (p0 < p.npos)
+    { u32 *out = (u32 *) (q.raw + p0);            /* p0 is a multiple of 32: 4-byte aligned */
+#pragma unroll
+      for (int i = 0; i < SCAN_PPT/2; i++)
+        if (p0 + 2*i < p.npos) out[i] = res[i];
+    }
+}
+
+/*  piece r: copy raw[src[r] .. src[r]+len[r]) to out[dst[r] ..]; one warp per piece                 */
+__global__ void k_gather_profile(const uint16_t *raw, const long long *src, const long long *dst, const int *len,
+                                 long long npieces, uint16_t *out)
+{ const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  for (long long r = (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < npieces; r += nwarps)
+    { const uint16_t *s = raw + src[r];
+      uint16_t *d = out + dst[r];
+      const int n = len[r];
+      for (int i = lane; i < n; i += 32) d[i] = s[i];
+    }
+}
+
 }  // namespace fk

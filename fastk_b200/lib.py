@@ -60,6 +60,8 @@ def load_library(path=None):
     lib.fkgpu_finish.restype = C.c_int
     lib.fkgpu_profiles.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(i64)), C.POINTER(C.POINTER(C.c_uint16))]
     lib.fkgpu_profiles.restype = C.c_int
+    lib.fkgpu_read_counts.argtypes = [vp, C.POINTER(i64)]
+    lib.fkgpu_read_counts.restype = C.c_int
     lib.fkgpu_packed_words.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
     lib.fkgpu_packed_words.restype = None
     lib.fkgpu_pack_ascii_dev.argtypes = [vp, vp, i64, vp, vp]
@@ -84,7 +86,7 @@ def load_library(path=None):
 
 
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
-           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
+           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_stage_times"]
 

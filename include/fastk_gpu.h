@@ -102,6 +102,10 @@ int  fkgpu_finish(fkgpu_ctx *ctx, int fetch_table, fkgpu_result *res);
  *  host memory owned by the context.                                                             */
 int  fkgpu_profiles(fkgpu_ctx *ctx, int64_t *nreads, const int64_t **off, const uint16_t **prof);
 
+/*  # of whole reads each tid delivered (continuation pieces of a split read are not counted twice); part t+1 of
+ *  the .prof output holds the reads of tid t (merge.c:926-928).  per_tid has cfg.nthreads entries.          */
+int  fkgpu_read_counts(fkgpu_ctx *ctx, int64_t *per_tid);
+
 /* ---- device-resident path (bench "value", multi-GPU stages) --------------------------------------
  *  Packed read stream: position i of the concatenated reads (one terminator position between reads)
  *    seq word i>>4 , bits 31-2*(i&15) .. 30-2*(i&15)   = base code a,c,g,t = 0..3

@@ -1,0 +1,79 @@
+"""GPU: the two host programs end to end, files on disk compared with the reference's golden outputs:
+  fastk_b200/bin/FastK            our C host (own reader / writers) over the C ABI
+  integration/_build/FastK_refhost the REFERENCE's own FastK.c + io.c + table.c + libfastk.c linked with fastk_shim.c
+Parity tiers: T0 .hist byte-identical; T1 .ktab stub byte-identical, part count = -T, concatenated
+payload byte-identical, parts cut on first-byte boundaries; P1 every decoded profile identical."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+OURS = os.path.join(util.ROOT, "fastk_b200", "bin", "FastK")
+REFHOST = os.path.join(util.ROOT, "integration", "_build", "FastK_refhost")
+
+
+def run_cli(exe, g, d, extra=()):
+    cmd = [exe, "-k%d" % g["k"], "-t%d" % g["t"], "-p", "-T%d" % g["T"], "-P" + d, "-N" + os.path.join(d, "out")] + list(extra) + [g["src"]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def check_outputs(d, g, oracle_lib, prof_parts=None):
+    h = util.read_hist_file(os.path.join(d, "out.hist"))
+    assert [h["k"], h["low"], h["high"], h["ilow"], h["max_inst"]] == g["hist_header"]
+    assert np.array_equal(h["hist"][1:], g["hist"][1:])
+    kt = util.read_ktab_files(d, "out")
+    assert kt["stub"] == g["ktab_stub"], "ktab stub differs from the reference"
+    assert kt["nparts"] == g["T"] and kt["cutoff"] == g["t"]
+    assert kt["payload"] == g["ktab_payload"], "concatenated table payload differs from the reference"
+    util.check_parts_on_first_byte_boundaries(kt)
+    prof, off, nparts = util.decode_prof_files(d, "out", oracle_lib)
+    assert np.array_equal(off, g["prof_off"]) and np.array_equal(prof, g["prof"])
+    if prof_parts is not None:
+        assert nparts == prof_parts
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_our_fastk_cli(oracle_lib, name, tmp_path):
+    assert os.path.exists(OURS), "host program not built"
+    g = util.golden(name)
+    run_cli(OURS, g, str(tmp_path), ["-v"])
+    check_outputs(str(tmp_path), g, oracle_lib)
+
+
+def test_our_fastk_cli_gz_and_default_names(oracle_lib, tmp_path):
+    g = util.golden("c1_k40")
+    src = os.path.join(str(tmp_path), "reads.fa")
+    shutil.copy(g["src"], src)
+    subprocess.check_call(["gzip", src])
+    r = subprocess.run([OURS, "-k40", "-t1", "-p", "-T4", src + ".gz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for f in ("reads.hist", "reads.ktab", "reads.prof", ".reads.ktab.4", ".reads.pidx.1"):
+        assert os.path.exists(os.path.join(str(tmp_path), f)), f
+    os.rename(os.path.join(str(tmp_path), "reads.hist"), os.path.join(str(tmp_path), "out.hist"))
+    h = util.read_hist_file(os.path.join(str(tmp_path), "out.hist"))
+    assert np.array_equal(h["hist"][1:], g["hist"][1:])
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_reference_host_with_gpu_shim(oracle_lib, name, tmp_path):
+    """The drop-in proof: the reference's unmodified driver, input module and table merger running on our library."""
+    if not os.path.exists(REFHOST):
+        pytest.skip("integration/_build/FastK_refhost not built (needs /root/reference at build time)")
+    g = util.golden(name)
+    run_cli(REFHOST, g, str(tmp_path))
+    check_outputs(str(tmp_path), g, oracle_lib, prof_parts=g.get("prof_parts"))
+
+
+def test_cli_error_paths(tmp_path):
+    r = subprocess.run([OURS, "-k40", os.path.join(str(tmp_path), "missing")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot find" in r.stderr
+    r = subprocess.run([OURS, "-k99", util.golden("c1_k40")["src"]], capture_output=True, text=True)
+    assert r.returncode == 1 and "not supported" in r.stderr

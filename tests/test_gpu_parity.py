@@ -82,3 +82,62 @@ def test_repeats_force_refinement(oracle_lib):
     reads = [unit * 3] * 3000 + synth.sample_reads(synth.random_genome(50_000, 1), 2000, 150, 0.01, 2)
     check(oracle_lib, reads, 40)
     check(oracle_lib, reads, 25)
+
+
+def run_gpu_profiles(reads, k, bc=0, nthreads=1, block_bytes=1_000_000):
+    g = FastKGPU(k=k, table_cutoff=1, profile=True, bc_prefix=bc, nthreads=nthreads)
+    try:
+        per_tid = [[] for _ in range(nthreads)]
+        # tid-major global order: give tid t a contiguous slice of the reads
+        for t in range(nthreads):
+            per_tid[t] = reads[len(reads) * t // nthreads: len(reads) * (t + 1) // nthreads]
+            for bases, boff in synth.blocks(per_tid[t], max_bytes=block_bytes):
+                g.ingest(bases, boff.astype(np.int32), tid=t)
+        res = g.finish(fetch_table=True)
+        off, prof = g.profiles()
+        return res, off, prof
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("k,bc,nthreads", [(40, 0, 1), (21, 0, 3), (63, 0, 2), (40, 10, 2)])
+def test_profiles_match_oracle(oracle_lib, k, bc, nthreads):
+    genome = synth.random_genome(30_000, 41)
+    reads = synth.sample_reads(genome, 1500, 200, 0.004, 42, n_rate=0.003, lower_rate=0.2, len_jitter=180)
+    reads += [b"", b"ACGT", b"N" * 100, b"A" * 300, b"ACGTN" * 40]
+    want = oracle_lib.count(reads, k, bc_prefix=bc, cutoff=1, profiles=True)
+    res, off, prof = run_gpu_profiles(reads, k, bc=bc, nthreads=nthreads)
+    assert np.array_equal(res.table, want["table"])
+    assert len(off) == len(reads) + 1
+    for r in range(len(reads)):
+        assert np.array_equal(prof[off[r]:off[r + 1]], want["profiles"][r]), f"profile of read {r} differs"
+
+
+def test_split_long_read_rem_semantics(oracle_lib):
+    """A read delivered in pieces with rem > 0 and a k-1 overlap (io.c:296-333) counts and profiles as one read."""
+    k = 40
+    genome = synth.random_genome(400_000, 51)
+    reads = synth.sample_reads(genome, 6, 60_000, 0.001, 52)
+    want = oracle_lib.count(reads, k, cutoff=1, profiles=True)
+    g = FastKGPU(k=k, table_cutoff=1, profile=True)
+    try:
+        piece = 25_000
+        for r in reads:
+            pos = 0
+            while True:
+                end = min(len(r), pos + piece)
+                last = end == len(r)
+                bases = r[pos:end] + b"\0"
+                g.ingest(bases, np.array([0, len(bases)], dtype=np.int32), tid=0, rem=0 if last else len(r) - end + (k - 1))
+                if last:
+                    break
+                pos = end - (k - 1)
+        res = g.finish(fetch_table=True)
+        off, prof = g.profiles()
+    finally:
+        g.close()
+    assert res.nkmers == want["nkmers"] and np.array_equal(res.table, want["table"])
+    assert res.nreads == len(reads) and res.nbases == sum(len(r) for r in reads)
+    assert len(off) == len(reads) + 1
+    for r in range(len(reads)):
+        assert np.array_equal(prof[off[r]:off[r + 1]], want["profiles"][r])

@@ -1,0 +1,119 @@
+"""Test helpers: file parsing and golden-fixture access (no product code)."""
+import gzip
+import json
+import os
+import struct
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+ROOT = os.path.dirname(HERE)
+
+
+def read_seq_file(path):
+    """FASTA (multi-line ok) / FASTQ (4-line) -> list of bytes, as io.c's automaton delivers them."""
+    op = gzip.open if path.endswith(".gz") else open
+    data = op(path, "rb").read()
+    reads = []
+    if data[:1] == b"@":
+        lines = data.split(b"\n")
+        for i in range(0, len(lines) - 1, 4):
+            if lines[i][:1] == b"@":
+                reads.append(lines[i + 1])
+    else:
+        cur = None
+        for ln in data.split(b"\n"):
+            if ln[:1] == b">":
+                if cur is not None:
+                    reads.append(cur)
+                cur = b""
+            elif cur is not None:
+                cur += ln
+        if cur is not None:
+            reads.append(cur)
+    return reads
+
+
+def golden_cases():
+    return sorted(f[:-5] for f in os.listdir(GOLD) if f.endswith(".json"))
+
+
+def golden(name):
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    src = os.path.join(GOLD, name + "." + meta["fmt"])
+    blob = gzip.open(os.path.join(GOLD, name + ".ktab.gz"), "rb").read()
+    sl = struct.unpack("<q", blob[:8])[0]
+    meta["src"] = src
+    meta["ktab_stub"] = blob[8:8 + sl]
+    meta["ktab_payload"] = blob[8 + sl:]
+    hist = np.zeros(32768, dtype=np.int64)
+    for k, v in meta["hist_nonzero"].items():
+        hist[int(k)] = v
+    meta["hist"] = hist
+    pz = os.path.join(GOLD, name + ".prof.npz")
+    if os.path.exists(pz):
+        z = np.load(pz)
+        meta["prof"], meta["prof_off"] = z["prof"], z["off"]
+    return meta
+
+
+def read_hist_file(path):
+    b = open(path, "rb").read()
+    assert len(b) == 262164, len(b)
+    k, lo, hi = struct.unpack("<iii", b[:12])
+    ilow, maxinst = struct.unpack("<qq", b[12:28])
+    h = np.zeros(32768, dtype=np.int64)
+    h[1:] = np.frombuffer(b[28:], dtype="<i8")
+    return dict(k=k, low=lo, high=hi, ilow=ilow, max_inst=maxinst, hist=h, raw=b)
+
+
+def read_ktab_files(d, root):
+    stub = open(os.path.join(d, root + ".ktab"), "rb").read()
+    k, nparts, cutoff, ib = struct.unpack("<iiii", stub[:16])
+    payload, ns = b"", []
+    for t in range(1, nparts + 1):
+        x = open(os.path.join(d, "." + root + ".ktab.%d" % t), "rb").read()
+        pk, n = struct.unpack("<iq", x[:12])
+        assert pk == k
+        pw = ((2 * k + 7) >> 3) + 2 - ib
+        assert len(x) == 12 + n * pw, (len(x), n, pw)
+        ns.append(n)
+        payload += x[12:]
+    return dict(k=k, nparts=nparts, cutoff=cutoff, ibyte=ib, stub=stub, payload=payload, part_entries=ns)
+
+
+def check_parts_on_first_byte_boundaries(kt):
+    """README.md:984 / table.c:257: a first-byte value never spans two parts; entries strictly increasing."""
+    k, ib = kt["k"], kt["ibyte"]
+    kb = (2 * k + 7) >> 3
+    idx = np.frombuffer(kt["stub"][16:], dtype="<i8")
+    assert len(idx) == 256 ** ib
+    assert idx[-1] == sum(kt["part_entries"])
+    first_byte_cum = idx[(np.arange(256) + 1) * 256 ** (ib - 1) - 1]
+    cum = np.cumsum(kt["part_entries"])
+    for c in cum[:-1]:
+        assert c in first_byte_cum or c == 0, "table part does not end on a first-byte boundary"
+    return kb
+
+
+def decode_prof_files(d, root, oracle):
+    """-> (prof uint16 concat, off int64) decoding every read with the oracle's restatement of Fetch_Profile."""
+    stub = open(os.path.join(d, root + ".prof"), "rb").read()
+    k, nparts = struct.unpack("<ii", stub[:8])
+    prof, off = [], [0]
+    total = 0
+    for t in range(1, nparts + 1):
+        x = open(os.path.join(d, "." + root + ".pidx.%d" % t), "rb").read()
+        pk, first, n = struct.unpack("<iqq", x[:20])
+        assert pk == k and first == total
+        idx = np.frombuffer(x[20:20 + 8 * n], dtype="<i8")
+        data = open(os.path.join(d, "." + root + ".prof.%d" % t), "rb").read()
+        prev = 0
+        for e in idx:
+            p = oracle.decode_profile(data[prev:int(e)], cap=1 << 22)
+            prof.append(p)
+            off.append(off[-1] + len(p))
+            prev = int(e)
+        total += n
+    return (np.concatenate(prof) if prof else np.zeros(0, np.uint16)), np.array(off, dtype=np.int64), nparts
