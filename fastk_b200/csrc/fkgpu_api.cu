@@ -337,7 +337,7 @@ template<int NW> static int run_large_scan(fkgpu_ctx *c, const u32 *in, long lon
 /*  Everything after "records are in bufA grouped by their top P1 bits, off1[] holds the group starts".
  *  nub = upper bound on the record count used for sizing.                                           */
 template<int NW>
-static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fetch_table, fkgpu_result *res)
+static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fetch_table, fkgpu_result *res, void *bufX, void *bufY)
 { typedef Key<NW> K;
   const int nb1 = 1 << P1;
   const long long m = (long long) nb1 << P2;           /* # fine buckets */
@@ -345,7 +345,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   const ScLayout L = sc_layout(NW);
   Misc *d_misc = (Misc *) c->misc.p;
 
-  K *X = (K *) c->bufA.p, *Y = (K *) c->bufB.p;
+  K *X = (K *) bufX, *Y = (K *) bufY;
   const u64 *offs = (const u64 *) c->off1.p;
 
   if (P2 > 0)
@@ -392,6 +392,10 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   struct Sub { u64 s, e; u32 fl; u32 parent; };
   std::vector<Sub> subs;
   std::vector<u32> sub_par_h, sub_eall_h;
+  static int verbose = -1;
+  if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (verbose)
+    fprintf(stderr,"[fkgpu] nub=%lld P1=%d P2=%d groups=%lld oversize_groups=%u\n",nub,P1,P2,gmax,hm.ovf_cnt);
   std::vector<u64> sub_base_pass;
   if (hm.ovf_cnt > 0)
     { if (hm.ovf_cnt > sp.ovf_cap) return set_err(FKGPU_E_CUDA,"internal: overflow list truncated");
@@ -581,13 +585,27 @@ static void choose_levels(long long nub, int *P1, int *P2)
   int p1max = 11;
   { const char *e = getenv("FKGPU_P1"); if (e) p1max = std::max(1,std::min(11,atoi(e))); }
   *P1 = std::min(P,p1max);
-  *P2 = std::min(13,P - *P1);
+  *P2 = std::min(13,P - *P1);            /* provisional; choose_p2 refines it from the level-1 histogram */
 }
 
-static int prepare_common(fkgpu_ctx *c, long long nub, int P1)
+/*  Level-2 fan-out from the DENSEST level-1 bucket (a rank of the multi-GPU path, or skewed data, fills only part of
+ *  the prefix space): fine buckets of that bucket average <= 512 records, well under the SC_CAP-SC_T+1 guarantee. */
+static int choose_p2(fkgpu_ctx *c, int P1, int *P2)
+{ const int nb1 = 1 << P1;
+  std::vector<u64> h(nb1);
+  CU(cudaMemcpyAsync(h.data(),c->hist1.p,(size_t) nb1 * 8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  u64 mx = 0;
+  for (u64 x : h) mx = std::max(mx,x);
+  int p2 = ilog2_ceil(std::max<u64>(1,(mx + 511) / 512));
+  *P2 = std::min(13,p2);
+  return FKGPU_OK;
+}
+
+static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true)
 { const int nb1 = 1 << P1;
   const size_t rb = (size_t) 8 * c->NW;
-  if (c->bufA.ensure((size_t) (nub + 4) * rb) || c->bufB.ensure((size_t) (nub + 4) * rb))
+  if (c->bufA.ensure((size_t) (nub + 4) * rb) || (needB && c->bufB.ensure((size_t) (nub + 4) * rb)))
     return set_err(FKGPU_E_NOMEM,"out of device memory: two record buffers of %lld x %zu bytes",nub,rb);
   if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8)
       || c->ghist.ensure(FKGPU_HIST_BINS * 8) || c->misc.ensure(sizeof(Misc)))
@@ -699,11 +717,13 @@ static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long
   if (rc) return rc;
   stage_end(c,FKGPU_ST_SCANHIST);
   k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) NULL,nb1); KCHECK();
+  rc = choose_p2(c,P1,&P2);
+  if (rc) return rc;
   stage_begin(c,FKGPU_ST_SCATTER);
   rc = scan_scatter<NW>(c,d_seq,d_val,npos,P1,(const u64 *) c->off1.p,c->bufA.p);
   if (rc) return rc;
   stage_end(c,FKGPU_ST_SCATTER);
-  rc = count_from_level1<NW>(c,npos,P1,P2,fetch_table,res);
+  rc = count_from_level1<NW>(c,npos,P1,P2,fetch_table,res,c->bufA.p,c->bufB.p);
   if (rc) return rc;
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
@@ -828,10 +848,10 @@ extern "C" int fkgpu_scatter_prefix(fkgpu_ctx *c, const uint32_t *d_seq, const u
 }
 
 template<int NW>
-static int count_records_t(fkgpu_ctx *c, const void *d_records, long long n, int fetch_table, fkgpu_result *res)
+static int count_records_t(fkgpu_ctx *c, void *d_records, long long n, int fetch_table, fkgpu_result *res)
 { int P1, P2;
   choose_levels(n,&P1,&P2);
-  int rc = prepare_common(c,n,P1);
+  int rc = prepare_common(c,n,P1,false);      /* the caller's buffer doubles as the second record buffer */
   if (rc) return rc;
   const int nb1 = 1 << P1;
   const size_t smh = (size_t) (nb1 + (nb1 & 1)) * 4;
@@ -844,13 +864,15 @@ static int count_records_t(fkgpu_ctx *c, const void *d_records, long long n, int
       stage_end(c,FKGPU_ST_L2HIST);
     }
   k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,nb1); KCHECK();
+  rc = choose_p2(c,P1,&P2);
+  if (rc) return rc;
   if (ntiles > 0)
     { stage_begin(c,FKGPU_ST_SCATTER);
       CU(cudaFuncSetAttribute(k_tilepart<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
       k_tilepart<NW,true><<<(unsigned) ntiles,TP_TPB,sms,c->st>>>((const Key<NW> *) d_records,(Key<NW> *) c->bufA.p,(u64) n,P1,(u64 *) c->cur1.p); KCHECK();
       stage_end(c,FKGPU_ST_SCATTER);
     }
-  rc = count_from_level1<NW>(c,n,P1,P2,fetch_table,res);
+  rc = count_from_level1<NW>(c,n,P1,P2,fetch_table,res,c->bufA.p,d_records);
   if (rc) return rc;
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));

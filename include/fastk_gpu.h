@@ -129,7 +129,8 @@ int  fkgpu_count_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d
  *                           grouped by that prefix, into d_records (capacity cap_records); d_offsets
  *                           (2^bits + 1 uint64, device) receives the group starts.
  *   3. fkgpu_count_records: sort / count / histogram / table over an arbitrary record array (e.g. the
- *                           records received from the peers).  Keys outside are not filtered.      */
+ *                           records received from the peers).  d_records is CONSUMED: it is reused as the second
+ *                           sort buffer and must have room for nrecords + 4 records.                            */
 int  fkgpu_record_bytes(int kmer);
 int  fkgpu_prefix_hist(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
                        int bits, uint64_t *d_hist);

@@ -1,0 +1,68 @@
+"""torchrun worker for tests/test_gpu_multi.py: N ranks count disjoint read sets with the prefix all-to-all; rank 0
+recounts the union on one GPU through fkgpu_ingest/finish and both must agree bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fastk_b200 import FastKGPU, synth, multigpu  # noqa: E402
+
+
+def reads_of(rank, k):
+    genome = synth.random_genome(150_000, 77)          # same genome on every rank: k-mers recur across ranks
+    return synth.sample_reads(genome, 6000, 250, 0.004, 1000 + rank, n_rate=0.001, len_jitter=100)
+
+
+def main():
+    k = int(sys.argv[1])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    eng = FastKGPU(k=k, table_cutoff=1, device=local)
+    reads = reads_of(rank, k)
+    bases, boff = synth.to_block(reads)
+    npos = len(bases)
+    a = torch.frombuffer(bytearray(bases + b"\0" * 64), dtype=torch.uint8).to(dev)
+    sw, vw = eng.packed_words(npos)
+    d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
+    d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
+    eng.pack_ascii_dev(a.data_ptr(), npos, d_seq.data_ptr(), d_val.data_ptr())
+    torch.cuda.synchronize()
+    mg = multigpu.MultiGPUCounter(eng, world, rank, dev)
+    out = mg.count_packed(d_seq, d_val, npos, fetch_table=True)
+    tw = out.kmer_bytes + 2
+    mx = max(out.table_sizes)
+    mine = torch.zeros((mx, tw), dtype=torch.uint8, device=dev)
+    if out.local.ntable:
+        mine[:out.local.ntable] = torch.from_numpy(out.local.table).to(dev)
+    allt = torch.zeros((world, mx, tw), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allt, mine)
+    ok = 1
+    if rank == 0:
+        table = np.concatenate([allt[r, :out.table_sizes[r]].cpu().numpy() for r in range(world)])
+        one = FastKGPU(k=k, table_cutoff=1, device=local)
+        for r in range(world):
+            for b, o in synth.blocks(reads_of(r, k)):
+                one.ingest(b, o.astype(np.int32))
+        want = one.finish(fetch_table=True)
+        one.close()
+        try:
+            assert out.nkmers == want.nkmers and out.ndistinct == want.ndistinct and out.max_inst == want.max_inst
+            assert np.array_equal(out.hist[1:], want.hist[1:]), "global histogram differs"
+            assert out.ntable == want.ntable and np.array_equal(table, want.table), "rank-ordered table differs"
+            print(f"MGPU_OK world={world} k={k} kmers={out.nkmers} distinct={out.ndistinct} sizes={out.table_sizes}")
+        except AssertionError as e:
+            ok = 0
+            print("MGPU_FAIL", e)
+    eng.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,28 @@
+"""GPU (>= 2 devices): the multi-GPU path (prefix histogram -> NCCL all-to-all -> local count) must reproduce
+the single-GPU result on the union of the reads: identical histogram and identical rank-ordered table."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ngpu():
+    import fastk_b200
+    return fastk_b200.load_library().fkgpu_device_count()
+
+
+@pytest.mark.parametrize("k", [40, 21])
+def test_multi_gpu_equals_single_gpu(k):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(HERE, "mgpu_worker.py"), str(k)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
