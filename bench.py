@@ -332,16 +332,29 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     W = 8 if k <= 32 else 16
     N, U = res.nkmers, res.ndistinct
-    alg = {"scan_hist": nbases * 0.375,
-           "scan_scatter": nbases * 0.375 + N * W,
-           "refine": 3 * N * W,
-           "sortcount": N * W + U * (W + 4),
-           "compact": U * (W + 4) + res.ntable * (res.kmer_bytes + 2)}
+    st = eng.last_stats() if world == 1 else dict(path=0, supermers=0, entries=0, groups=0)
+    if st["path"] == 1:
+        # super-mer path: 24-byte super-mer records through the partition, 16-byte (key|count) entries through the sort
+        S, E = st["supermers"], st["entries"]
+        alg = {"super_scan": nbases * 0.375 + S * 24,
+               "super_partition": 6 * S * 24,
+               "bucket_count": S * 24 + E * 16,
+               "entry_partition": 3 * E * 16,
+               "refine": 3 * E * 16,
+               "sortcount": E * 16 + E * 20,
+               "compact": E * 20 + res.ntable * (res.kmer_bytes + 2)}
+        W = 16
+    else:
+        alg = {"scan_hist": nbases * 0.375,
+               "scan_scatter": nbases * 0.375 + N * W,
+               "refine": 3 * N * W,
+               "sortcount": N * W + U * (W + 4),
+               "compact": U * (W + 4) + res.ntable * (res.kmer_bytes + 2)}
     per_stage = {}
     for s, b in alg.items():
         ms = stage_ms.get(s, 0.0) / args.steps
         per_stage[s] = {"ms": round(ms, 3), "alg_gbytes": round(b / 1e9, 3), "gbs": round(b / 1e9 / (ms / 1e3), 1) if ms > 0 else None}
-    dom = max(("scan_hist", "scan_scatter", "refine", "sortcount", "compact"), key=lambda s: per_stage[s]["ms"])
+    dom = max(alg.keys(), key=lambda s: per_stage[s]["ms"])
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -378,7 +391,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(args, per_gpu), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),
-                           "record_bytes": W, "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
+                           "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
+                           "supermer_records": st["supermers"], "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),
                            "parallelism": "1 process/GPU; prefix-range all-to-all over NCCL" if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}

@@ -102,6 +102,10 @@ struct fkgpu_ctx
     /* profile lookup table built by finish when cfg.do_profile */
     DevBuf eprof, qoff, pkeys, pcnts, pidx, praw, pout, psrc, pdst, plen;
     long long ptab_n = 0; int ptab_B = 0; long long last_npos = 0;
+    int weighted = 0;      /* the records being sorted are distinct (key|count) entries of the super-mer path */
+    int res_nw = 2;        /* words per key of the staged / profile-table keys of the last result            */
+    int last_path = 0;     /* 0 = record path, 1 = super-mer path                                            */
+    long long st_super = 0, st_ent = 0, st_groups = 0;
     long long last_ndist = 0;
   };
 
@@ -192,6 +196,14 @@ extern "C" int fkgpu_read_counts(fkgpu_ctx *c, int64_t *per_tid)
       for (char x : c->tids[t].rcont) n += (x == 0);
       per_tid[t] = n;
     }
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_last_path(fkgpu_ctx *c) { return c ? c->last_path : 0; }
+
+extern "C" int fkgpu_last_stats(fkgpu_ctx *c, int64_t *v)
+{ if (c == NULL || v == NULL) return set_err(FKGPU_E_ARG,"fkgpu_last_stats: NULL argument");
+  v[0] = c->last_path; v[1] = c->st_super; v[2] = c->st_ent; v[3] = c->st_groups;
   return FKGPU_OK;
 }
 
@@ -379,6 +391,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   sp.ovf_cnt = &d_misc->ovf_cnt; sp.ovf_list = (u32 *) c->segs.p; sp.ovf_cap = (u32) std::min<long long>(gmax,0x7fffffffll);
   sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax;
   sp.tab_off = L.tab_off; sp.srt_off = L.srt_off; sp.srt2_off = L.srt2_off;
+  sp.weighted = (u32) c->weighted;
   CU(cudaFuncSetAttribute(k_sortcount<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) L.total));
   k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK();
   stage_end(c,FKGPU_ST_SORTCOUNT);
@@ -566,6 +579,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   res->ndistinct = (int64_t) hm.ndistinct;
   res->nkmers = (int64_t) ntot;
   c->last_ndist = (long long) hm.ndistinct;
+  c->res_nw = NW;
   return FKGPU_OK;
 }
 
@@ -602,9 +616,9 @@ static int choose_p2(fkgpu_ctx *c, int P1, int *P2)
   return FKGPU_OK;
 }
 
-static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true)
+static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true, int rec_words = 0)
 { const int nb1 = 1 << P1;
-  const size_t rb = (size_t) 8 * c->NW;
+  const size_t rb = (size_t) 8 * (rec_words ? rec_words : c->NW);
   if (c->bufA.ensure((size_t) (nub + 4) * rb) || (needB && c->bufB.ensure((size_t) (nub + 4) * rb)))
     return set_err(FKGPU_E_NOMEM,"out of device memory: two record buffers of %lld x %zu bytes",nub,rb);
   if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8)
@@ -731,6 +745,191 @@ static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long
   return FKGPU_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/*  super-mer path: reads -> 24-byte super-mer records bucketed by canonical minimizer -> per-bucket on-chip
+ *  expansion + hash count -> (only if a table / profiles are wanted) key-order sort of the distinct entries.   */
+
+static bool super_path_ok(fkgpu_ctx *c)
+{ static int forced = -1;
+  if (forced < 0) { const char *e = getenv("FKGPU_PATH"); forced = e ? (strcmp(e,"records") == 0 ? 1 : (strcmp(e,"super") == 0 ? 2 : 0)) : 0; }
+  if (forced == 1) return false;
+  return c->cfg.kmer >= 18 && c->cfg.kmer <= 56;
+}
+
+struct SuperCounters { u64 nrec, nkmers, nent; u32 fail, pad; };
+
+static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
+                              bool own_total, bool *fell_back)
+{ const int k = c->cfg.kmer;
+  const int m = std::min(16,k - 8);
+  const int w = k - m + 1;
+  int p2 = 1; while (2*p2 <= w) p2 <<= 1;
+  const int lmax = std::min(32,82 - k);
+  *fell_back = false;
+
+  /* bucket-id width from the expected # of super-mers; the exact count is known after the scan */
+  const long long sest = std::max<long long>(1,npos / 10);
+  int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
+  if (bbits > 22) bbits = 22;
+  const int P1 = std::min(bbits,11), P2 = bbits - P1;
+  const int nb1 = 1 << P1;
+
+  int rc = prepare_common(c,npos,P1,true,2);
+  if (rc) return rc;
+  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  Misc *d_misc = (Misc *) c->misc.p;
+
+  /* the two super-mer buffers live inside record buffer A (free until the final sort) */
+  const size_t abytes = (size_t) (npos + 4) * 16;
+  const u64 scap = (u64) (abytes / 2 / sizeof(Key<3>)) - 4;
+  Key<3> *SA = (Key<3> *) c->bufA.p;
+  Key<3> *SB = (Key<3> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+
+  if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  stage_begin(c,FKGPU_ST_SUPERSCAN);
+  if (ntiles > 0)
+    { SuperParams sp;
+      sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+      sp.k = k; sp.m = m; sp.w = w; sp.p2 = p2; sp.lmax = lmax; sp.bbits = bbits ? bbits : 1;
+      sp.out = SA; sp.cap = scap; sp.counter = &d_cnt->nrec;
+      const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_L) * 4;
+      CU(cudaFuncSetAttribute(k_super,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+      k_super<<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
+    }
+  stage_end(c,FKGPU_ST_SUPERSCAN);
+  SuperCounters hc;
+  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (hc.nrec > scap) { *fell_back = true; return FKGPU_OK; }        /* very short super-mers: use the record path */
+  const long long S = (long long) hc.nrec;
+  const int effbits = bbits ? bbits : 1;                              /* with bbits = 0 every id is 0 in a 1-bit field */
+  (void) effbits;
+
+  /* level 1 / level 2 partition of the super-mer records on the bucket id (top bits of w[0]) */
+  stage_begin(c,FKGPU_ST_SUPERPART);
+  const u64 *offs;
+  const Key<3> *recs;
+  long long mbuckets;
+  { const int b1 = bbits ? P1 : 0;
+    const int n1 = 1 << b1;
+    const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+    const long long nt = (S + TP_TILE(3) - 1) / TP_TILE(3);
+    CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (nb1 + 1) * 8,c->st));
+    if (nt > 0)
+      { k_tilepart<3,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>(SA,NULL,(u64) S,b1,(u64 *) c->hist1.p); KCHECK(); }
+    k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
+    if (nt > 0)
+      { CU(cudaFuncSetAttribute(k_tilepart<3,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+        k_tilepart<3,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>(SA,SB,(u64) S,b1,(u64 *) c->cur1.p); KCHECK();
+      }
+    offs = (const u64 *) c->off1.p; recs = SB; mbuckets = n1;
+    if (bbits && P2 > 0)
+      { mbuckets = (long long) n1 << P2;
+        if (c->off2.ensure((size_t) (mbuckets + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
+        const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<3>) + (size_t) (1 << P2) * 4;
+        CU(cudaFuncSetAttribute(k_refine<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+        k_refine<3><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(SB,SA,(const u64 *) c->off1.p,n1,b1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
+        offs = (const u64 *) c->off2.p; recs = SA;
+      }
+  }
+  stage_end(c,FKGPU_ST_SUPERPART);
+
+  /* groups of whole buckets, ~128 super-mers each */
+  const u32 TS = 128;
+  const long long gmax = S / TS + 2;
+  if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
+  u64 *gstart = (u64 *) c->gstart.p;
+  k_fill_u64<<<(unsigned) ((gmax + 1 + 255) / 256),256,0,c->st>>>(gstart,gmax + 1,offs + mbuckets); KCHECK();
+  k_groups<<<(unsigned) ((mbuckets + 1 + 255) / 256),256,0,c->st>>>(offs,mbuckets,TS,gstart,gmax); KCHECK();
+
+  const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
+  stage_begin(c,FKGPU_ST_BUCKET);
+  { BucketParams bp;
+    bp.recs = recs; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = k;
+    bp.g_hist = (u64 *) c->ghist.p; bp.g_maxinst = &d_misc->maxinst; bp.g_ndistinct = &d_misc->ndistinct;
+    bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
+    bp.g_fail = &d_cnt->fail;
+    u32 km[4]; make_kmask(k,km);
+    const size_t sm = (size_t) BC_DC*16 + (size_t) BC_CH*16 + (size_t) BC_TS*4 + (size_t) BC_DC*4 + (size_t) BC_SC*8*4 + (size_t) (BC_SC+1)*4 + 64;
+    CU(cudaFuncSetAttribute(k_bucket_count,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+    k_bucket_count<<<(unsigned) gmax,BC_TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK();
+  }
+  stage_end(c,FKGPU_ST_BUCKET);
+  Misc hm;
+  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(&hm,d_misc,sizeof(hm),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (hc.fail) return set_err(FKGPU_E_CUDA,"internal: %u bucket groups could not be counted on chip",hc.fail);
+  if (hc.nent > (u64) npos) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow");
+  static int verbose = -1;
+  if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (verbose)
+    fprintf(stderr,"[fkgpu] super-mer path: k=%d m=%d w=%d bbits=%d supermers=%llu (%.2f k-mers each) kmers=%llu distinct=%llu groups=%lld\n",
+            k,m,w,bbits,hc.nrec,hc.nrec ? (double) hc.nkmers / hc.nrec : 0.,hc.nkmers,hm.ndistinct,gmax);
+
+  res->ntable = 0; res->table = NULL; res->table_dev = NULL;
+  c->ptab_n = 0;
+  if (want_entries)
+    { /* key-order sort of the U distinct (key|count) entries: the record pipeline in weighted mode, E = buffer B is consumed */
+      const long long U = (long long) hc.nent;
+      int q1, q2;
+      choose_levels(U,&q1,&q2);
+      const int n1 = 1 << q1;
+      CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (std::max(n1,nb1) + 1) * 8,c->st));
+      CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
+      c->weighted = 1;
+      const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+      const long long nt = (U + TP_TILE(2) - 1) / TP_TILE(2);
+      if (c->hist1.ensure((size_t) (n1 + 1) * 8) || c->off1.ensure((size_t) (n1 + 1) * 8) || c->cur1.ensure((size_t) (n1 + 1) * 8))
+        { c->weighted = 0; return set_err(FKGPU_E_NOMEM,"out of device memory"); }
+      stage_begin(c,FKGPU_ST_ENTPART);
+      if (nt > 0)
+        { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) c->bufB.p,NULL,(u64) U,q1,(u64 *) c->hist1.p); KCHECK(); }
+      k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
+      rc = choose_p2(c,q1,&q2);
+      if (rc) { c->weighted = 0; return rc; }
+      if (nt > 0)
+        { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+          k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) c->bufB.p,(Key<2> *) c->bufA.p,(u64) U,q1,(u64 *) c->cur1.p); KCHECK();
+        }
+      stage_end(c,FKGPU_ST_ENTPART);
+      rc = count_from_level1<2>(c,std::max<long long>(U,1),q1,q2,fetch_table,res,c->bufA.p,c->bufB.p);
+      c->weighted = 0;
+      if (rc) return rc;
+    }
+  else
+    { CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      res->hist = c->h_hist;
+    }
+  res->max_inst = (int64_t) hm.maxinst;
+  res->ndistinct = (int64_t) hm.ndistinct;
+  res->nkmers = (int64_t) hc.nkmers;
+  c->last_ndist = (long long) hm.ndistinct;
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  c->last_path = 1;
+  c->st_super = (long long) hc.nrec; c->st_ent = want_entries ? (long long) hc.nent : 0; c->st_groups = gmax;
+  return FKGPU_OK;
+}
+
+static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res, bool own_total)
+{ c->last_path = 0;
+  if (super_path_ok(c))
+    { bool fb = false;
+      int rc = count_packed_super(c,d_seq,d_val,npos,fetch_table,res,own_total,&fb);
+      if (rc || !fb) return rc;
+      memset(c->used,0,sizeof(c->used));
+      own_total = true;
+    }
+  return (c->NW == 1) ? count_packed_t<1>(c,d_seq,d_val,npos,fetch_table,res,own_total)
+                      : count_packed_t<2>(c,d_seq,d_val,npos,fetch_table,res,own_total);
+}
+
 static void init_result(fkgpu_ctx *c, fkgpu_result *res)
 { memset(res,0,sizeof(*res));
   res->kmer = c->cfg.kmer;
@@ -746,9 +945,7 @@ extern "C" int fkgpu_count_packed(fkgpu_ctx *c, const uint32_t *d_seq, const uin
   CU(cudaSetDevice(c->cfg.device));
   init_result(c,res);
   res->nbases = npos;
-  int rc = (c->NW == 1) ? count_packed_t<1>(c,d_seq,d_val,npos,fetch_table,res,true)
-                        : count_packed_t<2>(c,d_seq,d_val,npos,fetch_table,res,true);
-  return rc;
+  return count_packed_any(c,d_seq,d_val,npos,fetch_table,res,true);
 }
 
 extern "C" int fkgpu_pack_ascii_dev(fkgpu_ctx *c, const char *d_ascii, int64_t npos, uint32_t *d_seq, uint32_t *d_val)
@@ -810,9 +1007,7 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
         }
     }
   stage_end(c,FKGPU_ST_PACK);
-  rc = (c->NW == 1) ? count_packed_t<1>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false)
-                    : count_packed_t<2>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false);
-  return rc;
+  return count_packed_any(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -856,7 +1051,7 @@ static int count_records_t(fkgpu_ctx *c, void *d_records, long long n, int fetch
   const int nb1 = 1 << P1;
   const size_t smh = (size_t) (nb1 + (nb1 & 1)) * 4;
   const size_t sms = smh + (size_t) nb1 * 8;
-  const long long ntiles = (n + TP_TILE - 1) / TP_TILE;
+  const long long ntiles = (n + TP_TILE(NW) - 1) / TP_TILE(NW);
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
   if (ntiles > 0)
     { stage_begin(c,FKGPU_ST_L2HIST);
@@ -944,5 +1139,5 @@ extern "C" int fkgpu_profiles(fkgpu_ctx *c, int64_t *nreads, const int64_t **off
   if (!c->cfg.do_profile) return set_err(FKGPU_E_STATE,"fkgpu_profiles: the context was created without do_profile");
   if (!c->finished) return set_err(FKGPU_E_STATE,"fkgpu_profiles: call fkgpu_finish first");
   CU(cudaSetDevice(c->cfg.device));
-  return (c->NW == 1) ? profiles_t<1>(c,nreads,off,prof) : profiles_t<2>(c,nreads,off,prof);
+  return (c->res_nw == 1) ? profiles_t<1>(c,nreads,off,prof) : profiles_t<2>(c,nreads,off,prof);
 }

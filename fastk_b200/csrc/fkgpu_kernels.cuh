@@ -27,7 +27,7 @@ namespace fk {
 typedef unsigned long long u64;
 typedef uint32_t           u32;
 
-template<int NW> struct __align__(8 * NW) Key { u64 w[NW]; };
+template<int NW> struct __align__((NW == 2) ? 16 : 8) Key { u64 w[NW]; };
 
 template<int NW> __device__ __forceinline__ bool key_eq(const Key<NW> &a, const Key<NW> &b)
 { bool e = true;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ 
       if (b >= nb1) break;
       const u64 start = off1[b];
       const u64 n = off1[b+1] - start;
-      const u32 shift = (NW == 1) ? (u32) (start & 1ull) : 0u;
+      const u32 shift = (NW & 1) ? (u32) (start & 1ull) : 0u;
       const u64 ntl = (n + REF_TB - 1) / REF_TB;
       for (int i = threadIdx.x; i < nd; i += REF_TPB) s_cnt[i] = 0;
       __syncthreads();
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ 
             { u64 r0 = start + t * REF_TB;
               u64 cnt = n - t * REF_TB; if (cnt > REF_TB) cnt = REF_TB;
               u64 a0 = r0 - shift;
-              u64 len = cnt + shift; if (NW == 1) len = (len + 1) & ~1ull;
+              u64 len = cnt + shift; if (NW & 1) len = (len + 1) & ~1ull;
               u32 bytes = (u32) (len * sizeof(Key<NW>));
               u32 sl = qq % REF_ST;
               mbar_expect_tx(&s_full[sl],bytes);
@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ 
  *  the input is records rather than reads: the multi-GPU path after the exchange).                   */
 
 #define TP_TPB 256
-#define TP_RPT 16
-#define TP_TILE (TP_TPB*TP_RPT)
+#define TP_RPT(NW) ((NW) == 3 ? 8 : 16)
+#define TP_TILE(NW) (TP_TPB*TP_RPT(NW))
 
 template<int NW, bool SCATTER>
 __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__ src, Key<NW> *__restrict__ dst,
@@ -609,18 +609,19 @@ __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__
   u64 *s_base = (u64 *) (s_cnt + nd + (nd & 1));
   for (int i = threadIdx.x; i < nd; i += TP_TPB) s_cnt[i] = 0;
   __syncthreads();
-  const u64 t0 = (u64) blockIdx.x * TP_TILE;
-  Key<NW> r[TP_RPT];
-  u32 rk[TP_RPT/2];
+  constexpr int RPT = TP_RPT(NW);
+  const u64 t0 = (u64) blockIdx.x * TP_TILE(NW);
+  Key<NW> r[RPT];
+  u32 rk[RPT/2];
 #pragma unroll
-  for (int u = 0; u < TP_RPT/2; u++) rk[u] = 0;
+  for (int u = 0; u < RPT/2; u++) rk[u] = 0;
 #pragma unroll
-  for (int u = 0; u < TP_RPT; u++)
+  for (int u = 0; u < RPT; u++)
     { u64 i = t0 + u*TP_TPB + threadIdx.x;
       if (i < n) r[u] = src[i];
     }
 #pragma unroll
-  for (int u = 0; u < TP_RPT; u++)
+  for (int u = 0; u < RPT; u++)
     { u64 i = t0 + u*TP_TPB + threadIdx.x;
       if (i < n)
         { u32 rr = atomicAdd(&s_cnt[nbits ? key_digit<NW>(r[u],0,nbits) : 0u],1u);
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__
   if (!SCATTER) return;
   __syncthreads();
 #pragma unroll
-  for (int u = 0; u < TP_RPT; u++)
+  for (int u = 0; u < RPT; u++)
     { u64 i = t0 + u*TP_TPB + threadIdx.x;
       if (i < n)
         { u32 d = nbits ? key_digit<NW>(r[u],0,nbits) : 0u;
@@ -691,6 +692,7 @@ struct SortCountParams
     u32         cap;                     /* C                                                 */
     u32         tab_off, srt_off;        /* byte offsets of the hash table / sort array in smem */
     u32         srt2_off;                /* entries: second sort array inside srt (>= SC_RANKMAX free) */
+    u32         weighted;                /* 1: records are distinct (key | count in the low 16 bits): sort only */
     u32         cutoff;
     long long   nitems;
   };
@@ -773,6 +775,27 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   __syncthreads();
   rec += shift;
 
+  if (p.weighted)
+    { /* every record is already a distinct key carrying its count: nothing to merge, only to order */
+      const Key<NW> k0 = rec[0];
+      u32 orw[2*NW];
+#pragma unroll
+      for (int m = 0; m < 2*NW; m++) orw[m] = 0;
+      for (u32 i = threadIdx.x; i < n; i += SC_TPB)
+        { const Key<NW> key = rec[i];
+#pragma unroll
+          for (int m = 0; m < NW; m++)
+            { u64 x = key.w[m] ^ k0.w[m];
+              orw[2*m] |= (u32) (x >> 32); orw[2*m+1] |= (u32) x;
+            }
+        }
+#pragma unroll
+      for (int m = 0; m < 2*NW; m++)
+        { u32 x = __reduce_or_sync(0xffffffffu,orw[m]);
+          if ((threadIdx.x & 31) == 0 && x) atomicOr(&s_or[m],x);
+        }
+    }
+  else
   /* hash count: table slot = (owner record index << 16) | multiplicity */
   { const Key<NW> k0 = rec[0];
     u32 orw[2*NW];
@@ -822,6 +845,12 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   }
 
   /* gather the distinct keys */
+  if (p.weighted)
+    { for (u32 i = threadIdx.x; i < n; i += SC_TPB)
+        srt[i] = ((key_bits64<NW>(rec[i],pc) >> 32) << 32) | ((u64) i << 16);
+      if (threadIdx.x == 0) s_D = n;
+    }
+  else
   for (u32 s = threadIdx.x; s < H; s += SC_TPB)
     { u32 v = table[s];
       if (v != SC_EMPTY)
@@ -881,10 +910,17 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   for (u32 q = threadIdx.x; q < D; q += SC_TPB)
     { u32 v = (u32) fin[q];
       u32 c = v & 0xffffu;
-      stage[r0 + q] = rec[v >> 16];
+      Key<NW> key = rec[v >> 16];
+      if (p.weighted)
+        { c = (u32) (key.w[NW-1] & 0xffffull);
+          key.w[NW-1] &= ~0xffffull;
+        }
+      stage[r0 + q] = key;
       p.stage_cnt[r0 + q] = c;
-      if (c < SC_SMALLHIST) atomicAdd(&s_hist[c],1u);
-      else atomicAdd(p.g_hist + c,1ull);          /* c <= cap < 32767: never saturates here */
+      if (!p.weighted)
+        { if (c < SC_SMALLHIST) atomicAdd(&s_hist[c],1u);
+          else atomicAdd(p.g_hist + c,1ull);      /* c <= cap < 32767: never saturates here */
+        }
       npass += (c >= p.cutoff) ? 1u : 0u;
     }
 #pragma unroll
@@ -898,7 +934,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   if (threadIdx.x == 0)
     { p.e_all[g] = D;
       p.e_pass[g] = s_pass;
-      atomicAdd(p.g_ndistinct,(u64) D);
+      if (!p.weighted) atomicAdd(p.g_ndistinct,(u64) D);
     }
 }
 
@@ -1024,6 +1060,330 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
             }
           o += __popc(m);
         }
+    }
+}
+
+/* ============================================================================================== */
+/*  Super-mer front end (the reference's own idea, split.c:1016-1393 / Appendix D of SURVEY.md, re-cut for a GPU):
+ *  consecutive k-mers that share a canonical minimizer travel together as one 24-byte record
+ *      w[0] = [bucket:24][len-1:6][first 17 bases:34]   w[1], w[2] = the next 64 bases
+ *  so the partition passes move ~1.6 B per k-mer instead of 16.  Every instance of a canonical k-mer has the same
+ *  minimizer (the minimum over BOTH strands' m-mers under a bijective order hash), hence the same bucket: each
+ *  bucket can be counted on chip with no cross-bucket merge.                                                   */
+
+#define SUP_L     (SCAN_TILE + 64)
+#define SUP_BBITS 24
+#define SUP_LBITS 6
+
+struct SuperParams
+  { const u32 *seq; const u32 *val;
+    long long  npos, nseqw, nvalw;
+    int        k, m, w, p2, lmax, bbits;      /* w = k-m+1 window of m-mers, p2 = largest power of two <= w */
+    Key<3>    *out; u64 cap;
+    u64       *counter;                       /* [0] records emitted, [1] k-mers covered                    */
+  };
+
+__device__ __forceinline__ u32 mix32(u32 x)   /* bijective (murmur3 finaliser) */
+{ x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
+{ extern __shared__ u32 s_dyn[];
+  u32 *s_seq = s_dyn;
+  u32 *s_val = s_seq + SCAN_SEQW;
+  u32 *s_a   = s_val + SCAN_VALW;           /* [SUP_L] */
+  u32 *s_b   = s_a + SUP_L;                 /* [SUP_L] */
+  __shared__ u32 s_warp[SCAN_TPB/32];
+  __shared__ u64 s_base;
+
+  ScanParams sp; sp.seq = p.seq; sp.val = p.val; sp.nseqw = p.nseqw; sp.nvalw = p.nvalw;
+  scan_load_tile(sp,blockIdx.x,s_seq,s_val);
+  __syncthreads();
+
+  /* order key of the canonical m-mer at every tile position (each computed once per tile) */
+  const int m2 = 2*p.m;
+  const u32 mmask = (m2 == 32) ? 0xffffffffu : ((1u << m2) - 1u);
+  const int need = SCAN_TILE + p.w - 1;
+  for (int i = threadIdx.x; i < need; i += SCAN_TPB)
+    { const u32 *s = s_seq + SCAN_LHALO + (i >> 4);
+      u32 x = __funnelshift_l(s[1],s[0],2*(i & 15));          /* 16 bases starting at position i, left aligned */
+      u32 f = x >> (32 - m2);
+      u32 r = rc32(f << (32 - m2)) & mmask;
+      s_a[i] = mix32(f < r ? f : r);
+    }
+  __syncthreads();
+  /* sliding-window minimum of width w by doubling: after the loop cur[i] = min o[i .. i+p2) */
+  u32 *cur = s_a, *nxt = s_b;
+  int len = need;
+  for (int st = 1; 2*st <= p.w; st <<= 1)
+    { for (int i = threadIdx.x; i < len - st; i += SCAN_TPB)
+        { u32 a = cur[i], b = cur[i+st];
+          nxt[i] = a < b ? a : b;
+        }
+      len -= st;
+      __syncthreads();
+      u32 *t = cur; cur = nxt; nxt = t;
+    }
+  /* bucket of every k-mer start of this thread -> nxt[] */
+  const int base = threadIdx.x * SCAN_PPT;
+  const int d = p.w - p.p2;
+#pragma unroll 8
+  for (int j = 0; j < SCAN_PPT; j++)
+    { u32 a = cur[base+j], b = cur[base+j+d];
+      u32 mn = a < b ? a : b;
+      nxt[base+j] = (mn * 0x9E3779B1u) >> (32 - p.bbits);
+    }
+  V96 v; v.a = s_val[threadIdx.x]; v.b = s_val[threadIdx.x+1]; v.c = s_val[threadIdx.x+2];
+  const u32 ok = window_ok(v,p.k);
+  const u32 *bk = nxt + base;            /* only this thread reads/writes its own 32 entries: no barrier needed */
+
+  /* pass A: count this thread's super-mers */
+  u32 nrun = 0;
+  for (int j = 0; j < SCAN_PPT; )
+    { if (!((ok >> (31-j)) & 1u)) { j++; continue; }
+      const u32 b = bk[j];
+      int e = j+1;
+      while (e < SCAN_PPT && e-j < p.lmax && ((ok >> (31-e)) & 1u) && bk[e] == b) e++;
+      nrun++; j = e;
+    }
+  u32 incl = nrun;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  u32 nk = __popc(ok);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu,nk,o);
+  __syncthreads();
+  u32 woff = 0, tot = 0;
+  for (int i = 0; i < SCAN_TPB/32; i++)
+    { u32 x = s_warp[i];
+      if (i < (int) (threadIdx.x >> 5)) woff += x;
+      tot += x;
+    }
+  if ((threadIdx.x & 31) == 0 && nk) atomicAdd(p.counter + 1,(u64) nk);
+  if (threadIdx.x == 0) s_base = tot ? atomicAdd(p.counter,(u64) tot) : 0ull;
+  __syncthreads();
+  u64 pos = s_base + woff + incl - nrun;
+  if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and retries */
+
+  /* pass B: emit */
+  for (int j = 0; j < SCAN_PPT; )
+    { if (!((ok >> (31-j)) & 1u)) { j++; continue; }
+      const u32 b = bk[j];
+      int e = j+1;
+      while (e < SCAN_PPT && e-j < p.lmax && ((ok >> (31-e)) & 1u) && bk[e] == b) e++;
+      const int a = base + j;                            /* tile-local position of the first base */
+      const u32 *s = s_seq + SCAN_LHALO + (a >> 4);
+      const int sh = 2*(a & 15);
+      u32 x[6];
+#pragma unroll
+      for (int t = 0; t < 6; t++) x[t] = __funnelshift_l(s[t+1],s[t],sh);
+      /* 162 base bits: 34 into w0, then 2 x 64 */
+      u64 B0 = ((u64) x[0] << 32) | x[1], B1 = ((u64) x[2] << 32) | x[3], B2 = ((u64) x[4] << 32) | x[5];
+      Key<3> rec;
+      rec.w[0] = ((u64) b << (64 - p.bbits)) | ((u64) (e-j-1) << (64 - SUP_BBITS - SUP_LBITS)) | (B0 >> 30);
+      rec.w[1] = (B0 << 34) | (B1 >> 30);
+      rec.w[2] = (B1 << 34) | (B2 >> 30);
+      p.out[pos++] = rec;
+      j = e;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  k_bucket_count: one CTA per group of whole minimizer buckets.  Streams the group's super-mers in chunks of
+ *  BC_SC records: expand every k-mer (canonical form as in k_scan), hash-count it in a shared-memory table whose
+ *  distinct keys live in a pool that persists across chunks.  Emits histogram contributions and, if wanted, the
+ *  distinct (key | saturated count in the low 16 bits) records for the final key-order sort.
+ *  A group whose distinct keys overflow the pool is redone in 2x more rounds, each round taking the k-mers whose
+ *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
+
+#define BC_TPB 256
+#define BC_SC   32                      /* super-mers per chunk                                  */
+#define BC_CH   (BC_SC*32)              /* <= this many k-mer instances per chunk                 */
+#define BC_TS   4096                    /* hash slots                                            */
+#define BC_DC   2048                    /* distinct-key pool                                     */
+#define BC_EMPTY 0xffffffffu
+#define BC_PERS  0x80000000u
+
+struct BucketParams
+  { const Key<3> *recs;
+    const u64 *starts; const u64 *ends; long long nitems;
+    int        k;
+    u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
+    Key<2>    *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL)  */
+    u32       *g_fail;                                   /* set if a group could not be counted */
+  };
+
+/* canonical k-mer number j of a super-mer whose base string is b[0..5] (192 bits, left aligned) */
+__device__ __forceinline__ Key<2> supermer_kmer(const u32 *b, int j, int k, const u32 *kmask)
+{ const int q = j >> 4, sh = 2*(j & 15);
+  u32 F[4], Z[4], G[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) F[t] = __funnelshift_l(b[q+t+1],b[q+t],sh) & kmask[t];
+  /* reverse complement of the 64 base slots, then drop the (64-k) padding slots off the top */
+#pragma unroll
+  for (int t = 0; t < 4; t++) Z[t] = rc32(F[3-t]);
+  const int s = 128 - 2*k, sq = s >> 5, sr = s & 31;
+  u32 Y[8];
+#pragma unroll
+  for (int t = 0; t < 4; t++) { Y[t] = Z[t]; Y[t+4] = 0; }
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+    { u32 hi, lo;
+      if (sq == 0)      { hi = Y[t];   lo = Y[t+1]; }
+      else if (sq == 1) { hi = Y[t+1]; lo = Y[t+2]; }
+      else if (sq == 2) { hi = Y[t+2]; lo = Y[t+3]; }
+      else              { hi = Y[t+3]; lo = Y[t+4]; }
+      G[t] = __funnelshift_l(lo,hi,sr) & kmask[t];
+    }
+  bool lt = false, dec = false;
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+    if (!dec && F[t] != G[t]) { lt = G[t] < F[t]; dec = true; }
+  Key<2> key;
+  key.w[0] = lt ? (((u64) G[0] << 32) | G[1]) : (((u64) F[0] << 32) | F[1]);
+  key.w[1] = lt ? (((u64) G[2] << 32) | G[3]) : (((u64) F[2] << 32) | F[3]);
+  return key;
+}
+
+__global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
+{ extern __shared__ __align__(16) unsigned char s_raw[];
+  Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]            */
+  Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]            */
+  u32    *slot  = (u32 *) (rec + BC_CH);                             /* [BC_TS]            */
+  u32    *ocnt  = slot + BC_TS;                                      /* [BC_DC]            */
+  u32    *sbase = ocnt + BC_DC;                                      /* [BC_SC][8] base words */
+  u32    *spre  = sbase + BC_SC*8;                                   /* [BC_SC+1] prefix of lengths */
+  __shared__ u32 s_nd, s_ovf, s_hist[SC_SMALLHIST];
+  __shared__ u64 s_ebase;
+
+  const long long g = blockIdx.x;
+  if (g >= p.nitems) return;
+  const u64 r0 = p.starts[g], r1 = p.ends[g];
+  if (r1 <= r0) return;
+  const u32 kmask[4] = { km0, km1, km2, km3 };
+
+  /* work stack of (rounds, residue) classes: a class whose distinct keys overflow the pool splits in two */
+  u32 stR[28], stD[28];
+  int sp = 1;
+  stR[0] = 1; stD[0] = 0;
+  while (sp > 0)
+    { sp--;
+      const u32 rounds = stR[sp], rd = stD[sp];
+      bool failed = false;
+      for (u32 i = threadIdx.x; i < BC_TS; i += BC_TPB) slot[i] = BC_EMPTY;
+      for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB) s_hist[i] = 0;
+      if (threadIdx.x == 0) { s_nd = 0; s_ovf = 0; }
+      __syncthreads();
+      for (u64 c0 = r0; c0 < r1; c0 += BC_SC)
+        { const u32 ns = (u32) ((r1 - c0 < BC_SC) ? (r1 - c0) : BC_SC);
+          /* load the chunk's super-mers: warp 0 builds the length prefix and unpacks the base words */
+          if (threadIdx.x < BC_SC)
+            { u32 l = 0;
+              if (threadIdx.x < ns)
+                { const Key<3> sm = p.recs[c0 + threadIdx.x];
+                  l = (u32) ((sm.w[0] >> (64 - SUP_BBITS - SUP_LBITS)) & 63u) + 1u;
+                  const u64 B0 = (sm.w[0] << 30) | (sm.w[1] >> 34);
+                  const u64 B1 = (sm.w[1] << 30) | (sm.w[2] >> 34);
+                  const u64 B2 = (sm.w[2] << 30);
+                  u32 *d = sbase + threadIdx.x*8;
+                  d[0] = (u32) (B0 >> 32); d[1] = (u32) B0; d[2] = (u32) (B1 >> 32); d[3] = (u32) B1;
+                  d[4] = (u32) (B2 >> 32); d[5] = (u32) B2; d[6] = 0; d[7] = 0;
+                }
+              u32 incl = l;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1)
+                { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+                  if ((int) threadIdx.x >= o) incl += y;
+                }
+              spre[threadIdx.x+1] = incl;
+              if (threadIdx.x == 0) spre[0] = 0;
+            }
+          __syncthreads();
+          const u32 ninst = spre[BC_SC];
+          /* expand: instance i -> (super-mer, offset) by binary search in the prefix */
+          for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
+            { u32 lo = 0, hi = BC_SC;
+              while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= i) lo = mid; else hi = mid; }
+              rec[i] = supermer_kmer(sbase + lo*8,(int) (i - spre[lo]),p.k,kmask);
+            }
+          __syncthreads();
+          /* insert */
+          for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
+            { const Key<2> key = rec[i];
+              const u32 h = key_hash<2>(key);
+              if (((h >> 20) & (rounds-1)) != rd) continue;
+              u32 x = h & (BC_TS-1);
+              for (u32 step = 0; ; step++)
+                { if (step >= BC_TS) { s_ovf = 1; break; }
+                  u32 v = ((volatile u32 *) slot)[x];
+                  if (v == BC_EMPTY)
+                    { u32 old = atomicCAS(&slot[x],BC_EMPTY,(i << 16) | 1u);
+                      if (old == BC_EMPTY) break;
+                      v = old;
+                    }
+                  if (v & BC_PERS)
+                    { const u32 pi = v & ~BC_PERS;
+                      if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
+                    }
+                  else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
+                  x = (x+1) & (BC_TS-1);
+                }
+            }
+          __syncthreads();
+          /* migrate this chunk's new owners into the pool */
+          for (u32 x = threadIdx.x; x < BC_TS; x += BC_TPB)
+            { const u32 v = slot[x];
+              if (v != BC_EMPTY && !(v & BC_PERS))
+                { const u32 pi = atomicAdd(&s_nd,1u);
+                  if (pi < BC_DC)
+                    { pool[pi] = rec[v >> 16];
+                      ocnt[pi] = v & 0xffffu;
+                      slot[x] = BC_PERS | pi;
+                    }
+                  else s_ovf = 1;
+                }
+            }
+          __syncthreads();
+          if (s_ovf) { failed = true; break; }
+        }
+      if (failed)
+        { __syncthreads();
+          if (rounds >= 4096 || sp + 2 > 28)
+            { if (threadIdx.x == 0) atomicAdd(p.g_fail,1u);
+              return;
+            }
+          stR[sp] = 2*rounds; stD[sp] = rd + rounds; sp++;
+          stR[sp] = 2*rounds; stD[sp] = rd; sp++;
+          continue;
+        }
+      /* emit this class's distinct keys */
+      const u32 nd = s_nd;
+      if (threadIdx.x == 0 && p.ent != NULL) s_ebase = nd ? atomicAdd(p.ent_counter,(u64) nd) : 0ull;
+      __syncthreads();
+      for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
+        { const u32 c = ocnt[i];
+          const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
+          if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
+          else atomicAdd(p.g_hist + cs,1ull);
+          if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
+          if (p.ent != NULL && s_ebase + i < p.ent_cap)
+            { Key<2> e = pool[i];
+              e.w[1] |= (u64) cs;
+              p.ent[s_ebase + i] = e;
+            }
+        }
+      __syncthreads();
+      for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB)
+        { u32 c = s_hist[i];
+          if (c) atomicAdd(p.g_hist + i,(u64) c);
+        }
+      if (threadIdx.x == 0) atomicAdd(p.g_ndistinct,(u64) nd);
+      __syncthreads();
     }
 }
 

@@ -7,8 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libfastk_gpu.so")
 
 HIST_BINS = 32768
-NSTAGES = 8
-STAGES = ["pack", "scan_hist", "scan_scatter", "l1_hist_records", "refine", "sortcount", "compact", "profile"]
+NSTAGES = 12
+STAGES = ["pack", "scan_hist", "scan_scatter", "l1_hist_records", "refine", "sortcount", "compact", "profile",
+          "super_scan", "super_partition", "bucket_count", "entry_partition"]
 PACK_PAD = 16
 
 
@@ -78,6 +79,10 @@ def load_library(path=None):
     lib.fkgpu_count_records.restype = C.c_int
     lib.fkgpu_launch_count.argtypes = [vp]
     lib.fkgpu_launch_count.restype = i64
+    lib.fkgpu_last_stats.argtypes = [vp, C.POINTER(i64)]
+    lib.fkgpu_last_stats.restype = C.c_int
+    lib.fkgpu_last_path.argtypes = [vp]
+    lib.fkgpu_last_path.restype = C.c_int
     lib.fkgpu_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     lib.fkgpu_stage_times.restype = C.c_int
     if path is None:
@@ -88,7 +93,7 @@ def load_library(path=None):
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
            "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
-           "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_stage_times"]
+           "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times"]
 
 
 class FkResult:
@@ -185,6 +190,14 @@ class FastKGPU:
         self._chk(self.lib.fkgpu_count_records(self.h, d_rec_ptr, n, 1 if fetch_table else 0, C.byref(r)),
                   "fkgpu_count_records")
         return FkResult(r, copy_table)
+
+    def last_stats(self):
+        v = (C.c_int64 * 4)()
+        self._chk(self.lib.fkgpu_last_stats(self.h, v), "fkgpu_last_stats")
+        return dict(path=int(v[0]), supermers=int(v[1]), entries=int(v[2]), groups=int(v[3]))
+
+    def last_path(self):
+        return int(self.lib.fkgpu_last_path(self.h))
 
     def launch_count(self):
         return int(self.lib.fkgpu_launch_count(self.h))

@@ -142,8 +142,10 @@ int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int 
 /*  Instrumentation for bench.py: # of kernel launches issued by this context so far, and the
  *  accumulated CUDA-event time / algorithmic bytes of the dominant kernel family (final sort+count). */
 int64_t fkgpu_launch_count(fkgpu_ctx *ctx);
+int     fkgpu_last_stats(fkgpu_ctx *ctx, int64_t *v /*[4]: path, super-mer records, distinct entries sorted, work groups*/);
+int     fkgpu_last_path(fkgpu_ctx *ctx);     /* which pipeline served the last count: 0 = 16-byte records, 1 = super-mers */
 int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double *bytes /*[FKGPU_NSTAGES]*/);
-#define FKGPU_NSTAGES 8
+#define FKGPU_NSTAGES 12
 /* stage ids */
 #define FKGPU_ST_PACK      0
 #define FKGPU_ST_SCANHIST  1
@@ -153,6 +155,11 @@ int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double 
 #define FKGPU_ST_SORTCOUNT 5
 #define FKGPU_ST_COMPACT   6
 #define FKGPU_ST_PROFILE   7
+/* super-mer path (k in 18..56): stages 5/6 then only order the distinct entries */
+#define FKGPU_ST_SUPERSCAN 8     /* reads -> super-mer records                       */
+#define FKGPU_ST_SUPERPART 9     /* bucket partition of the super-mer records        */
+#define FKGPU_ST_BUCKET    10    /* on-chip expansion + hash count per bucket group  */
+#define FKGPU_ST_ENTPART   11    /* prefix partition of the distinct (key|count) entries */
 
 #ifdef __cplusplus
 }
