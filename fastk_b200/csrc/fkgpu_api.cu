@@ -853,7 +853,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(k,km);
-    const size_t sm = (size_t) BC_DC*16 + (size_t) BC_CH*16 + (size_t) BC_TS*4 + (size_t) BC_DC*4 + (size_t) BC_SC*8*4 + (size_t) (BC_SC+1)*4 + 64;
+    const size_t sm = (size_t) BC_DC*16 + (size_t) BC_CH*16 + (size_t) BC_TS*4 + (size_t) BC_DC*4 + (size_t) BC_GC*8*4 + (size_t) (BC_GC+2)*4 + (size_t) BC_CH*2 + 64;
     CU(cudaFuncSetAttribute(k_bucket_count,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
     k_bucket_count<<<(unsigned) gmax,BC_TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK();
   }

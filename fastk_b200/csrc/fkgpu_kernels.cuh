@@ -1071,7 +1071,7 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
  *  minimizer (the minimum over BOTH strands' m-mers under a bijective order hash), hence the same bucket: each
  *  bucket can be counted on chip with no cross-bucket merge.                                                   */
 
-#define SUP_L     (SCAN_TILE + 64)
+#define SUP_L     (SCAN_TILE + SCAN_TILE/32 + 64)   /* room for the +1-per-32 skew that keeps per-thread rows conflict-free */
 #define SUP_BBITS 24
 #define SUP_LBITS 6
 
@@ -1125,28 +1125,43 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
       __syncthreads();
       u32 *t = cur; cur = nxt; nxt = t;
     }
-  /* bucket of every k-mer start of this thread -> nxt[] */
-  const int base = threadIdx.x * SCAN_PPT;
+  /* bucket id of every k-mer start, stored skewed (+1 word per 32) so that a thread's own row is conflict-free */
   const int d = p.w - p.p2;
-#pragma unroll 8
-  for (int j = 0; j < SCAN_PPT; j++)
-    { u32 a = cur[base+j], b = cur[base+j+d];
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_TPB)
+    { u32 a = cur[i], b = cur[i+d];
       u32 mn = a < b ? a : b;
-      nxt[base+j] = (mn * 0x9E3779B1u) >> (32 - p.bbits);
+      nxt[i + (i >> 5)] = (mn * 0x9E3779B1u) >> (32 - p.bbits);
     }
   V96 v; v.a = s_val[threadIdx.x]; v.b = s_val[threadIdx.x+1]; v.c = s_val[threadIdx.x+2];
-  const u32 ok = window_ok(v,p.k);
-  const u32 *bk = nxt + base;            /* only this thread reads/writes its own 32 entries: no barrier needed */
+  const u32 ok = window_ok(v,p.k);                  /* bit 31-j = k-mer j of this thread is legal */
+  __syncthreads();
+  const u32 *bk = nxt + threadIdx.x * (SCAN_PPT + 1);
+  const int base = threadIdx.x * SCAN_PPT;
 
-  /* pass A: count this thread's super-mers */
-  u32 nrun = 0;
-  for (int j = 0; j < SCAN_PPT; )
-    { if (!((ok >> (31-j)) & 1u)) { j++; continue; }
-      const u32 b = bk[j];
-      int e = j+1;
-      while (e < SCAN_PPT && e-j < p.lmax && ((ok >> (31-e)) & 1u) && bk[e] == b) e++;
-      nrun++; j = e;
-    }
+  /* cont bit j: k-mer j continues the super-mer of k-mer j-1 (both legal, same bucket) */
+  u32 same = 0;
+  { u32 prev = bk[0];
+#pragma unroll
+    for (int j = 1; j < SCAN_PPT; j++)
+      { u32 x = bk[j];
+        same |= (x == prev ? 1u : 0u) << (31-j);
+        prev = x;
+      }
+  }
+  const u32 cont = ok & (ok >> 1) & same;
+  u32 starts = ok & ~cont;                          /* bit 31-j = a super-mer starts at j */
+  /* a run longer than lmax is cut: walk the runs once to add the extra starts (lmax >= 26, so at most one cut each) */
+  { u32 todo = starts;
+    while (todo)
+      { const int a = __clz(todo);
+        todo &= ~(0x80000000u >> a);
+        const u32 after = (a == 31) ? 0u : (0xffffffffu >> (a+1));
+        const u32 stop = (starts | ~ok) & after;    /* next start or first illegal position after a */
+        const int e = stop ? __clz(stop) : SCAN_PPT;
+        if (e - a > p.lmax) { starts |= 0x80000000u >> (a + p.lmax); todo |= 0x80000000u >> (a + p.lmax); }
+      }
+  }
+  const u32 nrun = __popc(starts);
   u32 incl = nrun;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1)
@@ -1168,14 +1183,16 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
   if (threadIdx.x == 0) s_base = tot ? atomicAdd(p.counter,(u64) tot) : 0ull;
   __syncthreads();
   u64 pos = s_base + woff + incl - nrun;
-  if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and retries */
+  if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and falls back */
 
-  /* pass B: emit */
-  for (int j = 0; j < SCAN_PPT; )
-    { if (!((ok >> (31-j)) & 1u)) { j++; continue; }
+  u32 todo = starts;
+  while (todo)
+    { const int j = __clz(todo);
+      todo &= ~(0x80000000u >> j);
+      const u32 after = (j == 31) ? 0u : (0xffffffffu >> (j+1));
+      const u32 stop = (starts | ~ok) & after;
+      const int e = stop ? __clz(stop) : SCAN_PPT;
       const u32 b = bk[j];
-      int e = j+1;
-      while (e < SCAN_PPT && e-j < p.lmax && ((ok >> (31-e)) & 1u) && bk[e] == b) e++;
       const int a = base + j;                            /* tile-local position of the first base */
       const u32 *s = s_seq + SCAN_LHALO + (a >> 4);
       const int sh = 2*(a & 15);
@@ -1189,7 +1206,6 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
       rec.w[1] = (B0 << 34) | (B1 >> 30);
       rec.w[2] = (B1 << 34) | (B2 >> 30);
       p.out[pos++] = rec;
-      j = e;
     }
 }
 
@@ -1202,8 +1218,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
  *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
 
 #define BC_TPB 256
-#define BC_SC   32                      /* super-mers per chunk                                  */
-#define BC_CH   (BC_SC*32)              /* <= this many k-mer instances per chunk                 */
+#define BC_GC   192                     /* super-mers held in smem at a time (one "piece" of a group) */
+#define BC_CH   1024                    /* k-mer instances expanded + inserted per chunk          */
 #define BC_TS   4096                    /* hash slots                                            */
 #define BC_DC   2048                    /* distinct-key pool                                     */
 #define BC_EMPTY 0xffffffffu
@@ -1252,13 +1268,14 @@ __device__ __forceinline__ Key<2> supermer_kmer(const u32 *b, int j, int k, cons
 
 __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
 { extern __shared__ __align__(16) unsigned char s_raw[];
-  Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]            */
-  Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]            */
-  u32    *slot  = (u32 *) (rec + BC_CH);                             /* [BC_TS]            */
-  u32    *ocnt  = slot + BC_TS;                                      /* [BC_DC]            */
-  u32    *sbase = ocnt + BC_DC;                                      /* [BC_SC][8] base words */
-  u32    *spre  = sbase + BC_SC*8;                                   /* [BC_SC+1] prefix of lengths */
-  __shared__ u32 s_nd, s_ovf, s_hist[SC_SMALLHIST];
+  Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
+  Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
+  u32    *slot  = (u32 *) (rec + BC_CH);                             /* [BC_TS]              */
+  u32    *ocnt  = slot + BC_TS;                                      /* [BC_DC]              */
+  u32    *sbase = ocnt + BC_DC;                                      /* [BC_GC][8] base words */
+  u32    *spre  = sbase + BC_GC*8;                                   /* [BC_GC+1] prefix of the lengths */
+  unsigned short *newl = (unsigned short *) (spre + BC_GC + 2);      /* [BC_CH] slots claimed in this chunk */
+  __shared__ u32 s_nd, s_nnew, s_ovf, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
   __shared__ u64 s_ebase;
 
   const long long g = blockIdx.x;
@@ -1277,79 +1294,83 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
       bool failed = false;
       for (u32 i = threadIdx.x; i < BC_TS; i += BC_TPB) slot[i] = BC_EMPTY;
       for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB) s_hist[i] = 0;
-      if (threadIdx.x == 0) { s_nd = 0; s_ovf = 0; }
+      if (threadIdx.x == 0) { s_nd = 0; s_nnew = 0; s_ovf = 0; }
       __syncthreads();
-      for (u64 c0 = r0; c0 < r1; c0 += BC_SC)
-        { const u32 ns = (u32) ((r1 - c0 < BC_SC) ? (r1 - c0) : BC_SC);
-          /* load the chunk's super-mers: warp 0 builds the length prefix and unpacks the base words */
-          if (threadIdx.x < BC_SC)
-            { u32 l = 0;
-              if (threadIdx.x < ns)
-                { const Key<3> sm = p.recs[c0 + threadIdx.x];
-                  l = (u32) ((sm.w[0] >> (64 - SUP_BBITS - SUP_LBITS)) & 63u) + 1u;
-                  const u64 B0 = (sm.w[0] << 30) | (sm.w[1] >> 34);
-                  const u64 B1 = (sm.w[1] << 30) | (sm.w[2] >> 34);
-                  const u64 B2 = (sm.w[2] << 30);
-                  u32 *d = sbase + threadIdx.x*8;
-                  d[0] = (u32) (B0 >> 32); d[1] = (u32) B0; d[2] = (u32) (B1 >> 32); d[3] = (u32) B1;
-                  d[4] = (u32) (B2 >> 32); d[5] = (u32) B2; d[6] = 0; d[7] = 0;
-                }
-              u32 incl = l;
+      for (u64 q0 = r0; q0 < r1 && !failed; q0 += BC_GC)
+        { const u32 ns = (u32) ((r1 - q0 < BC_GC) ? (r1 - q0) : BC_GC);
+          /* load one piece: thread t unpacks super-mer t; block scan of the lengths */
+          u32 l = 0;
+          if (threadIdx.x < ns)
+            { const Key<3> sm = p.recs[q0 + threadIdx.x];
+              l = (u32) ((sm.w[0] >> (64 - SUP_BBITS - SUP_LBITS)) & 63u) + 1u;
+              const u64 B0 = (sm.w[0] << 30) | (sm.w[1] >> 34);
+              const u64 B1 = (sm.w[1] << 30) | (sm.w[2] >> 34);
+              const u64 B2 = (sm.w[2] << 30);
+              u32 *d = sbase + threadIdx.x*8;
+              d[0] = (u32) (B0 >> 32); d[1] = (u32) B0; d[2] = (u32) (B1 >> 32); d[3] = (u32) B1;
+              d[4] = (u32) (B2 >> 32); d[5] = (u32) B2; d[6] = 0; d[7] = 0;
+            }
+          u32 incl = l;
 #pragma unroll
-              for (int o = 1; o < 32; o <<= 1)
-                { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
-                  if ((int) threadIdx.x >= o) incl += y;
+          for (int o = 1; o < 32; o <<= 1)
+            { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+              if ((threadIdx.x & 31) >= o) incl += y;
+            }
+          if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
+          __syncthreads();
+          u32 woff = 0;
+          for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_wsum[i];
+          if (threadIdx.x < BC_GC) spre[threadIdx.x+1] = woff + incl;
+          if (threadIdx.x == 0) spre[0] = 0;
+          __syncthreads();
+          const u32 total = spre[ns];
+          for (u32 c0 = 0; c0 < total; c0 += BC_CH)
+            { const u32 ninst = (total - c0 < BC_CH) ? (total - c0) : BC_CH;
+              /* expand: instance -> (super-mer, offset) by binary search in the prefix */
+              for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
+                { const u32 gi = c0 + i;
+                  u32 lo = 0, hi = ns;
+                  while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= gi) lo = mid; else hi = mid; }
+                  rec[i] = supermer_kmer(sbase + lo*8,(int) (gi - spre[lo]),p.k,kmask);
                 }
-              spre[threadIdx.x+1] = incl;
-              if (threadIdx.x == 0) spre[0] = 0;
-            }
-          __syncthreads();
-          const u32 ninst = spre[BC_SC];
-          /* expand: instance i -> (super-mer, offset) by binary search in the prefix */
-          for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
-            { u32 lo = 0, hi = BC_SC;
-              while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= i) lo = mid; else hi = mid; }
-              rec[i] = supermer_kmer(sbase + lo*8,(int) (i - spre[lo]),p.k,kmask);
-            }
-          __syncthreads();
-          /* insert */
-          for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
-            { const Key<2> key = rec[i];
-              const u32 h = key_hash<2>(key);
-              if (((h >> 20) & (rounds-1)) != rd) continue;
-              u32 x = h & (BC_TS-1);
-              for (u32 step = 0; ; step++)
-                { if (step >= BC_TS) { s_ovf = 1; break; }
-                  u32 v = ((volatile u32 *) slot)[x];
-                  if (v == BC_EMPTY)
-                    { u32 old = atomicCAS(&slot[x],BC_EMPTY,(i << 16) | 1u);
-                      if (old == BC_EMPTY) break;
-                      v = old;
+              __syncthreads();
+              /* insert */
+              for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
+                { const Key<2> key = rec[i];
+                  const u32 h = key_hash<2>(key);
+                  if (((h >> 20) & (rounds-1)) != rd) continue;
+                  u32 x = h & (BC_TS-1);
+                  for (u32 step = 0; ; step++)
+                    { if (step >= BC_TS) { s_ovf = 1; break; }
+                      u32 v = ((volatile u32 *) slot)[x];
+                      if (v == BC_EMPTY)
+                        { u32 old = atomicCAS(&slot[x],BC_EMPTY,(i << 16) | 1u);
+                          if (old == BC_EMPTY) { newl[atomicAdd(&s_nnew,1u)] = (unsigned short) x; break; }
+                          v = old;
+                        }
+                      if (v & BC_PERS)
+                        { const u32 pi = v & ~BC_PERS;
+                          if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
+                        }
+                      else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
+                      x = (x+1) & (BC_TS-1);
                     }
-                  if (v & BC_PERS)
-                    { const u32 pi = v & ~BC_PERS;
-                      if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
-                    }
-                  else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
-                  x = (x+1) & (BC_TS-1);
                 }
-            }
-          __syncthreads();
-          /* migrate this chunk's new owners into the pool */
-          for (u32 x = threadIdx.x; x < BC_TS; x += BC_TPB)
-            { const u32 v = slot[x];
-              if (v != BC_EMPTY && !(v & BC_PERS))
-                { const u32 pi = atomicAdd(&s_nd,1u);
-                  if (pi < BC_DC)
-                    { pool[pi] = rec[v >> 16];
-                      ocnt[pi] = v & 0xffffu;
-                      slot[x] = BC_PERS | pi;
-                    }
-                  else s_ovf = 1;
+              __syncthreads();
+              /* migrate this chunk's new owners into the pool */
+              const u32 nnew = s_nnew, nd0 = s_nd;
+              if (nd0 + nnew > BC_DC || s_ovf) { failed = true; break; }
+              for (u32 t = threadIdx.x; t < nnew; t += BC_TPB)
+                { const u32 x = newl[t];
+                  const u32 v = slot[x];
+                  pool[nd0 + t] = rec[v >> 16];
+                  ocnt[nd0 + t] = v & 0xffffu;
+                  slot[x] = BC_PERS | (nd0 + t);
                 }
+              __syncthreads();
+              if (threadIdx.x == 0) { s_nd = nd0 + nnew; s_nnew = 0; }
+              __syncthreads();
             }
-          __syncthreads();
-          if (s_ovf) { failed = true; break; }
         }
       if (failed)
         { __syncthreads();
