@@ -1217,9 +1217,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
  *  A group whose distinct keys overflow the pool is redone in 2x more rounds, each round taking the k-mers whose
  *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
 
-#define BC_TPB 256
+#define BC_TPB 512
 #define BC_GC   192                     /* super-mers held in smem at a time (one "piece" of a group) */
-#define BC_CH   1024                    /* k-mer instances expanded + inserted per chunk          */
+#define BC_CH   2048                    /* k-mer instances expanded + inserted per chunk          */
 #define BC_TS   4096                    /* hash slots                                            */
 #define BC_DC   2048                    /* distinct-key pool                                     */
 #define BC_EMPTY 0xffffffffu
@@ -1234,10 +1234,11 @@ struct BucketParams
     u32       *g_fail;                                   /* set if a group could not be counted */
   };
 
-/* canonical k-mer number j of a super-mer whose base string is b[0..5] (192 bits, left aligned) */
-__device__ __forceinline__ Key<2> supermer_kmer(const u32 *b, int j, int k, const u32 *kmask)
+/* both strands of k-mer number j of a super-mer whose base string is b[0..5] (192 bits, left aligned):
+ * F = forward, G = reverse complement, each as four 32-bit words, most significant first, 2k bits used */
+__device__ __forceinline__ void supermer_strands(const u32 *b, int j, int k, const u32 *kmask, u32 *F, u32 *G)
 { const int q = j >> 4, sh = 2*(j & 15);
-  u32 F[4], Z[4], G[4];
+  u32 Z[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) F[t] = __funnelshift_l(b[q+t+1],b[q+t],sh) & kmask[t];
   /* reverse complement of the 64 base slots, then drop the (64-k) padding slots off the top */
@@ -1256,7 +1257,21 @@ __device__ __forceinline__ Key<2> supermer_kmer(const u32 *b, int j, int k, cons
       else              { hi = Y[t+3]; lo = Y[t+4]; }
       G[t] = __funnelshift_l(lo,hi,sr) & kmask[t];
     }
-  bool lt = false, dec = false;
+}
+
+/* slide both strands one base to the right: base code c enters the forward strand at its low end */
+__device__ __forceinline__ void strands_roll(u32 *F, u32 *G, u32 c, int k, const u32 *kmask)
+{ const int s = 128 - 2*k, iw = 3 - (s >> 5), is = s & 31;      /* word / shift of the last base slot */
+  F[0] = __funnelshift_l(F[1],F[0],2); F[1] = __funnelshift_l(F[2],F[1],2);
+  F[2] = __funnelshift_l(F[3],F[2],2); F[3] = F[3] << 2;
+  const u32 ins = c << is;
+  F[0] |= (iw == 0) ? ins : 0u; F[1] |= (iw == 1) ? ins : 0u; F[2] |= (iw == 2) ? ins : 0u; F[3] |= (iw == 3) ? ins : 0u;
+  G[3] = __funnelshift_r(G[3],G[2],2) & kmask[3]; G[2] = __funnelshift_r(G[2],G[1],2) & kmask[2];
+  G[1] = __funnelshift_r(G[1],G[0],2) & kmask[1]; G[0] = ((G[0] >> 2) | ((3u - c) << 30)) & kmask[0];
+}
+
+__device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
+{ bool lt = false, dec = false;
 #pragma unroll
   for (int t = 0; t < 4; t++)
     if (!dec && F[t] != G[t]) { lt = G[t] < F[t]; dec = true; }
@@ -1326,13 +1341,36 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           const u32 total = spre[ns];
           for (u32 c0 = 0; c0 < total; c0 += BC_CH)
             { const u32 ninst = (total - c0 < BC_CH) ? (total - c0) : BC_CH;
-              /* expand: instance -> (super-mer, offset) by binary search in the prefix */
-              for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
-                { const u32 gi = c0 + i;
-                  u32 lo = 0, hi = ns;
-                  while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= gi) lo = mid; else hi = mid; }
-                  rec[i] = supermer_kmer(sbase + lo*8,(int) (gi - spre[lo]),p.k,kmask);
-                }
+              /* expand: every thread takes `per` consecutive instances; the first is located by binary search in the
+                 prefix and extracted from the base string, the following ones slide along the same super-mer */
+              { const u32 per = (ninst + BC_TPB - 1) / BC_TPB;
+                const u32 i0 = threadIdx.x * per;
+                const u32 i1 = (i0 + per < ninst) ? (i0 + per) : ninst;
+                if (i0 < i1)
+                  { const u32 gi = c0 + i0;
+                    u32 lo = 0, hi = ns;
+                    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= gi) lo = mid; else hi = mid; }
+                    u32 sidx = lo, j = gi - spre[lo], slen = spre[lo+1] - spre[lo];
+                    const u32 *sb = sbase + sidx*8;
+                    u32 F[4], G[4];
+                    supermer_strands(sb,(int) j,p.k,kmask,F,G);
+                    rec[i0] = strands_canon(F,G);
+                    for (u32 i = i0+1; i < i1; i++)
+                      { j++;
+                        if (j >= slen)
+                          { sidx++; j = 0; slen = spre[sidx+1] - spre[sidx];
+                            sb = sbase + sidx*8;
+                            supermer_strands(sb,0,p.k,kmask,F,G);
+                          }
+                        else
+                          { const u32 qb = j + p.k - 1;
+                            const u32 c = (sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u;
+                            strands_roll(F,G,c,p.k,kmask);
+                          }
+                        rec[i] = strands_canon(F,G);
+                      }
+                  }
+              }
               __syncthreads();
               /* insert */
               for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
