@@ -837,8 +837,13 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   }
   stage_end(c,FKGPU_ST_SUPERPART);
 
-  /* groups of whole buckets, ~128 super-mers each */
-  const u32 TS = 128;
+  /* groups of whole buckets, ~TS super-mers each */
+  static int bcvar = -1, tsv = 512;
+  if (bcvar < 0)
+    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 3;
+      const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
+    }
+  const u32 TS = (u32) tsv;
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -853,9 +858,16 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(k,km);
-    const size_t sm = (size_t) BC_DC*16 + (size_t) BC_CH*16 + (size_t) BC_TS*4 + (size_t) BC_DC*4 + (size_t) BC_GC*8*4 + (size_t) (BC_GC+2)*4 + (size_t) BC_CH*2 + 64;
-    CU(cudaFuncSetAttribute(k_bucket_count,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
-    k_bucket_count<<<(unsigned) gmax,BC_TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK();
+#define BC_LAUNCH(TPB,CH,DC) do { \
+      const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) BC_TS*4 + (size_t) (DC)*4 + (size_t) (TPB)*8*4 + (size_t) ((TPB)+2)*4 + (size_t) (CH)*2 + 64; \
+      CU(cudaFuncSetAttribute(k_bucket_count<TPB,CH,DC>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
+      k_bucket_count<TPB,CH,DC><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK(); } while (0)
+    if (bcvar == 1) BC_LAUNCH(256,1024,1536);
+    else if (bcvar == 3) BC_LAUNCH(512,1024,1024);
+    else if (bcvar == 4) BC_LAUNCH(256,1024,1024);
+    else if (bcvar == 5) BC_LAUNCH(512,2048,1024);
+    else if (bcvar == 6) BC_LAUNCH(1024,2048,2048);
+    else BC_LAUNCH(512,2048,2048);
   }
   stage_end(c,FKGPU_ST_BUCKET);
   Misc hm;

@@ -1217,11 +1217,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
  *  A group whose distinct keys overflow the pool is redone in 2x more rounds, each round taking the k-mers whose
  *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
 
-#define BC_TPB 512
-#define BC_GC   192                     /* super-mers held in smem at a time (one "piece" of a group) */
-#define BC_CH   2048                    /* k-mer instances expanded + inserted per chunk          */
-#define BC_TS   4096                    /* hash slots                                            */
-#define BC_DC   2048                    /* distinct-key pool                                     */
+/* template parameters of k_bucket_count: BC_TPB threads (= super-mers held in smem per piece), BC_CH k-mer instances
+ * expanded + inserted per chunk, BC_DC distinct-key pool; BC_TS hash slots                                        */
+#define BC_TS   4096
 #define BC_EMPTY 0xffffffffu
 #define BC_PERS  0x80000000u
 
@@ -1281,8 +1279,10 @@ __device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
   return key;
 }
 
+template<int BC_TPB, int BC_CH, int BC_DC>
 __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
-{ extern __shared__ __align__(16) unsigned char s_raw[];
+{ constexpr int BC_GC = BC_TPB;
+  extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
   Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
   u32    *slot  = (u32 *) (rec + BC_CH);                             /* [BC_TS]              */
@@ -1290,7 +1290,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
   u32    *sbase = ocnt + BC_DC;                                      /* [BC_GC][8] base words */
   u32    *spre  = sbase + BC_GC*8;                                   /* [BC_GC+1] prefix of the lengths */
   unsigned short *newl = (unsigned short *) (spre + BC_GC + 2);      /* [BC_CH] slots claimed in this chunk */
-  __shared__ u32 s_nd, s_nnew, s_ovf, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
+  __shared__ u32 s_nnew[2], s_ovf, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
   __shared__ u64 s_ebase;
 
   const long long g = blockIdx.x;
@@ -1309,7 +1309,8 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
       bool failed = false;
       for (u32 i = threadIdx.x; i < BC_TS; i += BC_TPB) slot[i] = BC_EMPTY;
       for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB) s_hist[i] = 0;
-      if (threadIdx.x == 0) { s_nd = 0; s_nnew = 0; s_ovf = 0; }
+      if (threadIdx.x == 0) { s_nnew[0] = 0; s_nnew[1] = 0; s_ovf = 0; }
+      u32 nd = 0, par = 0;                       /* distinct keys in the pool; parity of the chunk counter in use */
       __syncthreads();
       for (u64 q0 = r0; q0 < r1 && !failed; q0 += BC_GC)
         { const u32 ns = (u32) ((r1 - q0 < BC_GC) ? (r1 - q0) : BC_GC);
@@ -1334,8 +1335,18 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
           __syncthreads();
           u32 woff = 0;
-          for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_wsum[i];
-          if (threadIdx.x < BC_GC) spre[threadIdx.x+1] = woff + incl;
+          { const u32 lane = threadIdx.x & 31;
+            u32 x = (lane < BC_TPB/32) ? s_wsum[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+              { u32 y = __shfl_up_sync(0xffffffffu,x,o);
+                if ((int) lane >= o) x += y;
+              }
+            const u32 wid = threadIdx.x >> 5;
+            woff = __shfl_sync(0xffffffffu,x,wid ? wid-1 : 0);
+            if (wid == 0) woff = 0;
+          }
+          spre[threadIdx.x+1] = woff + incl;
           if (threadIdx.x == 0) spre[0] = 0;
           __syncthreads();
           const u32 total = spre[ns];
@@ -1354,7 +1365,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                     const u32 *sb = sbase + sidx*8;
                     u32 F[4], G[4];
                     supermer_strands(sb,(int) j,p.k,kmask,F,G);
-                    rec[i0] = strands_canon(F,G);
+                    rec[threadIdx.x] = strands_canon(F,G);
                     for (u32 i = i0+1; i < i1; i++)
                       { j++;
                         if (j >= slen)
@@ -1367,14 +1378,16 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                             const u32 c = (sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u;
                             strands_roll(F,G,c,p.k,kmask);
                           }
-                        rec[i] = strands_canon(F,G);
+                        rec[(i - i0)*BC_TPB + threadIdx.x] = strands_canon(F,G);
                       }
                   }
               }
               __syncthreads();
-              /* insert */
-              for (u32 i = threadIdx.x; i < ninst; i += BC_TPB)
-                { const Key<2> key = rec[i];
+              /* insert: rec[] is laid out [instance-of-thread][thread]; slot i holds instance (i % TPB)*per + i / TPB */
+              const u32 perx = (ninst + BC_TPB - 1) / BC_TPB;
+              for (u32 i = threadIdx.x; i < perx*BC_TPB; i += BC_TPB)
+                { if (threadIdx.x*perx + i / BC_TPB >= ninst) continue;
+                  const Key<2> key = rec[i];
                   const u32 h = key_hash<2>(key);
                   if (((h >> 20) & (rounds-1)) != rd) continue;
                   u32 x = h & (BC_TS-1);
@@ -1383,7 +1396,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                       u32 v = ((volatile u32 *) slot)[x];
                       if (v == BC_EMPTY)
                         { u32 old = atomicCAS(&slot[x],BC_EMPTY,(i << 16) | 1u);
-                          if (old == BC_EMPTY) { newl[atomicAdd(&s_nnew,1u)] = (unsigned short) x; break; }
+                          if (old == BC_EMPTY) { newl[atomicAdd(&s_nnew[par],1u)] = (unsigned short) x; break; }
                           v = old;
                         }
                       if (v & BC_PERS)
@@ -1396,8 +1409,9 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                 }
               __syncthreads();
               /* migrate this chunk's new owners into the pool */
-              const u32 nnew = s_nnew, nd0 = s_nd;
+              const u32 nnew = s_nnew[par], nd0 = nd;
               if (nd0 + nnew > BC_DC || s_ovf) { failed = true; break; }
+              if (threadIdx.x == 0) s_nnew[par ^ 1] = 0;       /* the other counter: nobody reads it until after the next barrier */
               for (u32 t = threadIdx.x; t < nnew; t += BC_TPB)
                 { const u32 x = newl[t];
                   const u32 v = slot[x];
@@ -1405,8 +1419,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                   ocnt[nd0 + t] = v & 0xffffu;
                   slot[x] = BC_PERS | (nd0 + t);
                 }
-              __syncthreads();
-              if (threadIdx.x == 0) { s_nd = nd0 + nnew; s_nnew = 0; }
+              nd = nd0 + nnew; par ^= 1;
               __syncthreads();
             }
         }
@@ -1421,7 +1434,6 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           continue;
         }
       /* emit this class's distinct keys */
-      const u32 nd = s_nd;
       if (threadIdx.x == 0 && p.ent != NULL) s_ebase = nd ? atomicAdd(p.ent_counter,(u64) nd) : 0ull;
       __syncthreads();
       for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
