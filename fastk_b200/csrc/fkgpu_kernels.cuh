@@ -672,7 +672,8 @@ __global__ void k_groups(const u64 *off, long long m /* # of buckets; off[m] = N
 #define SC_EMPTY 0xffffffffu
 #define SC_PAD   0xffffffffffffffffull
 #define SC_SMALLHIST 256
-#define SC_RANKMAX   256     /* <= this many distinct keys: rank by counting instead of the bitonic network */
+#define SC_BINBITS   10
+#define SC_NBIN      (1 << SC_BINBITS)
 
 #define ITEM_UNIFORM 1u      /* every record of the item holds the same key                  */
 #define ITEM_ALTBUF  2u      /* item lives in the alternate buffer (input/staging swapped)    */
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   __shared__ u64 s_bar;
   __shared__ u32 s_D, s_pass, s_or[2*NW];
   __shared__ u32 s_hist[SC_SMALLHIST];
+  __shared__ u32 s_bin[SC_NBIN], s_boff[SC_NBIN+1], s_wtot[SC_TPB/32];
 
   const long long g = blockIdx.x;
   if (g >= p.nitems) return;
@@ -861,49 +863,59 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
     }
   __syncthreads();
   const u32 D = s_D;
-  u32 D2 = 1; while (D2 < D) D2 <<= 1;
-  if (D > SC_RANKMAX)
-    { for (u32 i = D + threadIdx.x; i < D2; i += SC_TPB) srt[i] = SC_PAD;
-      __syncthreads();
-    }
 
-  const u64 *fin = srt;
-  if (D <= SC_RANKMAX)
-    { /* few distinct keys (the common, high-coverage case): rank by counting, no barriers */
-      u64 *srt2 = srt + p.srt2_off;
-      for (u32 e = threadIdx.x; e < D; e += SC_TPB)
-        { const u64 a = srt[e];
-          const u32 pa = (u32) (a >> 32);
-          u32 rank = 0;
-          for (u32 j = 0; j < D; j++)
-            { const u64 b = srt[j];
-              const u32 pb = (u32) (b >> 32);
-              bool lt = pb < pa;
-              if (pb == pa && j != e) lt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
-              rank += lt ? 1u : 0u;
-            }
-          srt2[rank] = a;
-        }
-      fin = srt2;
-      __syncthreads();
-    }
-  else
-  /* bitonic sort of srt[0..D2) by (32-bit prefix, then full key) */
-  for (u32 kk = 2; kk <= D2; kk <<= 1)
-    for (u32 j = kk >> 1; j > 0; j >>= 1)
-      { for (u32 t = threadIdx.x; t < (D2 >> 1); t += SC_TPB)
-          { u32 i = ((t & ~(j-1)) << 1) | (t & (j-1));
-            u32 l = i | j;
-            u64 a = srt[i], b = srt[l];
-            bool up = ((i & kk) == 0);
-            bool gt;                                   /* a > b ? */
-            if ((a >> 32) != (b >> 32)) gt = (a >> 32) > (b >> 32);
-            else if (a == SC_PAD || b == SC_PAD) gt = (a == SC_PAD) && (b != SC_PAD);
-            else gt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
-            if (gt == up) { srt[i] = b; srt[l] = a; }
-          }
-        __syncthreads();
+  /* order the D distinct keys: bin on the 10 bits that follow the common prefix, then rank inside the (tiny) bins
+     by counting -- 4 barriers, no sorting network (the bitonic sort's barriers were 29 % of this kernel's time)   */
+  u64 *srtB = (u64 *) table;                       /* the hash table is dead now; it holds >= D entries of 8 bytes   */
+  for (u32 i = threadIdx.x; i < SC_NBIN; i += SC_TPB) s_bin[i] = 0;
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < D; e += SC_TPB)
+    atomicAdd(&s_bin[(u32) (srt[e] >> (64 - SC_BINBITS))],1u);
+  __syncthreads();
+  { /* exclusive scan of the SC_NBIN counters: SC_NBIN / SC_TPB per thread + warp scan + warp totals */
+    constexpr int PER = SC_NBIN / SC_TPB;
+    u32 v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = s_bin[threadIdx.x*PER + i]; sum += v[i]; }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+      { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+        if ((threadIdx.x & 31) >= o) incl += y;
       }
+    if ((threadIdx.x & 31) == 31) s_wtot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 woff = 0;
+    for (int i = 0; i < (int) (threadIdx.x >> 5); i++) woff += s_wtot[i];
+    u32 run = woff + incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; i++)
+      { s_boff[threadIdx.x*PER + i] = run; s_bin[threadIdx.x*PER + i] = run; run += v[i]; }
+    if (threadIdx.x == SC_TPB-1) s_boff[SC_NBIN] = run;
+  }
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < D; e += SC_TPB)
+    { const u64 a = srt[e];
+      srtB[atomicAdd(&s_bin[(u32) (a >> (64 - SC_BINBITS))],1u)] = a;
+    }
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < D; e += SC_TPB)
+    { const u64 a = srtB[e];
+      const u32 bn = (u32) (a >> (64 - SC_BINBITS));
+      const u32 lo = s_boff[bn], hi = s_boff[bn+1];
+      const u32 pa = (u32) (a >> 32);
+      u32 rank = lo;
+      for (u32 j = lo; j < hi; j++)
+        { const u64 b = srtB[j];
+          const u32 pb = (u32) (b >> 32);
+          bool lt = pb < pa;
+          if (pb == pa && j != e) lt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
+          rank += lt ? 1u : 0u;
+        }
+      srt[rank] = a;
+    }
+  const u64 *fin = srt;
+  __syncthreads();
 
   /* emit: staged (key,count), histogram */
   u32 npass = 0;
@@ -1290,7 +1302,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
   u32    *sbase = ocnt + BC_DC;                                      /* [BC_GC][8] base words */
   u32    *spre  = sbase + BC_GC*8;                                   /* [BC_GC+1] prefix of the lengths */
   unsigned short *newl = (unsigned short *) (spre + BC_GC + 2);      /* [BC_CH] slots claimed in this chunk */
-  __shared__ u32 s_nnew[2], s_ovf, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
+  __shared__ u32 s_nnew[2], s_ovf, s_ecnt, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
   __shared__ u64 s_ebase;
 
   const long long g = blockIdx.x;
@@ -1350,23 +1362,23 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           if (threadIdx.x == 0) spre[0] = 0;
           __syncthreads();
           const u32 total = spre[ns];
-          for (u32 c0 = 0; c0 < total; c0 += BC_CH)
-            { const u32 ninst = (total - c0 < BC_CH) ? (total - c0) : BC_CH;
-              /* expand: every thread takes `per` consecutive instances; the first is located by binary search in the
-                 prefix and extracted from the base string, the following ones slide along the same super-mer */
-              { const u32 per = (ninst + BC_TPB - 1) / BC_TPB;
-                const u32 i0 = threadIdx.x * per;
-                const u32 i1 = (i0 + per < ninst) ? (i0 + per) : ninst;
-                if (i0 < i1)
-                  { const u32 gi = c0 + i0;
-                    u32 lo = 0, hi = ns;
-                    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= gi) lo = mid; else hi = mid; }
-                    u32 sidx = lo, j = gi - spre[lo], slen = spre[lo+1] - spre[lo];
-                    const u32 *sb = sbase + sidx*8;
-                    u32 F[4], G[4];
-                    supermer_strands(sb,(int) j,p.k,kmask,F,G);
-                    rec[threadIdx.x] = strands_canon(F,G);
-                    for (u32 i = i0+1; i < i1; i++)
+          /* fused expand + insert: every thread takes `per` consecutive k-mer instances of the piece; the first is
+             located by binary search in the prefix and cut out of the base string, the next ones slide along the
+             same super-mer.  Only a k-mer that claims an empty slot is written to rec[] (before its CAS, so that
+             whoever finds the slot can compare against it); the others never leave registers.                   */
+          { const u32 per = (total + BC_TPB - 1) / BC_TPB;
+            const u32 i0 = threadIdx.x * per;
+            const u32 i1 = (i0 + per < total) ? (i0 + per) : total;
+            u32 myrec = 0xffffffffu;
+            if (i0 < i1)
+              { u32 lo = 0, hi = ns;
+                while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= i0) lo = mid; else hi = mid; }
+                u32 sidx = lo, j = i0 - spre[lo], slen = spre[lo+1] - spre[lo];
+                const u32 *sb = sbase + sidx*8;
+                u32 F[4], G[4];
+                supermer_strands(sb,(int) j,p.k,kmask,F,G);
+                for (u32 i = i0; i < i1; i++)
+                  { if (i > i0)
                       { j++;
                         if (j >= slen)
                           { sidx++; j = 0; slen = spre[sidx+1] - spre[sidx];
@@ -1375,53 +1387,54 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                           }
                         else
                           { const u32 qb = j + p.k - 1;
-                            const u32 c = (sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u;
-                            strands_roll(F,G,c,p.k,kmask);
+                            strands_roll(F,G,(sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u,p.k,kmask);
                           }
-                        rec[(i - i0)*BC_TPB + threadIdx.x] = strands_canon(F,G);
+                      }
+                    const Key<2> key = strands_canon(F,G);
+                    const u32 h = key_hash<2>(key);
+                    if (((h >> 20) & (rounds-1)) != rd) continue;
+                    u32 x = h & (BC_TS-1);
+                    for (u32 step = 0; ; step++)
+                      { if (step >= BC_TS) { s_ovf = 1; break; }
+                        u32 v = ((volatile u32 *) slot)[x];
+                        if (v == BC_EMPTY)
+                          { if (myrec == 0xffffffffu)
+                              { myrec = atomicAdd(&s_nnew[par],1u);
+                                if (myrec >= BC_CH) { s_ovf = 1; myrec = 0xffffffffu; break; }
+                              }
+                            rec[myrec] = key;
+                            __threadfence_block();
+                            u32 old = atomicCAS(&slot[x],BC_EMPTY,(myrec << 16) | 1u);
+                            if (old == BC_EMPTY) { newl[myrec] = (unsigned short) x; myrec = 0xffffffffu; break; }
+                            v = old;
+                          }
+                        if (v & BC_PERS)
+                          { const u32 pi = v & ~BC_PERS;
+                            if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
+                          }
+                        else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
+                        x = (x+1) & (BC_TS-1);
                       }
                   }
               }
-              __syncthreads();
-              /* insert: rec[] is laid out [instance-of-thread][thread]; slot i holds instance (i % TPB)*per + i / TPB */
-              const u32 perx = (ninst + BC_TPB - 1) / BC_TPB;
-              for (u32 i = threadIdx.x; i < perx*BC_TPB; i += BC_TPB)
-                { if (threadIdx.x*perx + i / BC_TPB >= ninst) continue;
-                  const Key<2> key = rec[i];
-                  const u32 h = key_hash<2>(key);
-                  if (((h >> 20) & (rounds-1)) != rd) continue;
-                  u32 x = h & (BC_TS-1);
-                  for (u32 step = 0; ; step++)
-                    { if (step >= BC_TS) { s_ovf = 1; break; }
-                      u32 v = ((volatile u32 *) slot)[x];
-                      if (v == BC_EMPTY)
-                        { u32 old = atomicCAS(&slot[x],BC_EMPTY,(i << 16) | 1u);
-                          if (old == BC_EMPTY) { newl[atomicAdd(&s_nnew[par],1u)] = (unsigned short) x; break; }
-                          v = old;
-                        }
-                      if (v & BC_PERS)
-                        { const u32 pi = v & ~BC_PERS;
-                          if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
-                        }
-                      else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
-                      x = (x+1) & (BC_TS-1);
-                    }
-                }
-              __syncthreads();
-              /* migrate this chunk's new owners into the pool */
-              const u32 nnew = s_nnew[par], nd0 = nd;
-              if (nd0 + nnew > BC_DC || s_ovf) { failed = true; break; }
-              if (threadIdx.x == 0) s_nnew[par ^ 1] = 0;       /* the other counter: nobody reads it until after the next barrier */
-              for (u32 t = threadIdx.x; t < nnew; t += BC_TPB)
-                { const u32 x = newl[t];
-                  const u32 v = slot[x];
-                  pool[nd0 + t] = rec[v >> 16];
-                  ocnt[nd0 + t] = v & 0xffffu;
-                  slot[x] = BC_PERS | (nd0 + t);
-                }
-              nd = nd0 + nnew; par ^= 1;
-              __syncthreads();
-            }
+            if (myrec != 0xffffffffu) newl[myrec] = 0xffffu;        /* a record allocated for a claim that lost its race */
+          }
+          __syncthreads();
+          /* migrate the new owners into the pool (holes -- lost races -- become pool entries of count 0) */
+          { const u32 nnew = s_nnew[par] < BC_CH ? s_nnew[par] : BC_CH, nd0 = nd;
+            if (nd0 + nnew > BC_DC || s_ovf) { failed = true; break; }
+            if (threadIdx.x == 0) s_nnew[par ^ 1] = 0;           /* the other counter: unused until after the next barrier */
+            for (u32 t = threadIdx.x; t < nnew; t += BC_TPB)
+              { const u32 x = newl[t];
+                if (x == 0xffffu) { ocnt[nd0 + t] = 0; continue; }
+                const u32 v = slot[x];
+                pool[nd0 + t] = rec[t];
+                ocnt[nd0 + t] = v & 0xffffu;
+                slot[x] = BC_PERS | (nd0 + t);
+              }
+            nd = nd0 + nnew; par ^= 1;
+            __syncthreads();
+          }
         }
       if (failed)
         { __syncthreads();
@@ -1433,19 +1446,35 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           stR[sp] = 2*rounds; stD[sp] = rd; sp++;
           continue;
         }
-      /* emit this class's distinct keys */
-      if (threadIdx.x == 0 && p.ent != NULL) s_ebase = nd ? atomicAdd(p.ent_counter,(u64) nd) : 0ull;
+      /* emit this class's distinct keys (pool entries of count 0 are holes) */
+      u32 mine = 0;
+      for (u32 i = threadIdx.x; i < nd; i += BC_TPB) mine += (ocnt[i] != 0) ? 1u : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu,mine,o);
+      if (threadIdx.x == 0) s_ecnt = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_ecnt,mine);
+      __syncthreads();
+      const u32 nreal = s_ecnt;
+      if (threadIdx.x == 0)
+        { s_ebase = (p.ent != NULL && nreal) ? atomicAdd(p.ent_counter,(u64) nreal) : 0ull;
+          s_ecnt = 0;
+        }
       __syncthreads();
       for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
         { const u32 c = ocnt[i];
+          if (c == 0) continue;
           const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
           if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
           else atomicAdd(p.g_hist + cs,1ull);
           if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
-          if (p.ent != NULL && s_ebase + i < p.ent_cap)
-            { Key<2> e = pool[i];
-              e.w[1] |= (u64) cs;
-              p.ent[s_ebase + i] = e;
+          if (p.ent != NULL)
+            { const u64 at = s_ebase + atomicAdd(&s_ecnt,1u);
+              if (at < p.ent_cap)
+                { Key<2> e = pool[i];
+                  e.w[1] |= (u64) cs;
+                  p.ent[at] = e;
+                }
             }
         }
       __syncthreads();
@@ -1453,7 +1482,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
         { u32 c = s_hist[i];
           if (c) atomicAdd(p.g_hist + i,(u64) c);
         }
-      if (threadIdx.x == 0) atomicAdd(p.g_ndistinct,(u64) nd);
+      if (threadIdx.x == 0) atomicAdd(p.g_ndistinct,(u64) nreal);
       __syncthreads();
     }
 }
