@@ -764,14 +764,17 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const int m = std::min(16,k - 8);
   const int w = k - m + 1;
   int p2 = 1; while (2*p2 <= w) p2 <<= 1;
-  const int lmax = std::min(32,82 - k);
+  const int lmax = SUP_LMAX;
   *fell_back = false;
 
   /* bucket-id width from the expected # of super-mers; the exact count is known after the scan */
   const long long sest = std::max<long long>(1,npos / 10);
   int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
   if (bbits > 22) bbits = 22;
-  const int P1 = std::min(bbits,11), P2 = bbits - P1;
+  static int sp1 = -1, sbb = -1;
+  if (sp1 < 0) { const char *e = getenv("FKGPU_SP1"); sp1 = e ? atoi(e) : 11; const char *f = getenv("FKGPU_SBB"); sbb = f ? atoi(f) : 0; }
+  if (sbb > 0 && bbits > sbb) bbits = sbb;
+  const int P1 = std::min(bbits,sp1), P2 = bbits - P1;
   const int nb1 = 1 << P1;
 
   int rc = prepare_common(c,npos,P1,true,2);
@@ -783,9 +786,9 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
 
   /* the two super-mer buffers live inside record buffer A (free until the final sort) */
   const size_t abytes = (size_t) (npos + 4) * 16;
-  const u64 scap = (u64) (abytes / 2 / sizeof(Key<3>)) - 4;
-  Key<3> *SA = (Key<3> *) c->bufA.p;
-  Key<3> *SB = (Key<3> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
+  Key<1> *SA = (Key<1> *) c->bufA.p;
+  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
 
   if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
   const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
@@ -794,7 +797,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     { SuperParams sp;
       sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
       sp.k = k; sp.m = m; sp.w = w; sp.p2 = p2; sp.lmax = lmax; sp.bbits = bbits ? bbits : 1;
-      sp.out = SA; sp.cap = scap; sp.counter = &d_cnt->nrec;
+      sp.out = (u64 *) SA; sp.cap = scap; sp.counter = &d_cnt->nrec;
       const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_L) * 4;
       CU(cudaFuncSetAttribute(k_super,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
       k_super<<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
@@ -811,27 +814,27 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   /* level 1 / level 2 partition of the super-mer records on the bucket id (top bits of w[0]) */
   stage_begin(c,FKGPU_ST_SUPERPART);
   const u64 *offs;
-  const Key<3> *recs;
+  const Key<1> *recs;
   long long mbuckets;
   { const int b1 = bbits ? P1 : 0;
     const int n1 = 1 << b1;
     const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
-    const long long nt = (S + TP_TILE(3) - 1) / TP_TILE(3);
+    const long long nt = (S + TP_TILE(1) - 1) / TP_TILE(1);
     CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (nb1 + 1) * 8,c->st));
     if (nt > 0)
-      { k_tilepart<3,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>(SA,NULL,(u64) S,b1,(u64 *) c->hist1.p); KCHECK(); }
+      { k_tilepart<1,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>(SA,NULL,(u64) S,b1,(u64 *) c->hist1.p); KCHECK(); }
     k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
     if (nt > 0)
-      { CU(cudaFuncSetAttribute(k_tilepart<3,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-        k_tilepart<3,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>(SA,SB,(u64) S,b1,(u64 *) c->cur1.p); KCHECK();
+      { CU(cudaFuncSetAttribute(k_tilepart<1,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+        k_tilepart<1,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>(SA,SB,(u64) S,b1,(u64 *) c->cur1.p); KCHECK();
       }
     offs = (const u64 *) c->off1.p; recs = SB; mbuckets = n1;
     if (bbits && P2 > 0)
       { mbuckets = (long long) n1 << P2;
         if (c->off2.ensure((size_t) (mbuckets + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
-        const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<3>) + (size_t) (1 << P2) * 4;
-        CU(cudaFuncSetAttribute(k_refine<3>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
-        k_refine<3><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(SB,SA,(const u64 *) c->off1.p,n1,b1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
+        const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<1>) + (size_t) (1 << P2) * 4;
+        CU(cudaFuncSetAttribute(k_refine<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+        k_refine<1><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(SB,SA,(const u64 *) c->off1.p,n1,b1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
         offs = (const u64 *) c->off2.p; recs = SA;
       }
   }
@@ -853,7 +856,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   stage_begin(c,FKGPU_ST_BUCKET);
   { BucketParams bp;
-    bp.recs = recs; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = k;
+    bp.recs = (const u64 *) recs; bp.seq = d_seq; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = k;
     bp.g_hist = (u64 *) c->ghist.p; bp.g_maxinst = &d_misc->maxinst; bp.g_ndistinct = &d_misc->ndistinct;
     bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;

@@ -1077,13 +1077,18 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
 
 /* ============================================================================================== */
 /*  Super-mer front end (the reference's own idea, split.c:1016-1393 / Appendix D of SURVEY.md, re-cut for a GPU):
- *  consecutive k-mers that share a canonical minimizer travel together as one 24-byte record
- *      w[0] = [bucket:24][len-1:6][first 17 bases:34]   w[1], w[2] = the next 64 bases
- *  so the partition passes move ~1.6 B per k-mer instead of 16.  Every instance of a canonical k-mer has the same
- *  minimizer (the minimum over BOTH strands' m-mers under a bijective order hash), hence the same bucket: each
- *  bucket can be counted on chip with no cross-bucket merge.                                                   */
+ *  consecutive k-mers that share a canonical minimizer travel together as ONE 8-byte record that points into the
+ *  packed reads, which stay resident in HBM:
+ *      [bucket:24][len-1:6][position of the first base:34]
+ *  so the partition passes move < 1 B per k-mer instead of 16, and the counting kernel gathers the bases itself.
+ *  Every instance of a canonical k-mer has the same minimizer (the minimum over BOTH strands' m-mers under a
+ *  bijective order hash), hence the same bucket: each bucket is counted on chip with no cross-bucket merge.
+ *  A super-mer starts at a legal k-mer that does not continue its predecessor (other bucket / illegal) or sits on
+ *  a multiple of 64 (so no super-mer exceeds 64 k-mers and every thread can decide its starts locally).          */
 
 #define SUP_L     (SCAN_TILE + SCAN_TILE/32 + 64)   /* room for the +1-per-32 skew that keeps per-thread rows conflict-free */
+#define SUP_PBITS 34
+#define SUP_LMAX  64
 #define SUP_BBITS 24
 #define SUP_LBITS 6
 
@@ -1091,7 +1096,7 @@ struct SuperParams
   { const u32 *seq; const u32 *val;
     long long  npos, nseqw, nvalw;
     int        k, m, w, p2, lmax, bbits;      /* w = k-m+1 window of m-mers, p2 = largest power of two <= w */
-    Key<3>    *out; u64 cap;
+    u64       *out; u64 cap;
     u64       *counter;                       /* [0] records emitted, [1] k-mers covered                    */
   };
 
@@ -1106,7 +1111,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
   u32 *s_val = s_seq + SCAN_SEQW;
   u32 *s_a   = s_val + SCAN_VALW;           /* [SUP_L] */
   u32 *s_b   = s_a + SUP_L;                 /* [SUP_L] */
-  __shared__ u32 s_warp[SCAN_TPB/32];
+  __shared__ u32 s_warp[SCAN_TPB/32], s_okw[SCAN_TPB+1];
   __shared__ u64 s_base;
 
   ScanParams sp; sp.seq = p.seq; sp.val = p.val; sp.nseqw = p.nseqw; sp.nvalw = p.nvalw;
@@ -1146,11 +1151,13 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
     }
   V96 v; v.a = s_val[threadIdx.x]; v.b = s_val[threadIdx.x+1]; v.c = s_val[threadIdx.x+2];
   const u32 ok = window_ok(v,p.k);                  /* bit 31-j = k-mer j of this thread is legal */
+  s_okw[threadIdx.x] = ok;
+  if (threadIdx.x == 0) s_okw[SCAN_TPB] = 0;
   __syncthreads();
   const u32 *bk = nxt + threadIdx.x * (SCAN_PPT + 1);
   const int base = threadIdx.x * SCAN_PPT;
 
-  /* cont bit j: k-mer j continues the super-mer of k-mer j-1 (both legal, same bucket) */
+  /* cont bit j: k-mer j continues the super-mer of k-mer j-1 (both legal, same bucket, not on a multiple of 64) */
   u32 same = 0;
   { u32 prev = bk[0];
 #pragma unroll
@@ -1159,20 +1166,14 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
         same |= (x == prev ? 1u : 0u) << (31-j);
         prev = x;
       }
-  }
-  const u32 cont = ok & (ok >> 1) & same;
-  u32 starts = ok & ~cont;                          /* bit 31-j = a super-mer starts at j */
-  /* a run longer than lmax is cut: walk the runs once to add the extra starts (lmax >= 26, so at most one cut each) */
-  { u32 todo = starts;
-    while (todo)
-      { const int a = __clz(todo);
-        todo &= ~(0x80000000u >> a);
-        const u32 after = (a == 31) ? 0u : (0xffffffffu >> (a+1));
-        const u32 stop = (starts | ~ok) & after;    /* next start or first illegal position after a */
-        const int e = stop ? __clz(stop) : SCAN_PPT;
-        if (e - a > p.lmax) { starts |= 0x80000000u >> (a + p.lmax); todo |= 0x80000000u >> (a + p.lmax); }
+    if (threadIdx.x & 1)                             /* j = 0 of an odd thread is not a multiple of 64: may continue */
+      { const u32 pb = nxt[(base-1) + ((base-1) >> 5)];
+        if ((s_okw[threadIdx.x-1] & 1u) && pb == bk[0]) same |= 0x80000000u;
       }
   }
+  const u32 okprev = (ok >> 1) | ((threadIdx.x & 1) ? (s_okw[threadIdx.x-1] << 31) : 0u);
+  const u32 cont = ok & okprev & same;
+  const u32 starts = ok & ~cont;                    /* bit 31-j = a super-mer starts at j */
   const u32 nrun = __popc(starts);
   u32 incl = nrun;
 #pragma unroll
@@ -1197,27 +1198,23 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
   u64 pos = s_base + woff + incl - nrun;
   if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and falls back */
 
+  const u64 tile0 = (u64) blockIdx.x * SCAN_TILE;
   u32 todo = starts;
   while (todo)
     { const int j = __clz(todo);
       todo &= ~(0x80000000u >> j);
+      /* length: first within this thread's window by bit tricks, then (rarely far) into the following windows */
       const u32 after = (j == 31) ? 0u : (0xffffffffu >> (j+1));
-      const u32 stop = (starts | ~ok) & after;
-      const int e = stop ? __clz(stop) : SCAN_PPT;
-      const u32 b = bk[j];
-      const int a = base + j;                            /* tile-local position of the first base */
-      const u32 *s = s_seq + SCAN_LHALO + (a >> 4);
-      const int sh = 2*(a & 15);
-      u32 x[6];
-#pragma unroll
-      for (int t = 0; t < 6; t++) x[t] = __funnelshift_l(s[t+1],s[t],sh);
-      /* 162 base bits: 34 into w0, then 2 x 64 */
-      u64 B0 = ((u64) x[0] << 32) | x[1], B1 = ((u64) x[2] << 32) | x[3], B2 = ((u64) x[4] << 32) | x[5];
-      Key<3> rec;
-      rec.w[0] = ((u64) b << (64 - p.bbits)) | ((u64) (e-j-1) << (64 - SUP_BBITS - SUP_LBITS)) | (B0 >> 30);
-      rec.w[1] = (B0 << 34) | (B1 >> 30);
-      rec.w[2] = (B1 << 34) | (B2 >> 30);
-      p.out[pos++] = rec;
+      const u32 stop = ~cont & after;
+      int e = stop ? __clz(stop) : SCAN_PPT;             /* window-local end (exclusive) */
+      int len = e - j;
+      if (e == SCAN_PPT)
+        { const u32 b = bk[j];
+          int q = base + SCAN_PPT;                       /* tile-local position of the next candidate */
+          while (q < SCAN_TILE && (q & 63) != 0 && ((s_okw[q >> 5] >> (31 - (q & 31))) & 1u) && nxt[q + (q >> 5)] == b)
+            { q++; len++; }
+        }
+      p.out[pos++] = ((u64) bk[j] << (64 - p.bbits)) | ((u64) (len-1) << SUP_PBITS) | (tile0 + (u64) (base + j));
     }
 }
 
@@ -1236,7 +1233,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
 #define BC_PERS  0x80000000u
 
 struct BucketParams
-  { const Key<3> *recs;
+  { const u64 *recs; const u32 *seq;
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
@@ -1329,14 +1326,18 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           /* load one piece: thread t unpacks super-mer t; block scan of the lengths */
           u32 l = 0;
           if (threadIdx.x < ns)
-            { const Key<3> sm = p.recs[q0 + threadIdx.x];
-              l = (u32) ((sm.w[0] >> (64 - SUP_BBITS - SUP_LBITS)) & 63u) + 1u;
-              const u64 B0 = (sm.w[0] << 30) | (sm.w[1] >> 34);
-              const u64 B1 = (sm.w[1] << 30) | (sm.w[2] >> 34);
-              const u64 B2 = (sm.w[2] << 30);
+            { const u64 sm = p.recs[q0 + threadIdx.x];
+              l = (u32) ((sm >> SUP_PBITS) & 63u) + 1u;
+              const u64 ps = sm & ((1ull << SUP_PBITS) - 1ull);
+              const u32 *g = p.seq + (ps >> 4);
+              const int sh = 2*(int) (ps & 15ull);
+              const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
+              u32 x[9];
+#pragma unroll
+              for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(g + t) : 0u;
               u32 *d = sbase + threadIdx.x*8;
-              d[0] = (u32) (B0 >> 32); d[1] = (u32) B0; d[2] = (u32) (B1 >> 32); d[3] = (u32) B1;
-              d[4] = (u32) (B2 >> 32); d[5] = (u32) B2; d[6] = 0; d[7] = 0;
+#pragma unroll
+              for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
             }
           u32 incl = l;
 #pragma unroll
