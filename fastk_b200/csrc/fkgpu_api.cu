@@ -843,10 +843,10 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   /* groups of whole buckets, ~TS super-mers each */
   static int bcvar = -1, tsv = 512;
   if (bcvar < 0)
-    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 3;
+    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 10;
       const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
     }
-  const u32 TS = (u32) tsv;
+  const u32 TS = (u32) ((bcvar == 8 || bcvar == 10 || bcvar == 11) ? std::min(tsv,384) : tsv);
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -861,16 +861,15 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(k,km);
-#define BC_LAUNCH(TPB,CH,DC) do { \
-      const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) BC_TS*4 + (size_t) (DC)*4 + (size_t) (TPB)*8*4 + (size_t) ((TPB)+2)*4 + (size_t) (CH)*2 + 64; \
-      CU(cudaFuncSetAttribute(k_bucket_count<TPB,CH,DC>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
-      k_bucket_count<TPB,CH,DC><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK(); } while (0)
-    if (bcvar == 1) BC_LAUNCH(256,1024,1536);
-    else if (bcvar == 3) BC_LAUNCH(512,1024,1024);
-    else if (bcvar == 4) BC_LAUNCH(256,1024,1024);
-    else if (bcvar == 5) BC_LAUNCH(512,2048,1024);
-    else if (bcvar == 6) BC_LAUNCH(1024,2048,2048);
-    else BC_LAUNCH(512,2048,2048);
+#define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
+      const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
+      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
+      k_bucket_count<TPB,GC,CH,DC,TSL><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK(); } while (0)
+    if (bcvar == 8) BC_LAUNCH(512,384,1024,1024,4096);
+    else if (bcvar == 9) BC_LAUNCH(512,512,768,1024,2048);
+    else if (bcvar == 10) BC_LAUNCH(512,384,768,1024,2048);
+    else if (bcvar == 11) BC_LAUNCH(384,384,768,1024,2048);
+    else BC_LAUNCH(512,512,1024,1024,4096);
   }
   stage_end(c,FKGPU_ST_BUCKET);
   Misc hm;

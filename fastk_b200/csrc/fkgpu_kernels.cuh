@@ -1226,9 +1226,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
  *  A group whose distinct keys overflow the pool is redone in 2x more rounds, each round taking the k-mers whose
  *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
 
-/* template parameters of k_bucket_count: BC_TPB threads (= super-mers held in smem per piece), BC_CH k-mer instances
- * expanded + inserted per chunk, BC_DC distinct-key pool; BC_TS hash slots                                        */
-#define BC_TS   4096
+/* template parameters of k_bucket_count: BC_TPB threads, BC_GC super-mers held in smem per piece, BC_CH new keys
+ * accepted per piece, BC_DC distinct-key pool, BC_TS hash slots (>= BC_DC + BC_CH so a probe always terminates)   */
 #define BC_EMPTY 0xffffffffu
 #define BC_PERS  0x80000000u
 
@@ -1288,9 +1287,9 @@ __device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
   return key;
 }
 
-template<int BC_TPB, int BC_CH, int BC_DC>
+template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS>
 __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
-{ constexpr int BC_GC = BC_TPB;
+{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
   Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
@@ -1298,7 +1297,8 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
   u32    *ocnt  = slot + BC_TS;                                      /* [BC_DC]              */
   u32    *sbase = ocnt + BC_DC;                                      /* [BC_GC][8] base words */
   u32    *spre  = sbase + BC_GC*8;                                   /* [BC_GC+1] prefix of the lengths */
-  unsigned short *newl = (unsigned short *) (spre + BC_GC + 2);      /* [BC_CH] slots claimed in this chunk */
+  u32    *sg0   = spre + BC_GC + 2;                                  /* [BC_GC][4] reverse strand of each super-mer's first k-mer */
+  unsigned short *newl = (unsigned short *) (sg0 + BC_GC*4);         /* [BC_CH] slots claimed in this piece */
   __shared__ u32 s_nnew[2], s_ovf, s_ecnt, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
   __shared__ u64 s_ebase;
 
@@ -1338,6 +1338,12 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
               u32 *d = sbase + threadIdx.x*8;
 #pragma unroll
               for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
+              /* both strands of the first k-mer: every loader thread does this together, so sliding onto the next
+                 super-mer inside the insert loop is a plain load instead of a divergent recomputation           */
+              u32 F0[4], G0[4];
+              supermer_strands(d,0,p.k,kmask,F0,G0);
+              u32 *gq = sg0 + threadIdx.x*4;
+              gq[0] = G0[0]; gq[1] = G0[1]; gq[2] = G0[2]; gq[3] = G0[3];
             }
           u32 incl = l;
 #pragma unroll
@@ -1359,7 +1365,7 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
             woff = __shfl_sync(0xffffffffu,x,wid ? wid-1 : 0);
             if (wid == 0) woff = 0;
           }
-          spre[threadIdx.x+1] = woff + incl;
+          if (threadIdx.x < BC_GC) spre[threadIdx.x+1] = woff + incl;
           if (threadIdx.x == 0) spre[0] = 0;
           __syncthreads();
           const u32 total = spre[ns];
@@ -1384,7 +1390,9 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
                         if (j >= slen)
                           { sidx++; j = 0; slen = spre[sidx+1] - spre[sidx];
                             sb = sbase + sidx*8;
-                            supermer_strands(sb,0,p.k,kmask,F,G);
+                            const u32 *gq = sg0 + sidx*4;
+#pragma unroll
+                            for (int t = 0; t < 4; t++) { F[t] = sb[t] & kmask[t]; G[t] = gq[t]; }
                           }
                         else
                           { const u32 qb = j + p.k - 1;

@@ -1,4 +1,4 @@
 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -2
-for v in "2 512" "2 1024" "3 512" "3 1024" "4 512" "5 512" "6 1024"; do set -- $v; echo "BC=$1 TS=$2"; FKGPU_BC=$1 FKGPU_TS=$2 python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --cutoff 0 2>&1 | tail -1 | python -c "
+for v in 7 8 9 10 11; do echo "BC=$v"; FKGPU_BC=$v python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --cutoff 0 2>&1 | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print(round(d['value'],2),'Gbases/s', round(d['ms_per_step'],1),'ms', {k:v['ms'] for k,v in d['roofline']['stages'].items() if v['ms']>0})"; done
