@@ -7,7 +7,7 @@ in-smem sort/count -> histogram -> table) over one batch of synthetic HiFi-like 
   value   device-resident: packed reads already in HBM when the timed region starts, results left in HBM
   e2e     the same batch through the reference-facing C ABI with HOST buffers: fkgpu_ingest of DATA_BLOCKs from
           pinned host memory (8 ingest threads, like io.c's ITHREADS), H2D, count, D2H of the table + histogram
-  roofline  dominant kernel (k_sortcount): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+  roofline  dominant kernel (k_bucket_count on the super-mer path): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
   cpu_baseline  the reference FastK (oracle/_ref, built from the reference's own sources) on a bounded sample
 
 `--impl reference` times only that CPU reference arm.  Under torchrun (N>1) every rank owns 1/N of the reads
@@ -299,18 +299,27 @@ def main():
                 r0, r1 = blocks[bi]
                 eng.ingest_ptr(base_ptr + r0 * (args.read_len + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
 
+        e2e_split = {"ingest_ms": 0.0, "finish_ms": 0.0}
+
         def e2e_step():
+            ta = time.perf_counter()
             eng.reset()
             th = [threading.Thread(target=worker, args=(t,)) for t in range(nthr)]
             for t in th:
                 t.start()
             for t in th:
                 t.join()
-            return eng.finish(fetch_table=True, copy_table=False)
+            tb = time.perf_counter()
+            r = eng.finish(fetch_table=True, copy_table=False)
+            tc = time.perf_counter()
+            e2e_split["ingest_ms"] += 1e3 * (tb - ta)
+            e2e_split["finish_ms"] += 1e3 * (tc - tb)
+            return r
 
         for _ in range(max(1, args.warmup - 1)):
             r2 = e2e_step()
         torch.cuda.synchronize()
+        e2e_split["ingest_ms"] = e2e_split["finish_ms"] = 0.0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             r2 = e2e_step()
@@ -319,6 +328,9 @@ def main():
         e2e = {"value": nbases * args.steps / (t1 - t0) / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(npos), "d2h_bytes_per_step": int(r2.ntable * (r2.kmer_bytes + 2) + 32768 * 8),
                "ms_per_step": 1e3 * (t1 - t0) / args.steps,
+               "ingest_ms_per_step": e2e_split["ingest_ms"] / args.steps,
+               "finish_ms_per_step": e2e_split["finish_ms"] / args.steps,
+               "finish_device_ms": r2.ms_total,
                "path": "fkgpu_ingest (8 threads, DATA_BLOCKs in pinned host memory) -> fkgpu_finish(fetch_table=1)"}
         assert r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct, "e2e and device-resident arms disagree"
 
@@ -334,11 +346,13 @@ def main():
     N, U = res.nkmers, res.ndistinct
     st = eng.last_stats() if world == 1 else dict(path=0, supermers=0, entries=0, groups=0)
     if st["path"] == 1:
-        # super-mer path: 24-byte super-mer records through the partition, 16-byte (key|count) entries through the sort
+        # super-mer path: 8-byte super-mer pointers (bucket|len|position) through the partition (histogram read, scatter
+        # read+write, refine 2 reads + write = 6 passes), base gather + 16-byte (key|count) entries out of the bucket
+        # kernel, entries through the weighted key-order sort
         S, E = st["supermers"], st["entries"]
-        alg = {"super_scan": nbases * 0.375 + S * 24,
-               "super_partition": 6 * S * 24,
-               "bucket_count": S * 24 + E * 16,
+        alg = {"super_scan": nbases * 0.375 + S * 8,
+               "super_partition": 6 * S * 8,
+               "bucket_count": S * 8 + (N + S * (k - 1)) * 0.25 + E * 16,
                "entry_partition": 3 * E * 16,
                "refine": 3 * E * 16,
                "sortcount": E * 16 + E * 20,
@@ -359,7 +373,9 @@ def main():
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get(dom)
+            tr = json.load(open(tj))
+            if dom in tr and tr.get("kmers"):
+                traffic = int(tr[dom] * (N / tr["kmers"]))       # ncu capture of a smaller batch, scaled by k-mers
         except Exception:
             traffic = None
     ach = per_stage[dom]["gbs"] or 0.0
