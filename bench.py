@@ -239,10 +239,18 @@ def main():
     # ---- build the batch: ASCII on the device -> packed (device-resident arm) and pinned host copy (e2e arm)
     ascii_dev = gen_reads_ascii(torch, dev, genome_bp, nreads, args.read_len, args.sub_rate, args.seed + 7919 * rank)
     eng = FastKGPU(k=k, table_cutoff=args.cutoff, device=local, nthreads=8, reserve_bases=npos)
-    sw, vw = eng.packed_words(npos)
-    d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
-    d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
-    eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, d_seq.data_ptr(), d_val.data_ptr())
+    runner = None
+    if world > 1:
+        # packed reads live in library-owned buffers that every peer maps over CUDA IPC (NVLink gathers in the count kernel)
+        from fastk_b200 import multigpu
+        runner = multigpu.MultiGPUCounter(eng, world, rank, dev)
+        seq_ptr, val_ptr = runner.alloc_reads(npos)
+    else:
+        sw, vw = eng.packed_words(npos)
+        d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
+        d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
+        seq_ptr, val_ptr = d_seq.data_ptr(), d_val.data_ptr()
+    eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, seq_ptr, val_ptr)
     torch.cuda.synchronize()
     host_ascii = None
     if not args.no_e2e and world == 1:
@@ -252,14 +260,11 @@ def main():
     torch.cuda.empty_cache()
 
     if world > 1:
-        from fastk_b200 import multigpu
-        runner = multigpu.MultiGPUCounter(eng, world, rank, dev)
-
         def one_step():
-            return runner.count_packed(d_seq, d_val, npos)
+            return runner.count_packed(seq_ptr, val_ptr, npos)
     else:
         def one_step():
-            return eng.count_packed(d_seq.data_ptr(), d_val.data_ptr(), npos, fetch_table=False)
+            return eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=False)
 
     # ---- device-resident arm ---------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -273,7 +278,7 @@ def main():
     for _ in range(args.steps):
         res = one_step()
         dev_ms += res.ms_total
-        for kname, v in eng.stage_times().items():
+        for kname, v in (res.stage_ms if world > 1 else eng.stage_times()).items():
             stage_ms[kname] = stage_ms.get(kname, 0.0) + v
     barrier()
     t1 = time.perf_counter()
@@ -344,7 +349,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     W = 8 if k <= 32 else 16
     N, U = res.nkmers, res.ndistinct
-    st = eng.last_stats() if world == 1 else dict(path=0, supermers=0, entries=0, groups=0)
+    if world == 1:
+        st = eng.last_stats()
+    else:
+        # rank 0's share of the job: its own stage times against its own record / entry counts
+        st = dict(path=1 if res.path == "super-mer" else 0, supermers=getattr(res, "supermers", 0),
+                  entries=getattr(res, "entries", 0), groups=0)
+        N, U = N // world, U // world
     if st["path"] == 1:
         # super-mer path: 8-byte super-mer pointers (bucket|len|position) through the partition (histogram read, scatter
         # read+write, refine 2 reads + write = 6 passes), base gather + 16-byte (key|count) entries out of the bucket
@@ -410,9 +421,15 @@ def main():
                            "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
                            "supermer_records": st["supermers"], "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),
-                           "parallelism": "1 process/GPU; prefix-range all-to-all over NCCL" if world > 1 else "single GPU"},
+                           "parallelism": ("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, bases gathered from "
+                                           "peer HBM over NVLink in the count kernel, second all-to-all of the distinct entries"
+                                           if st["path"] == 1 else "1 process/GPU; prefix-range all-to-all of k-mer records over NCCL")
+                           if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    if runner is not None:
+        dist.barrier(device_ids=[local])
+        runner.close_peers()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -616,11 +616,8 @@ static int choose_p2(fkgpu_ctx *c, int P1, int *P2)
   return FKGPU_OK;
 }
 
-static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true, int rec_words = 0)
+static int prepare_small(fkgpu_ctx *c, int P1)
 { const int nb1 = 1 << P1;
-  const size_t rb = (size_t) 8 * (rec_words ? rec_words : c->NW);
-  if (c->bufA.ensure((size_t) (nub + 4) * rb) || (needB && c->bufB.ensure((size_t) (nub + 4) * rb)))
-    return set_err(FKGPU_E_NOMEM,"out of device memory: two record buffers of %lld x %zu bytes",nub,rb);
   if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8)
       || c->ghist.ensure(FKGPU_HIST_BINS * 8) || c->misc.ensure(sizeof(Misc)))
     return set_err(FKGPU_E_NOMEM,"out of device memory (histograms)");
@@ -628,6 +625,13 @@ static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true
   CU(cudaMemsetAsync(c->ghist.p,0,FKGPU_HIST_BINS * 8,c->st));
   CU(cudaMemsetAsync(c->misc.p,0,sizeof(Misc),c->st));
   return FKGPU_OK;
+}
+
+static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true, int rec_words = 0)
+{ const size_t rb = (size_t) 8 * (rec_words ? rec_words : c->NW);
+  if (c->bufA.ensure((size_t) (nub + 4) * rb) || (needB && c->bufB.ensure((size_t) (nub + 4) * rb)))
+    return set_err(FKGPU_E_NOMEM,"out of device memory: two record buffers of %lld x %zu bytes",nub,rb);
+  return prepare_small(c,P1);
 }
 
 static void collect_times(fkgpu_ctx *c, fkgpu_result *res)
@@ -749,95 +753,91 @@ static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long
 /*  super-mer path: reads -> 24-byte super-mer records bucketed by canonical minimizer -> per-bucket on-chip
  *  expansion + hash count -> (only if a table / profiles are wanted) key-order sort of the distinct entries.   */
 
-static bool super_path_ok(fkgpu_ctx *c)
+static bool super_path_ok_k(int kmer)
 { static int forced = -1;
   if (forced < 0) { const char *e = getenv("FKGPU_PATH"); forced = e ? (strcmp(e,"records") == 0 ? 1 : (strcmp(e,"super") == 0 ? 2 : 0)) : 0; }
   if (forced == 1) return false;
-  return c->cfg.kmer >= 18 && c->cfg.kmer <= 56;
+  return kmer >= 18 && kmer <= 56;
 }
+static bool super_path_ok(fkgpu_ctx *c) { return super_path_ok_k(c->cfg.kmer); }
 
 struct SuperCounters { u64 nrec, nkmers, nent; u32 fail, pad; };
 
-static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
-                              bool own_total, bool *fell_back)
-{ const int k = c->cfg.kmer;
-  const int m = std::min(16,k - 8);
-  const int w = k - m + 1;
-  int p2 = 1; while (2*p2 <= w) p2 <<= 1;
-  const int lmax = SUP_LMAX;
-  *fell_back = false;
+struct SuperGeom { int k, m, w, p2, bbits, P1, P2; };
 
-  /* bucket-id width from the expected # of super-mers; the exact count is known after the scan */
-  const long long sest = std::max<long long>(1,npos / 10);
+/*  npos_total = positions over ALL ranks' read streams (multi-GPU: every rank must derive the same bucket-id width) */
+static SuperGeom super_geom(int k, long long npos_total)
+{ SuperGeom g;
+  g.k = k; g.m = std::min(16,k - 8); g.w = k - g.m + 1;
+  g.p2 = 1; while (2*g.p2 <= g.w) g.p2 <<= 1;
+  const long long sest = std::max<long long>(1,npos_total / 10);        /* expected # of super-mers */
   int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
-  if (bbits > 22) bbits = 22;
+  if (bbits > SUP_BBITS) bbits = SUP_BBITS;
   static int sp1 = -1, sbb = -1;
   if (sp1 < 0) { const char *e = getenv("FKGPU_SP1"); sp1 = e ? atoi(e) : 11; const char *f = getenv("FKGPU_SBB"); sbb = f ? atoi(f) : 0; }
   if (sbb > 0 && bbits > sbb) bbits = sbb;
-  const int P1 = std::min(bbits,sp1), P2 = bbits - P1;
-  const int nb1 = 1 << P1;
+  g.bbits = bbits; g.P1 = std::min(bbits,sp1); g.P2 = bbits - g.P1;
+  return g;
+}
 
-  int rc = prepare_common(c,npos,P1,true,2);
-  if (rc) return rc;
-  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
-  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
-  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
-  Misc *d_misc = (Misc *) c->misc.p;
+/*  stage A: reads -> super-mer records appended at out[0..) (count in d_cnt->nrec, k-mers covered in d_cnt->nkmers) */
+static int super_scan_stage(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, const SuperGeom &g, u64 pos_offset,
+                            u64 *out, u64 cap, SuperCounters *d_cnt)
+{ const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
+  if (ntiles <= 0) return FKGPU_OK;
+  SuperParams sp;
+  sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
+  sp.k = g.k; sp.m = g.m; sp.w = g.w; sp.p2 = g.p2; sp.lmax = SUP_LMAX; sp.bbits = g.bbits ? g.bbits : 1;
+  sp.out = out; sp.cap = cap; sp.counter = &d_cnt->nrec; sp.pos_offset = pos_offset;
+  const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_L) * 4;
+  CU(cudaFuncSetAttribute(k_super,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+  k_super<<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
+  return FKGPU_OK;
+}
 
-  /* the two super-mer buffers live inside record buffer A (free until the final sort) */
-  const size_t abytes = (size_t) (npos + 4) * 16;
-  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
-  Key<1> *SA = (Key<1> *) c->bufA.p;
-  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
-
-  if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
-  const long long ntiles = (npos + SCAN_TILE - 1) / SCAN_TILE;
-  stage_begin(c,FKGPU_ST_SUPERSCAN);
-  if (ntiles > 0)
-    { SuperParams sp;
-      sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
-      sp.k = k; sp.m = m; sp.w = w; sp.p2 = p2; sp.lmax = lmax; sp.bbits = bbits ? bbits : 1;
-      sp.out = (u64 *) SA; sp.cap = scap; sp.counter = &d_cnt->nrec;
-      const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_L) * 4;
-      CU(cudaFuncSetAttribute(k_super,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
-      k_super<<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
+/*  level-1 histogram + partition of S super-mer records on the top b1 bucket-id bits: in -> out, starts in c->off1,
+ *  per-bucket counts in c->hist1 (both 2^b1 (+1) u64)                                                                */
+static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S, int b1)
+{ const int n1 = 1 << b1;
+  const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+  const long long nt = (S + TP_TILE(1) - 1) / TP_TILE(1);
+  CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (n1 + 1) * 8,c->st));
+  if (nt > 0)
+    { k_tilepart<1,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>(in,NULL,(u64) S,b1,(u64 *) c->hist1.p); KCHECK(); }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
+  if (nt > 0)
+    { CU(cudaFuncSetAttribute(k_tilepart<1,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<1,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>(in,out,(u64) S,b1,(u64 *) c->cur1.p); KCHECK();
     }
-  stage_end(c,FKGPU_ST_SUPERSCAN);
-  SuperCounters hc;
-  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
-  CU(cudaStreamSynchronize(c->st));
-  if (hc.nrec > scap) { *fell_back = true; return FKGPU_OK; }        /* very short super-mers: use the record path */
-  const long long S = (long long) hc.nrec;
-  const int effbits = bbits ? bbits : 1;                              /* with bbits = 0 every id is 0 in a 1-bit field */
-  (void) effbits;
+  return FKGPU_OK;
+}
 
-  /* level 1 / level 2 partition of the super-mer records on the bucket id (top bits of w[0]) */
+/*  stage B: S super-mer records in `in` (consumed; `scratch` has room for S records too) -> bucket partition -> per-bucket
+ *  on-chip expansion + hash count.  Histogram contributions go to c->ghist, scalars to d_misc / d_cnt, the distinct
+ *  (key | count) entries to ent[0..ent_cap) when ent != NULL.  The records may point into the read streams of several
+ *  ranks (seqr/pbase, nranks > 1): the bucket kernel then gathers the bases from peer memory over NVLink.             */
+static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
+                             const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase,
+                             Key<2> *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
+{ Misc *d_misc = (Misc *) c->misc.p;
+  const int bbits = g.bbits;
   stage_begin(c,FKGPU_ST_SUPERPART);
-  const u64 *offs;
-  const Key<1> *recs;
-  long long mbuckets;
-  { const int b1 = bbits ? P1 : 0;
-    const int n1 = 1 << b1;
-    const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
-    const long long nt = (S + TP_TILE(1) - 1) / TP_TILE(1);
-    CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (nb1 + 1) * 8,c->st));
-    if (nt > 0)
-      { k_tilepart<1,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>(SA,NULL,(u64) S,b1,(u64 *) c->hist1.p); KCHECK(); }
-    k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
-    if (nt > 0)
-      { CU(cudaFuncSetAttribute(k_tilepart<1,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-        k_tilepart<1,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>(SA,SB,(u64) S,b1,(u64 *) c->cur1.p); KCHECK();
-      }
-    offs = (const u64 *) c->off1.p; recs = SB; mbuckets = n1;
-    if (bbits && P2 > 0)
-      { mbuckets = (long long) n1 << P2;
-        if (c->off2.ensure((size_t) (mbuckets + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
-        const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<1>) + (size_t) (1 << P2) * 4;
-        CU(cudaFuncSetAttribute(k_refine<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
-        k_refine<1><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(SB,SA,(const u64 *) c->off1.p,n1,b1,P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
-        offs = (const u64 *) c->off2.p; recs = SA;
-      }
-  }
+  const int b1 = bbits ? g.P1 : 0;
+  const int n1 = 1 << b1;
+  int rc = super_level1(c,in,scratch,S,b1);
+  if (rc) return rc;
+  const u64 *offs = (const u64 *) c->off1.p;
+  const Key<1> *recs = scratch;
+  long long mbuckets = n1;
+  if (bbits && g.P2 > 0)
+    { mbuckets = (long long) n1 << g.P2;
+      if (c->off2.ensure((size_t) (mbuckets + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
+      const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<1>) + (size_t) (1 << g.P2) * 4;
+      CU(cudaFuncSetAttribute(k_refine<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
+      CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
+      k_refine<1><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(scratch,in,(const u64 *) c->off1.p,n1,b1,g.P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
+      offs = (const u64 *) c->off2.p; recs = in;
+    }
   stage_end(c,FKGPU_ST_SUPERPART);
 
   /* groups of whole buckets, ~TS super-mers each */
@@ -853,14 +853,18 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   k_fill_u64<<<(unsigned) ((gmax + 1 + 255) / 256),256,0,c->st>>>(gstart,gmax + 1,offs + mbuckets); KCHECK();
   k_groups<<<(unsigned) ((mbuckets + 1 + 255) / 256),256,0,c->st>>>(offs,mbuckets,TS,gstart,gmax); KCHECK();
 
-  const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   stage_begin(c,FKGPU_ST_BUCKET);
   { BucketParams bp;
-    bp.recs = (const u64 *) recs; bp.seq = d_seq; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = k;
+    bp.recs = (const u64 *) recs; bp.seq = d_seq; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = g.k;
+    bp.nranks = nranks;
+    for (int r = 0; r < SUP_MAXRANKS; r++)
+      { bp.seqr[r] = (nranks > 1 && r < nranks) ? seqr[r] : d_seq;
+        bp.pbase[r] = (nranks > 1 && r < nranks) ? pbase[r] : 0;
+      }
     bp.g_hist = (u64 *) c->ghist.p; bp.g_maxinst = &d_misc->maxinst; bp.g_ndistinct = &d_misc->ndistinct;
-    bp.ent = want_entries ? (Key<2> *) c->bufB.p : NULL; bp.ent_cap = (u64) npos; bp.ent_counter = &d_cnt->nent;
+    bp.ent = ent; bp.ent_cap = ent_cap; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;
-    u32 km[4]; make_kmask(k,km);
+    u32 km[4]; make_kmask(g.k,km);
 #define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
       const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
       CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
@@ -872,46 +876,87 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     else BC_LAUNCH(512,512,1024,1024,4096);
   }
   stage_end(c,FKGPU_ST_BUCKET);
-  Misc hm;
-  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
-  CU(cudaMemcpyAsync(&hm,d_misc,sizeof(hm),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(hc,d_cnt,sizeof(*hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(hm,d_misc,sizeof(*hm),cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
-  if (hc.fail) return set_err(FKGPU_E_CUDA,"internal: %u bucket groups could not be counted on chip",hc.fail);
-  if (hc.nent > (u64) npos) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow");
+  if (hc->fail) return set_err(FKGPU_E_CUDA,"internal: %u bucket groups could not be counted on chip",hc->fail);
+  if (ent != NULL && hc->nent > ent_cap) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow (%llu > %llu)",hc->nent,ent_cap);
+  *ngroups = gmax;
+  return FKGPU_OK;
+}
+
+/*  stage C: U distinct (key | count in the low 16 bits) entries in `ent` -> key order -> table.  The record pipeline in
+ *  weighted mode; `ent` is consumed (second sort buffer), `other` holds U + 4 entries.                               */
+static int entries_sort_stage(fkgpu_ctx *c, void *ent, void *other, long long U, int fetch_table, fkgpu_result *res)
+{ Misc *d_misc = (Misc *) c->misc.p;
+  int q1, q2;
+  choose_levels(U,&q1,&q2);
+  const int n1 = 1 << q1;
+  if (c->hist1.ensure((size_t) (n1 + 1) * 8) || c->off1.ensure((size_t) (n1 + 1) * 8) || c->cur1.ensure((size_t) (n1 + 1) * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory");
+  CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (n1 + 1) * 8,c->st));
+  CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
+  const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+  const long long nt = (U + TP_TILE(2) - 1) / TP_TILE(2);
+  stage_begin(c,FKGPU_ST_ENTPART);
+  if (nt > 0)
+    { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) ent,NULL,(u64) U,q1,(u64 *) c->hist1.p); KCHECK(); }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
+  int rc = choose_p2(c,q1,&q2);
+  if (rc) return rc;
+  if (nt > 0)
+    { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) ent,(Key<2> *) other,(u64) U,q1,(u64 *) c->cur1.p); KCHECK();
+    }
+  stage_end(c,FKGPU_ST_ENTPART);
+  c->weighted = 1;
+  rc = count_from_level1<2>(c,std::max<long long>(U,1),q1,q2,fetch_table,res,other,ent);
+  c->weighted = 0;
+  return rc;
+}
+
+static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
+                              bool own_total, bool *fell_back)
+{ const SuperGeom g = super_geom(c->cfg.kmer,npos);
+  *fell_back = false;
+  int rc = prepare_common(c,npos,std::max(g.P1,1),true,2);
+  if (rc) return rc;
+  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+
+  /* the two super-mer buffers live inside record buffer A (free until the final sort) */
+  const size_t abytes = (size_t) (npos + 4) * 16;
+  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
+  Key<1> *SA = (Key<1> *) c->bufA.p;
+  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+
+  if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  stage_begin(c,FKGPU_ST_SUPERSCAN);
+  rc = super_scan_stage(c,d_seq,d_val,npos,g,0,(u64 *) SA,scap,d_cnt);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERSCAN);
+  SuperCounters hc;
+  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (hc.nrec > scap) { *fell_back = true; return FKGPU_OK; }        /* very short super-mers: use the record path */
+  const long long S = (long long) hc.nrec;
+
+  const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
+  Misc hm;
+  long long gmax = 0;
+  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) npos,d_cnt,&hc,&hm,&gmax);
+  if (rc) return rc;
   static int verbose = -1;
   if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose)
     fprintf(stderr,"[fkgpu] super-mer path: k=%d m=%d w=%d bbits=%d supermers=%llu (%.2f k-mers each) kmers=%llu distinct=%llu groups=%lld\n",
-            k,m,w,bbits,hc.nrec,hc.nrec ? (double) hc.nkmers / hc.nrec : 0.,hc.nkmers,hm.ndistinct,gmax);
+            g.k,g.m,g.w,g.bbits,hc.nrec,hc.nrec ? (double) hc.nkmers / hc.nrec : 0.,hc.nkmers,hm.ndistinct,gmax);
 
   res->ntable = 0; res->table = NULL; res->table_dev = NULL;
   c->ptab_n = 0;
   if (want_entries)
-    { /* key-order sort of the U distinct (key|count) entries: the record pipeline in weighted mode, E = buffer B is consumed */
-      const long long U = (long long) hc.nent;
-      int q1, q2;
-      choose_levels(U,&q1,&q2);
-      const int n1 = 1 << q1;
-      CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (std::max(n1,nb1) + 1) * 8,c->st));
-      CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
-      c->weighted = 1;
-      const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
-      const long long nt = (U + TP_TILE(2) - 1) / TP_TILE(2);
-      if (c->hist1.ensure((size_t) (n1 + 1) * 8) || c->off1.ensure((size_t) (n1 + 1) * 8) || c->cur1.ensure((size_t) (n1 + 1) * 8))
-        { c->weighted = 0; return set_err(FKGPU_E_NOMEM,"out of device memory"); }
-      stage_begin(c,FKGPU_ST_ENTPART);
-      if (nt > 0)
-        { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) c->bufB.p,NULL,(u64) U,q1,(u64 *) c->hist1.p); KCHECK(); }
-      k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
-      rc = choose_p2(c,q1,&q2);
-      if (rc) { c->weighted = 0; return rc; }
-      if (nt > 0)
-        { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-          k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) c->bufB.p,(Key<2> *) c->bufA.p,(u64) U,q1,(u64 *) c->cur1.p); KCHECK();
-        }
-      stage_end(c,FKGPU_ST_ENTPART);
-      rc = count_from_level1<2>(c,std::max<long long>(U,1),q1,q2,fetch_table,res,c->bufA.p,c->bufB.p);
-      c->weighted = 0;
+    { rc = entries_sort_stage(c,c->bufB.p,c->bufA.p,(long long) hc.nent,fetch_table,res);
       if (rc) return rc;
     }
   else
@@ -1096,6 +1141,181 @@ extern "C" int fkgpu_count_records(fkgpu_ctx *c, void *d_records, int64_t nrecor
   init_result(c,res);
   return (c->NW == 1) ? count_records_t<1>(c,d_records,nrecords,fetch_table,res)
                       : count_records_t<2>(c,d_records,nrecords,fetch_table,res);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  multi-GPU stages of the super-mer path                                                           */
+
+extern "C" int fkgpu_super_supported(int kmer)
+{ return super_path_ok_k(kmer) ? 1 : 0; }
+
+extern "C" int fkgpu_super_bucket_bits(int kmer, int64_t npos_total) { return super_geom(kmer,npos_total).bbits; }
+
+extern "C" int fkgpu_reads_alloc(fkgpu_ctx *c, int64_t npos, uint32_t **d_seq, uint32_t **d_val)
+{ if (c == NULL || d_seq == NULL || d_val == NULL || npos < 0) return set_err(FKGPU_E_ARG,"fkgpu_reads_alloc: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  int64_t sw, vw;
+  fkgpu_packed_words(npos,&sw,&vw);
+  if (c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4))
+    return set_err(FKGPU_E_NOMEM,"fkgpu_reads_alloc: out of device memory (packed reads of %lld positions)",(long long) npos);
+  *d_seq = (uint32_t *) c->seq.p; *d_val = (uint32_t *) c->val.p;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_ipc_export(fkgpu_ctx *c, const void *d_ptr, uint8_t *handle)
+{ if (c == NULL || d_ptr == NULL || handle == NULL) return set_err(FKGPU_E_ARG,"fkgpu_ipc_export: NULL argument");
+  CU(cudaSetDevice(c->cfg.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == FKGPU_IPC_HANDLE_BYTES,"IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h,(void *) d_ptr));
+  memcpy(handle,&h,sizeof(h));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_ipc_open(fkgpu_ctx *c, const uint8_t *handle, void **d_ptr)
+{ if (c == NULL || d_ptr == NULL || handle == NULL) return set_err(FKGPU_E_ARG,"fkgpu_ipc_open: NULL argument");
+  CU(cudaSetDevice(c->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h,handle,sizeof(h));
+  CU(cudaIpcOpenMemHandle(d_ptr,h,cudaIpcMemLazyEnablePeerAccess));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_ipc_close(fkgpu_ctx *c, void *d_ptr)
+{ if (c == NULL || d_ptr == NULL) return set_err(FKGPU_E_ARG,"fkgpu_ipc_close: NULL argument");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_super_scan(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int64_t npos_total,
+                                int64_t pos_offset, const uint64_t **d_records, int64_t *nrecords, int64_t *nkmers,
+                                const uint64_t **d_bucket_hist, const uint64_t **d_bucket_offsets, int32_t *hist_bits)
+{ if (c == NULL || d_records == NULL || nrecords == NULL || nkmers == NULL || d_bucket_hist == NULL || d_bucket_offsets == NULL
+      || hist_bits == NULL || npos < 0 || (npos > 0 && (d_seq == NULL || d_val == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_super_scan: bad argument");
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  if ((unsigned long long) (pos_offset + npos) >= (1ull << SUP_PBITS))
+    return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: global position %lld exceeds the %d-bit record field",(long long) (pos_offset + npos),SUP_PBITS);
+  CU(cudaSetDevice(c->cfg.device));
+  memset(c->used,0,sizeof(c->used));
+  const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
+  int rc = prepare_common(c,npos,std::max(g.P1,1),false,2);
+  if (rc) return rc;
+  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  const size_t abytes = (size_t) (npos + 4) * 16;
+  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
+  Key<1> *SA = (Key<1> *) c->bufA.p;
+  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  stage_begin(c,FKGPU_ST_SUPERSCAN);
+  rc = super_scan_stage(c,d_seq,d_val,npos,g,(u64) pos_offset,(u64 *) SA,scap,d_cnt);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERSCAN);
+  SuperCounters hc;
+  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (hc.nrec > scap) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: %llu super-mers exceed the staging buffer (very short super-mers)",hc.nrec);
+  const int b1 = g.bbits ? g.P1 : 0;
+  stage_begin(c,FKGPU_ST_SUPERPART);
+  rc = super_level1(c,SA,SB,(long long) hc.nrec,b1);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERPART);
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  fkgpu_result tmp; collect_times(c,&tmp);
+  *d_records = (const uint64_t *) SB; *nrecords = (int64_t) hc.nrec; *nkmers = (int64_t) hc.nkmers;
+  *d_bucket_hist = (const uint64_t *) c->hist1.p; *d_bucket_offsets = (const uint64_t *) c->off1.p; *hist_bits = b1;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrecords, int64_t npos_total, int32_t nranks,
+                                 const uint32_t *const *seq_of_rank, const int64_t *pos_base, int want_entries,
+                                 fkgpu_result *res, const void **d_entries, int64_t *nentries)
+{ if (c == NULL || res == NULL || nrecords < 0 || (nrecords > 0 && d_records == NULL) || nranks < 1 || nranks > SUP_MAXRANKS
+      || seq_of_rank == NULL || pos_base == NULL || (want_entries && (d_entries == NULL || nentries == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_super_count: bad argument");
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_count: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
+  int rc = prepare_small(c,std::max(g.P1,1));
+  if (rc) return rc;
+  if (c->bufA.ensure((size_t) (nrecords + 8) * 8) || c->segs.ensure(sizeof(SuperCounters)) || c->bsum.ensure(8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (super-mer scratch of %lld records)",(long long) nrecords);
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  /* k-mers covered by the received records = capacity bound of the distinct-entry buffer */
+  u64 nk = 0;
+  CU(cudaMemsetAsync(c->bsum.p,0,8,c->st));
+  if (nrecords > 0)
+    { k_sum_lengths<<<c->sms * 4,256,0,c->st>>>((const u64 *) d_records,(long long) nrecords,(u64 *) c->bsum.p); KCHECK(); }
+  CU(cudaMemcpyAsync(&nk,c->bsum.p,8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  Key<2> *ent = NULL;
+  if (want_entries)
+    { if (c->bufB.ensure((size_t) (nk + 4) * 16)) return set_err(FKGPU_E_NOMEM,"out of device memory (entries of %llu k-mers)",nk);
+      ent = (Key<2> *) c->bufB.p;
+    }
+  const u32 *seqr[SUP_MAXRANKS]; u64 pb[SUP_MAXRANKS];
+  for (int r = 0; r < SUP_MAXRANKS; r++)
+    { seqr[r] = seq_of_rank[r < nranks ? r : 0]; pb[r] = (u64) pos_base[r < nranks ? r : 0]; }
+  SuperCounters hc; Misc hm; long long gmax = 0;
+  rc = super_count_stage(c,g,(Key<1> *) d_records,(Key<1> *) c->bufA.p,(long long) nrecords,seqr[0],nranks,seqr,pb,
+                         ent,nk,d_cnt,&hc,&hm,&gmax);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  res->hist = c->h_hist;
+  res->max_inst = (int64_t) hm.maxinst;
+  res->ndistinct = (int64_t) hm.ndistinct;
+  res->nkmers = (int64_t) nk;
+  c->last_path = 1; c->st_super = (long long) nrecords; c->st_ent = want_entries ? (long long) hc.nent : 0; c->st_groups = gmax;
+  if (want_entries) { *d_entries = ent; *nentries = (int64_t) hc.nent; }
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_entries_partition(fkgpu_ctx *c, const void *d_entries, int64_t n, int bits, void *d_out,
+                                       uint64_t *d_hist, uint64_t *d_offsets)
+{ if (c == NULL || n < 0 || (n > 0 && (d_entries == NULL || d_out == NULL)) || d_hist == NULL || d_offsets == NULL || bits < 0 || bits > 11)
+    return set_err(FKGPU_E_ARG,"fkgpu_entries_partition: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const int n1 = 1 << bits;
+  if (c->cur1.ensure((size_t) (n1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (cursors)");
+  const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+  const long long nt = (n + TP_TILE(2) - 1) / TP_TILE(2);
+  CU(cudaMemsetAsync(d_hist,0,(size_t) n1 * 8,c->st));
+  if (nt > 0)
+    { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) d_entries,NULL,(u64) n,bits,(u64 *) d_hist); KCHECK(); }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) c->cur1.p,n1); KCHECK();
+  if (nt > 0)
+    { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) d_entries,(Key<2> *) d_out,(u64) n,bits,(u64 *) c->cur1.p); KCHECK();
+    }
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL || n < 0 || (n > 0 && d_entries == NULL)) return set_err(FKGPU_E_ARG,"fkgpu_entries_sort: bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  int rc = prepare_small(c,1);
+  if (rc) return rc;
+  if (c->bufA.ensure((size_t) (n + 4) * 16)) return set_err(FKGPU_E_NOMEM,"out of device memory (entry sort buffer)");
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  rc = entries_sort_stage(c,d_entries,c->bufA.p,(long long) n,fetch_table,res);
+  if (rc) return rc;
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  res->nkmers = 0; res->ndistinct = n;
+  return FKGPU_OK;
 }
 
 template<int NW>

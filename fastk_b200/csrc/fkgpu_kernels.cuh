@@ -1087,10 +1087,11 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
  *  a multiple of 64 (so no super-mer exceeds 64 k-mers and every thread can decide its starts locally).          */
 
 #define SUP_L     (SCAN_TILE + SCAN_TILE/32 + 64)   /* room for the +1-per-32 skew that keeps per-thread rows conflict-free */
-#define SUP_PBITS 34
+#define SUP_PBITS 36                                /* position field: global position over all ranks' read streams */
 #define SUP_LMAX  64
-#define SUP_BBITS 24
+#define SUP_BBITS 22                                /* most bucket-id bits (22 + 6 + 36 = 64)                        */
 #define SUP_LBITS 6
+#define SUP_MAXRANKS 8                              /* read streams (one per GPU of the node) a record can point into */
 
 struct SuperParams
   { const u32 *seq; const u32 *val;
@@ -1098,6 +1099,7 @@ struct SuperParams
     int        k, m, w, p2, lmax, bbits;      /* w = k-m+1 window of m-mers, p2 = largest power of two <= w */
     u64       *out; u64 cap;
     u64       *counter;                       /* [0] records emitted, [1] k-mers covered                    */
+    u64        pos_offset;                    /* global position of this stream's position 0 (multi-GPU: sum of the lower ranks' lengths) */
   };
 
 __device__ __forceinline__ u32 mix32(u32 x)   /* bijective (murmur3 finaliser) */
@@ -1198,7 +1200,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
   u64 pos = s_base + woff + incl - nrun;
   if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and falls back */
 
-  const u64 tile0 = (u64) blockIdx.x * SCAN_TILE;
+  const u64 tile0 = p.pos_offset + (u64) blockIdx.x * SCAN_TILE;
   u32 todo = starts;
   while (todo)
     { const int j = __clz(todo);
@@ -1233,6 +1235,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
 
 struct BucketParams
   { const u64 *recs; const u32 *seq;
+    const u32 *seqr[SUP_MAXRANKS];                       /* multi-GPU: packed reads of every rank (peer memory over NVLink) */
+    u64        pbase[SUP_MAXRANKS];                      /* global position of rank r's position 0                          */
+    int        nranks;                                   /* 1: every record points into seq                                 */
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
@@ -1328,8 +1333,16 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
           if (threadIdx.x < ns)
             { const u64 sm = p.recs[q0 + threadIdx.x];
               l = (u32) ((sm >> SUP_PBITS) & 63u) + 1u;
-              const u64 ps = sm & ((1ull << SUP_PBITS) - 1ull);
-              const u32 *g = p.seq + (ps >> 4);
+              u64 ps = sm & ((1ull << SUP_PBITS) - 1ull);
+              const u32 *sq = p.seq;
+              if (p.nranks > 1)
+                { u64 pb = 0;                         /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
+#pragma unroll
+                  for (int r = 1; r < SUP_MAXRANKS; r++)
+                    if (r < p.nranks && ps >= p.pbase[r]) { pb = p.pbase[r]; sq = p.seqr[r]; }
+                  ps -= pb;
+                }
+              const u32 *g = sq + (ps >> 4);
               const int sh = 2*(int) (ps & 15ull);
               const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
               u32 x[9];
@@ -1494,6 +1507,16 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
       if (threadIdx.x == 0) atomicAdd(p.g_ndistinct,(u64) nreal);
       __syncthreads();
     }
+}
+
+/* total k-mers covered by n super-mer records (sizes the distinct-entry buffer of a rank after the exchange) */
+__global__ void __launch_bounds__(256) k_sum_lengths(const u64 *recs, long long n, u64 *total)
+{ u64 s = 0;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+    s += ((recs[i] >> SUP_PBITS) & 63ull) + 1ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total,s);
 }
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -85,6 +85,28 @@ def load_library(path=None):
     lib.fkgpu_last_path.restype = C.c_int
     lib.fkgpu_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     lib.fkgpu_stage_times.restype = C.c_int
+    u8p, pp = C.POINTER(C.c_uint8), C.POINTER(vp)
+    lib.fkgpu_super_supported.argtypes = [C.c_int]
+    lib.fkgpu_super_supported.restype = C.c_int
+    lib.fkgpu_super_bucket_bits.argtypes = [C.c_int, i64]
+    lib.fkgpu_super_bucket_bits.restype = C.c_int
+    lib.fkgpu_reads_alloc.argtypes = [vp, i64, pp, pp]
+    lib.fkgpu_reads_alloc.restype = C.c_int
+    lib.fkgpu_ipc_export.argtypes = [vp, vp, u8p]
+    lib.fkgpu_ipc_export.restype = C.c_int
+    lib.fkgpu_ipc_open.argtypes = [vp, u8p, pp]
+    lib.fkgpu_ipc_open.restype = C.c_int
+    lib.fkgpu_ipc_close.argtypes = [vp, vp]
+    lib.fkgpu_ipc_close.restype = C.c_int
+    lib.fkgpu_super_scan.argtypes = [vp, vp, vp, i64, i64, i64, pp, C.POINTER(i64), C.POINTER(i64), pp, pp, C.POINTER(i32)]
+    lib.fkgpu_super_scan.restype = C.c_int
+    lib.fkgpu_super_count.argtypes = [vp, vp, i64, i64, i32, pp, C.POINTER(i64), C.c_int, C.POINTER(_Result), pp,
+                                      C.POINTER(i64)]
+    lib.fkgpu_super_count.restype = C.c_int
+    lib.fkgpu_entries_partition.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp]
+    lib.fkgpu_entries_partition.restype = C.c_int
+    lib.fkgpu_entries_sort.argtypes = [vp, vp, i64, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_entries_sort.restype = C.c_int
     if path is None:
         _lib = lib
     return lib
@@ -93,7 +115,9 @@ def load_library(path=None):
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
            "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
-           "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times"]
+           "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
+           "fkgpu_super_supported", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
+           "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort"]
 
 
 class FkResult:
@@ -129,6 +153,7 @@ class FastKGPU:
             raise FkgpuError(f"fkgpu_create -> {rc}: {self.lib.fkgpu_last_error().decode()}")
         self.h = h
         self.k = k
+        self.table_cutoff, self.profile = table_cutoff, bool(profile)
 
     def _chk(self, rc, what):
         if rc != 0:
@@ -189,6 +214,58 @@ class FastKGPU:
         r = _Result()
         self._chk(self.lib.fkgpu_count_records(self.h, d_rec_ptr, n, 1 if fetch_table else 0, C.byref(r)),
                   "fkgpu_count_records")
+        return FkResult(r, copy_table)
+
+    # ---- multi-GPU stages of the super-mer path (include/fastk_gpu.h) ------------------------------------------
+    def super_supported(self):
+        return bool(self.lib.fkgpu_super_supported(self.k))
+
+    def reads_alloc(self, npos):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._chk(self.lib.fkgpu_reads_alloc(self.h, npos, C.byref(a), C.byref(b)), "fkgpu_reads_alloc")
+        return a.value, b.value
+
+    def ipc_export(self, d_ptr):
+        h = (C.c_uint8 * 64)()
+        self._chk(self.lib.fkgpu_ipc_export(self.h, d_ptr, h), "fkgpu_ipc_export")
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self._chk(self.lib.fkgpu_ipc_open(self.h, h, C.byref(out)), "fkgpu_ipc_open")
+        return out.value
+
+    def ipc_close(self, d_ptr):
+        self._chk(self.lib.fkgpu_ipc_close(self.h, d_ptr), "fkgpu_ipc_close")
+
+    def super_scan(self, d_seq_ptr, d_val_ptr, npos, npos_total, pos_offset):
+        """-> dict(records=device ptr, n, nkmers, hist=device ptr, offsets=device ptr, bits)"""
+        rec, hist, offs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, nk, bits = C.c_int64(), C.c_int64(), C.c_int32()
+        self._chk(self.lib.fkgpu_super_scan(self.h, d_seq_ptr, d_val_ptr, npos, npos_total, pos_offset, C.byref(rec),
+                                            C.byref(n), C.byref(nk), C.byref(hist), C.byref(offs), C.byref(bits)),
+                  "fkgpu_super_scan")
+        return dict(records=rec.value or 0, n=n.value, nkmers=nk.value, hist=hist.value, offsets=offs.value, bits=bits.value)
+
+    def super_count(self, d_rec_ptr, n, npos_total, seq_ptrs, pos_base, want_entries):
+        """-> (FkResult with the histogram of this rank's buckets, entries device ptr, # entries)"""
+        nr = len(seq_ptrs)
+        sp = (C.c_void_p * nr)(*seq_ptrs)
+        pb = (C.c_int64 * (nr + 1))(*pos_base)
+        r = _Result()
+        ent, ne = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.fkgpu_super_count(self.h, d_rec_ptr, n, npos_total, nr, sp, pb, 1 if want_entries else 0,
+                                             C.byref(r), C.byref(ent), C.byref(ne)), "fkgpu_super_count")
+        return FkResult(r, False), (ent.value or 0), ne.value
+
+    def entries_partition(self, d_ent_ptr, n, bits, d_out_ptr, d_hist_ptr, d_off_ptr):
+        self._chk(self.lib.fkgpu_entries_partition(self.h, d_ent_ptr, n, bits, d_out_ptr, d_hist_ptr, d_off_ptr),
+                  "fkgpu_entries_partition")
+
+    def entries_sort(self, d_ent_ptr, n, fetch_table=False, copy_table=True):
+        r = _Result()
+        self._chk(self.lib.fkgpu_entries_sort(self.h, d_ent_ptr, n, 1 if fetch_table else 0, C.byref(r)), "fkgpu_entries_sort")
         return FkResult(r, copy_table)
 
     def last_stats(self):

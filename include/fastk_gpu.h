@@ -139,6 +139,40 @@ int  fkgpu_scatter_prefix(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t 
                           uint64_t *d_offsets);
 int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int fetch_table, fkgpu_result *res);
 
+/*  Multi-GPU stages of the super-mer path (k in 18..56; fastk_b200/multigpu.py drives them, one process per GPU).
+ *  A super-mer record is 8 bytes, [minimizer bucket : <= 22][# k-mers - 1 : 6][GLOBAL position of its first base : 36],
+ *  where the global position space is the concatenation of every rank's packed read stream (rank r starts at
+ *  pos_base[r]).  Ranks own contiguous bucket ranges; ONE all-to-all moves the 8-byte records (not the k-mers), and the
+ *  counting kernel of the owner gathers the bases straight from the source rank's HBM over NVLink (peer pointers obtained
+ *  with the IPC calls below).  Every instance of a canonical k-mer falls in one bucket, so counts never merge across
+ *  ranks; only the (much smaller) distinct (key | count) entries take a second all-to-all, by key prefix, when a sorted
+ *  table is wanted.
+ *   fkgpu_reads_alloc       packed-read buffers owned by the context (plain cudaMalloc: exportable over CUDA IPC)
+ *   fkgpu_ipc_export/open/close   64-byte handle of a device allocation <-> pointer valid in this process
+ *   fkgpu_super_bucket_bits bucket-id width every rank derives from the GLOBAL position count
+ *   fkgpu_super_scan        reads -> records, partitioned by the top *hist_bits bucket bits; all outputs are device
+ *                           pointers into context memory, valid until the next call on this context
+ *   fkgpu_super_count       received records (consumed; room for nrecords + 8) -> histogram / scalars in res and, if
+ *                           want_entries, the distinct (16-byte key | count in the low 16 bits) entries on the device
+ *   fkgpu_entries_partition entries -> d_out ordered by the top `bits` key bits; d_hist [2^bits], d_offsets [2^bits+1]
+ *   fkgpu_entries_sort      distinct entries (consumed; room for n + 4) -> key order -> table in res               */
+#define FKGPU_IPC_HANDLE_BYTES 64
+int  fkgpu_super_supported(int kmer);
+int  fkgpu_super_bucket_bits(int kmer, int64_t npos_total);
+int  fkgpu_reads_alloc(fkgpu_ctx *ctx, int64_t npos, uint32_t **d_seq, uint32_t **d_val);
+int  fkgpu_ipc_export(fkgpu_ctx *ctx, const void *d_ptr, uint8_t *handle /*[FKGPU_IPC_HANDLE_BYTES]*/);
+int  fkgpu_ipc_open  (fkgpu_ctx *ctx, const uint8_t *handle, void **d_ptr);
+int  fkgpu_ipc_close (fkgpu_ctx *ctx, void *d_ptr);
+int  fkgpu_super_scan(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int64_t npos_total,
+                      int64_t pos_offset, const uint64_t **d_records, int64_t *nrecords, int64_t *nkmers,
+                      const uint64_t **d_bucket_hist, const uint64_t **d_bucket_offsets, int32_t *hist_bits);
+int  fkgpu_super_count(fkgpu_ctx *ctx, uint64_t *d_records, int64_t nrecords, int64_t npos_total, int32_t nranks,
+                       const uint32_t *const *seq_of_rank, const int64_t *pos_base, int want_entries,
+                       fkgpu_result *res, const void **d_entries, int64_t *nentries);
+int  fkgpu_entries_partition(fkgpu_ctx *ctx, const void *d_entries, int64_t n, int bits, void *d_out,
+                             uint64_t *d_hist, uint64_t *d_offsets);
+int  fkgpu_entries_sort(fkgpu_ctx *ctx, void *d_entries, int64_t n, int fetch_table, fkgpu_result *res);
+
 /*  Instrumentation for bench.py: # of kernel launches issued by this context so far, and the
  *  accumulated CUDA-event time / algorithmic bytes of the dominant kernel family (final sort+count). */
 int64_t fkgpu_launch_count(fkgpu_ctx *ctx);

@@ -28,13 +28,13 @@ def main():
     bases, boff = synth.to_block(reads)
     npos = len(bases)
     a = torch.frombuffer(bytearray(bases + b"\0" * 64), dtype=torch.uint8).to(dev)
-    sw, vw = eng.packed_words(npos)
-    d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
-    d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
-    eng.pack_ascii_dev(a.data_ptr(), npos, d_seq.data_ptr(), d_val.data_ptr())
-    torch.cuda.synchronize()
     mg = multigpu.MultiGPUCounter(eng, world, rank, dev)
+    d_seq, d_val = mg.alloc_reads(npos)        # library-owned: the peers map them over CUDA IPC (super-mer path)
+    eng.pack_ascii_dev(a.data_ptr(), npos, d_seq, d_val)
+    torch.cuda.synchronize()
     out = mg.count_packed(d_seq, d_val, npos, fetch_table=True)
+    want_path = sys.argv[2] if len(sys.argv) > 2 else None
+    assert want_path is None or out.path == want_path, (out.path, want_path)
     tw = out.kmer_bytes + 2
     mx = max(out.table_sizes)
     mine = torch.zeros((mx, tw), dtype=torch.uint8, device=dev)
@@ -55,10 +55,12 @@ def main():
             assert out.nkmers == want.nkmers and out.ndistinct == want.ndistinct and out.max_inst == want.max_inst
             assert np.array_equal(out.hist[1:], want.hist[1:]), "global histogram differs"
             assert out.ntable == want.ntable and np.array_equal(table, want.table), "rank-ordered table differs"
-            print(f"MGPU_OK world={world} k={k} kmers={out.nkmers} distinct={out.ndistinct} sizes={out.table_sizes}")
+            print(f"MGPU_OK world={world} k={k} path={out.path} kmers={out.nkmers} distinct={out.ndistinct} sizes={out.table_sizes}")
         except AssertionError as e:
             ok = 0
             print("MGPU_FAIL", e)
+    dist.barrier(device_ids=[local])
+    mg.close_peers()
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -16,13 +16,24 @@ def _ngpu():
     return fastk_b200.load_library().fkgpu_device_count()
 
 
-@pytest.mark.parametrize("k", [40, 21])
-def test_multi_gpu_equals_single_gpu(k):
+@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (21, "super-mer", {}), (40, "records", {"FKGPU_MG": "records"}),
+                                        (63, "records", {})])
+def test_multi_gpu_equals_single_gpu(k, path, env):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(HERE, "mgpu_worker.py"), str(k)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(HERE, "mgpu_worker.py"), str(k), path]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (40, "records", {"FKGPU_MG": "records"})])
+def test_multi_gpu_stages_world1(k, path, env):
+    """The same staged pipeline (scan -> exchange -> count -> entry exchange -> sort) with a world of ONE rank: runs on a
+    single-GPU box, so every stage entry point of the multi-GPU path is parity-checked there too."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1",
+           "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(HERE, "mgpu_worker.py"), str(k), path]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
