@@ -6,7 +6,7 @@ in-smem sort/count -> histogram -> table) over one batch of synthetic HiFi-like 
 
   value   device-resident: packed reads already in HBM when the timed region starts, results left in HBM
   e2e     the same batch through the reference-facing C ABI with HOST buffers: fkgpu_ingest of DATA_BLOCKs from
-          pinned host memory (8 ingest threads, like io.c's ITHREADS), H2D, count, D2H of the table + histogram
+          pinned host memory (one ingest thread per host core up to 16, like io.c's ITHREADS), H2D, count, D2H of the table + histogram
   roofline  dominant kernel (k_bucket_count on the super-mer path): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
   cpu_baseline  the reference FastK (oracle/_ref, built from the reference's own sources) on a bounded sample
 
@@ -238,7 +238,8 @@ def main():
 
     # ---- build the batch: ASCII on the device -> packed (device-resident arm) and pinned host copy (e2e arm)
     ascii_dev = gen_reads_ascii(torch, dev, genome_bp, nreads, args.read_len, args.sub_rate, args.seed + 7919 * rank)
-    eng = FastKGPU(k=k, table_cutoff=args.cutoff, device=local, nthreads=8, reserve_bases=npos)
+    nthr = max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
+    eng = FastKGPU(k=k, table_cutoff=args.cutoff, device=local, nthreads=nthr, reserve_bases=npos)
     runner = None
     if world > 1:
         # packed reads live in library-owned buffers that every peer maps over CUDA IPC (NVLink gathers in the count kernel)
@@ -297,7 +298,6 @@ def main():
         boff_full = (np.arange(rows_per_block + 1, dtype=np.int64) * (args.read_len + 1)).astype(np.int32)
         base_ptr = host_ascii.data_ptr()
         blocks = [(r0, min(nreads, r0 + rows_per_block)) for r0 in range(0, nreads, rows_per_block)]
-        nthr = 8
 
         def worker(tid):
             for bi in range(tid, len(blocks), nthr):
@@ -336,7 +336,8 @@ def main():
                "ingest_ms_per_step": e2e_split["ingest_ms"] / args.steps,
                "finish_ms_per_step": e2e_split["finish_ms"] / args.steps,
                "finish_device_ms": r2.ms_total,
-               "path": "fkgpu_ingest (8 threads, DATA_BLOCKs in pinned host memory) -> fkgpu_finish(fetch_table=1)"}
+               "path": f"fkgpu_ingest ({nthr} threads, DATA_BLOCKs in pinned host memory; chunks packed + scanned on the device as "
+                       "they land) -> fkgpu_finish(fetch_table=1)"}
         assert r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct, "e2e and device-resident arms disagree"
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------

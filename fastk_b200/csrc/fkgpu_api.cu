@@ -60,7 +60,9 @@ struct PinBuf
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
   };
 
-#define CHUNK_BYTES (32u << 20)
+#define CHUNK_BYTES (8u << 20)         /* pinned staging chunk per ingest thread; also the granule of the streamed pack + scan */
+
+struct SuperGeom { int k, m, w, p2, bbits, P1, P2; };
 
 struct TidState
   { char   *pin = nullptr;            /* pinned staging chunk                       */
@@ -92,6 +94,12 @@ struct fkgpu_ctx
     long long    ascii_used = 0;
     long long    nreads = 0, nbases = 0;
     bool         finished = false;
+    /* streamed front end (cfg.reserve_bases > 0): every staging chunk is packed -- and, on the super-mer path, scanned
+       into super-mer records -- as soon as its host-to-device copy lands, overlapping the ingest                       */
+    size_t       chunk_bytes = CHUNK_BYTES;   /* FKGPU_CHUNK_BYTES overrides (tests force many small chunks) */
+    bool         stream_started = false, stream_on = false, stream_scan = false;
+    long long    stream_cap = 0;      /* positions the device buffers were sized for */
+    SuperGeom    sgeom;
 
     /* device working set */
     DevBuf ctah, ctao, seq, val, bufA, bufB, scnt, hist1, off1, cur1, off2, gstart, eall, epass, poff, bsum, ghist, misc, table;
@@ -145,6 +153,9 @@ extern "C" int fkgpu_create(const fkgpu_config *cfg, fkgpu_ctx **out)
   c->NW = (cfg->kmer <= 32) ? 1 : 2;
   c->kbytes = (2*cfg->kmer + 7) >> 3;
   c->tids.resize(c->cfg.nthreads);
+  { const char *e = getenv("FKGPU_CHUNK_BYTES");
+    if (e && atoll(e) >= 4096) c->chunk_bytes = ((size_t) atoll(e) + 63) & ~(size_t) 63;
+  }
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop,cfg->device));
   c->sms = prop.multiProcessorCount;
@@ -186,6 +197,7 @@ extern "C" int fkgpu_reset(fkgpu_ctx *c)
   for (auto &t : c->tids)
     { t.fill = 0; t.inflight = false; t.chunks.clear(); t.rstart.clear(); t.rlen.clear(); t.rcont.clear(); t.carry = 0; }
   c->ascii_used = 0; c->nreads = 0; c->nbases = 0; c->finished = false;
+  c->stream_started = c->stream_on = c->stream_scan = false;
   return FKGPU_OK;
 }
 
@@ -237,20 +249,36 @@ static int ascii_reserve(fkgpu_ctx *c, long long need)      /* c->mu held */
   return 0;
 }
 
+static int stream_begin(fkgpu_ctx *c);
+static int stream_chunk(fkgpu_ctx *c, long long off, long long len);
+
 static int flush_tid(fkgpu_ctx *c, TidState &t)
 { if (t.fill == 0) return FKGPU_OK;
+  /* chunks start on multiples of 64 positions (whole seq / val words per chunk); the gap is zero = invalid positions */
+  const size_t padded = (t.fill + 63) & ~(size_t) 63;
+  memset(t.pin + t.fill,0,padded - t.fill);
   long long off;
   { std::lock_guard<std::mutex> lk(c->mu);
-    if (ascii_reserve(c,c->ascii_used + (long long) t.fill))
-      return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot grow the device read buffer to %lld bytes",c->ascii_used + (long long) t.fill);
+    if (c->stream_on && c->ascii_used + (long long) padded > c->stream_cap)
+      { /* more reads than reserved: the buffers must grow, so the rest is packed and scanned at finish instead */
+        CU(cudaStreamSynchronize(c->st));
+        c->stream_on = c->stream_scan = false;
+      }
+    if (ascii_reserve(c,c->ascii_used + (long long) padded))
+      return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot grow the device read buffer to %lld bytes",c->ascii_used + (long long) padded);
     off = c->ascii_used;
-    c->ascii_used += (long long) t.fill;
-    /* rebase the read starts of this chunk (they were recorded chunk-relative, tagged negative) */
-    CU(cudaMemcpyAsync((char *) c->ascii.p + off,t.pin,t.fill,cudaMemcpyHostToDevice,c->cst));
+    c->ascii_used += (long long) padded;
+    CU(cudaMemcpyAsync((char *) c->ascii.p + off,t.pin,padded,cudaMemcpyHostToDevice,c->cst));
     CU(cudaEventRecord(t.done,c->cst));
+    if (c->stream_on)
+      { CU(cudaStreamWaitEvent(c->st,t.done,0));
+        int rc = stream_chunk(c,off,(long long) padded);
+        if (rc) return rc;
+      }
   }
   t.inflight = true;
   t.chunks.push_back(std::make_pair(off,(long long) t.fill));
+  /* rebase the read starts of this chunk (they were recorded chunk-relative, tagged negative) */
   for (size_t i = t.rstart.size(); i-- > 0; )
     { if (t.rstart[i] >= 0) break;
       t.rstart[i] = off + (-(t.rstart[i]) - 1);
@@ -267,14 +295,21 @@ extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int3
   if (nreads <= 0) return FKGPU_OK;
   CU(cudaSetDevice(c->cfg.device));
   TidState &t = c->tids[tid];
+  if (!c->stream_started)
+    { std::lock_guard<std::mutex> lk(c->mu);
+      if (!c->stream_started)
+        { int rc = stream_begin(c);
+          if (rc) return rc;
+        }
+    }
   if (t.pin == nullptr)
-    { if (cudaMallocHost((void **) &t.pin,CHUNK_BYTES) != cudaSuccess)
+    { if (cudaMallocHost((void **) &t.pin,c->chunk_bytes + 64) != cudaSuccess)
         { cudaGetLastError(); return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot allocate pinned staging"); }
       CU(cudaEventCreateWithFlags(&t.done,cudaEventDisableTiming));
     }
   const size_t len = (size_t) boff[nreads] - (size_t) boff[0];
-  if (len > CHUNK_BYTES) return set_err(FKGPU_E_ARG,"fkgpu_ingest: block of %zu bytes exceeds the %u byte staging chunk",len,CHUNK_BYTES);
-  if (t.fill + len > CHUNK_BYTES)
+  if (len > c->chunk_bytes) return set_err(FKGPU_E_ARG,"fkgpu_ingest: block of %zu bytes exceeds the %zu byte staging chunk",len,c->chunk_bytes);
+  if (t.fill + len > c->chunk_bytes)
     { int rc = flush_tid(c,t);
       if (rc) return rc;
     }
@@ -763,8 +798,6 @@ static bool super_path_ok(fkgpu_ctx *c) { return super_path_ok_k(c->cfg.kmer); }
 
 struct SuperCounters { u64 nrec, nkmers, nent; u32 fail, pad; };
 
-struct SuperGeom { int k, m, w, p2, bbits, P1, P2; };
-
 /*  npos_total = positions over ALL ranks' read streams (multi-GPU: every rank must derive the same bucket-id width) */
 static SuperGeom super_geom(int k, long long npos_total)
 { SuperGeom g;
@@ -915,27 +948,43 @@ static int entries_sort_stage(fkgpu_ctx *c, void *ent, void *other, long long U,
   return rc;
 }
 
-static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
-                              bool own_total, bool *fell_back)
-{ const SuperGeom g = super_geom(c->cfg.kmer,npos);
-  *fell_back = false;
-  int rc = prepare_common(c,npos,std::max(g.P1,1),true,2);
-  if (rc) return rc;
-  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
-  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
-  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+/*  layout of the super-mer staging inside record buffer A (free until the final sort), for a buffer sized for nub positions */
+struct SuperBufs { Key<1> *SA, *SB; u64 scap; };
+static SuperBufs super_bufs(fkgpu_ctx *c, long long nub)
+{ SuperBufs b;
+  const size_t abytes = (size_t) (nub + 4) * 16;
+  b.scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
+  b.SA = (Key<1> *) c->bufA.p;
+  b.SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+  return b;
+}
 
-  /* the two super-mer buffers live inside record buffer A (free until the final sort) */
-  const size_t abytes = (size_t) (npos + 4) * 16;
-  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
-  Key<1> *SA = (Key<1> *) c->bufA.p;
-  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+/*  prescanned: the streamed front end (stream_begin / stream_chunk) already sized the buffers for c->stream_cap positions,
+ *  zeroed the counters and scanned every chunk into super-mer records during the ingest                                  */
+static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
+                              bool own_total, bool *fell_back, bool prescanned)
+{ const long long nub = prescanned ? c->stream_cap : npos;
+  const SuperGeom g = prescanned ? c->sgeom : super_geom(c->cfg.kmer,npos);
+  *fell_back = false;
+  int rc;
+  if (!prescanned)
+    { rc = prepare_common(c,nub,std::max(g.P1,1),true,2);
+      if (rc) return rc;
+      if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+    }
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  if (!prescanned) CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  const SuperBufs sb = super_bufs(c,nub);
+  Key<1> *SA = sb.SA, *SB = sb.SB;
+  const u64 scap = sb.scap;
 
   if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
-  stage_begin(c,FKGPU_ST_SUPERSCAN);
-  rc = super_scan_stage(c,d_seq,d_val,npos,g,0,(u64 *) SA,scap,d_cnt);
-  if (rc) return rc;
-  stage_end(c,FKGPU_ST_SUPERSCAN);
+  if (!prescanned)
+    { stage_begin(c,FKGPU_ST_SUPERSCAN);
+      rc = super_scan_stage(c,d_seq,d_val,npos,g,0,(u64 *) SA,scap,d_cnt);
+      if (rc) return rc;
+      stage_end(c,FKGPU_ST_SUPERSCAN);
+    }
   SuperCounters hc;
   CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
@@ -945,7 +994,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   Misc hm;
   long long gmax = 0;
-  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) npos,d_cnt,&hc,&hm,&gmax);
+  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   static int verbose = -1;
   if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
@@ -976,11 +1025,54 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   return FKGPU_OK;
 }
 
-static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res, bool own_total)
+/*  Streamed front end.  stream_begin (first fkgpu_ingest after create / reset, c->mu held) sizes the device buffers from
+ *  cfg.reserve_bases; stream_chunk (flush_tid, c->mu held, after c->st was made to wait for the chunk's copy) packs the
+ *  chunk and, on the super-mer path, appends its super-mer records: chunks are self-contained (whole 0-terminated reads,
+ *  a continued read re-delivers its k-1 overlap), so no k-mer spans two chunks.                                        */
+static int stream_begin(fkgpu_ctx *c)
+{ c->stream_started = true; c->stream_on = c->stream_scan = false;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("FKGPU_NOSTREAM"); off = (e && atoi(e)) ? 1 : 0; }
+  if (c->cfg.reserve_bases <= 0 || off) return FKGPU_OK;
+  if (ascii_reserve(c,1)) return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot reserve the device read buffer");
+  long long cap = std::min<long long>((long long) c->ascii.cap - 256,c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20));
+  cap &= ~63ll;
+  int64_t sw, vw;
+  fkgpu_packed_words(cap,&sw,&vw);
+  if (c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (packed reads)");
+  c->stream_cap = cap;
+  c->stream_on = true;
+  if (super_path_ok(c) && c->cfg.bc_prefix == 0)
+    { c->sgeom = super_geom(c->cfg.kmer,cap);
+      int rc = prepare_common(c,cap,std::max(c->sgeom.P1,1),true,2);
+      if (rc) return rc;
+      if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+      CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
+      c->stream_scan = true;
+    }
+  return FKGPU_OK;
+}
+
+static int stream_chunk(fkgpu_ctx *c, long long off, long long len)       /* off, len: multiples of 64 positions */
+{ u32 *seq = (u32 *) c->seq.p + (off >> 4), *val = (u32 *) c->val.p + (off >> 5);
+  const long long vw = len >> 5;
+  if (vw <= 0) return FKGPU_OK;
+  k_pack_ascii<<<(unsigned) ((vw + 255) / 256),256,0,c->st>>>((const uint4 *) ((const char *) c->ascii.p + off),len,seq,val,vw);
+  KCHECK();
+  if (c->stream_scan)
+    { const SuperBufs sb = super_bufs(c,c->stream_cap);
+      return super_scan_stage(c,seq,val,len,c->sgeom,(u64) off,(u64 *) sb.SA,sb.scap,(SuperCounters *) c->segs.p);
+    }
+  return FKGPU_OK;
+}
+
+static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res, bool own_total,
+                            bool prescanned = false)
 { c->last_path = 0;
   if (super_path_ok(c))
     { bool fb = false;
-      int rc = count_packed_super(c,d_seq,d_val,npos,fetch_table,res,own_total,&fb);
+      int rc = count_packed_super(c,d_seq,d_val,npos,fetch_table,res,own_total,&fb,prescanned);
       if (rc || !fb) return rc;
       memset(c->used,0,sizeof(c->used));
       own_total = true;
@@ -1046,7 +1138,15 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
   }
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
   stage_begin(c,FKGPU_ST_PACK);
-  int rc = fkgpu_pack_ascii_dev(c,(const char *) c->ascii.p,npos,(uint32_t *) c->seq.p,(uint32_t *) c->val.p);
+  int rc = FKGPU_OK;
+  if (c->stream_on)
+    { /* every chunk was packed as it arrived; only the zero words behind the stream remain */
+      const long long vwn = (npos + 31) / 32;
+      CU(cudaMemsetAsync((u32 *) c->seq.p + 2*vwn,0,FKGPU_PACK_PAD * 4,c->st));
+      CU(cudaMemsetAsync((u32 *) c->val.p + vwn,0,FKGPU_PACK_PAD * 4,c->st));
+    }
+  else
+    rc = fkgpu_pack_ascii_dev(c,(const char *) c->ascii.p,npos,(uint32_t *) c->seq.p,(uint32_t *) c->val.p);
   if (rc) return rc;
   if (c->cfg.bc_prefix > 0 || c->cfg.do_profile)
     { /* read starts on the device, tid-major */
@@ -1066,7 +1166,7 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
         }
     }
   stage_end(c,FKGPU_ST_PACK);
-  return count_packed_any(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false);
+  return count_packed_any(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false,c->stream_on && c->stream_scan);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

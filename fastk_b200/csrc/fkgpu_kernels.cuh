@@ -1293,7 +1293,7 @@ __device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
 }
 
 template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS>
-__global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
+__global__ void __launch_bounds__(BC_TPB,3) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
 { static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
@@ -1336,11 +1336,11 @@ __global__ void __launch_bounds__(BC_TPB) k_bucket_count(BucketParams p, u32 km0
               u64 ps = sm & ((1ull << SUP_PBITS) - 1ull);
               const u32 *sq = p.seq;
               if (p.nranks > 1)
-                { u64 pb = 0;                         /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
-#pragma unroll
-                  for (int r = 1; r < SUP_MAXRANKS; r++)
-                    if (r < p.nranks && ps >= p.pbase[r]) { pb = p.pbase[r]; sq = p.seqr[r]; }
-                  ps -= pb;
+                { int r = 0;                          /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
+#pragma unroll 1
+                  for (int q = 1; q < p.nranks; q++)
+                    if (ps >= p.pbase[q]) r = q;
+                  ps -= p.pbase[r]; sq = p.seqr[r];
                 }
               const u32 *g = sq + (ps >> 4);
               const int sh = 2*(int) (ps & 15ull);

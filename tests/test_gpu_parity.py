@@ -9,8 +9,8 @@ from fastk_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(reads, k, cutoff=1, bc=0, nthreads=1, block_bytes=1_000_000):
-    g = FastKGPU(k=k, table_cutoff=cutoff, bc_prefix=bc, nthreads=nthreads)
+def run_gpu(reads, k, cutoff=1, bc=0, nthreads=1, block_bytes=1_000_000, reserve=0):
+    g = FastKGPU(k=k, table_cutoff=cutoff, bc_prefix=bc, nthreads=nthreads, reserve_bases=reserve)
     try:
         for i, (bases, boff) in enumerate(synth.blocks(reads, max_bytes=block_bytes)):
             g.ingest(bases, boff.astype(np.int32), tid=i % nthreads)
@@ -19,9 +19,9 @@ def run_gpu(reads, k, cutoff=1, bc=0, nthreads=1, block_bytes=1_000_000):
         g.close()
 
 
-def check(oracle_lib, reads, k, cutoff=1, bc=0, nthreads=1):
+def check(oracle_lib, reads, k, cutoff=1, bc=0, nthreads=1, **kw):
     want = oracle_lib.count(reads, k, bc_prefix=bc, cutoff=cutoff)
-    got = run_gpu(reads, k, cutoff=cutoff, bc=bc, nthreads=nthreads)
+    got = run_gpu(reads, k, cutoff=cutoff, bc=bc, nthreads=nthreads, **kw)
     assert got.nkmers == want["nkmers"]
     assert got.ndistinct == want["ndistinct"]
     assert got.max_inst == want["max_inst"]
@@ -66,6 +66,18 @@ def test_medium_30x(oracle_lib):
     reads = synth.sample_reads(genome, 40_000, 150, 0.002, 22)
     check(oracle_lib, reads, 40, nthreads=4)
     check(oracle_lib, reads, 21, cutoff=4, nthreads=3)
+
+
+@pytest.mark.parametrize("k,bc,reserve_frac", [(40, 0, 1.2), (21, 0, 1.2), (40, 0, 0.4), (63, 0, 1.2), (40, 10, 1.2)])
+def test_streamed_front_end(oracle_lib, monkeypatch, k, bc, reserve_frac):
+    """reserve_bases > 0: every staging chunk is packed (and, on the super-mer path, scanned into super-mer records) as
+    soon as it lands on the device.  Many small chunks from 3 ingest threads; reserve_frac < 1 makes the reservation too
+    small, so the stream is abandoned half way and finish packs + scans the whole buffer instead."""
+    monkeypatch.setenv("FKGPU_CHUNK_BYTES", str(128 << 10))
+    genome = synth.random_genome(150_000, 61)
+    reads = synth.sample_reads(genome, 20_000, 150, 0.003, 62, n_rate=0.001, len_jitter=60)
+    total = sum(len(r) + 1 for r in reads)
+    check(oracle_lib, reads, k, bc=bc, nthreads=3, block_bytes=40_000, reserve=int(total * reserve_frac))
 
 
 def test_long_reads_hifi_like(oracle_lib):
