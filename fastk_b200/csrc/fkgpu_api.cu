@@ -822,9 +822,14 @@ static int super_scan_stage(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
   sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
   sp.k = g.k; sp.m = g.m; sp.w = g.w; sp.p2 = g.p2; sp.lmax = SUP_LMAX; sp.bbits = g.bbits ? g.bbits : 1;
   sp.out = out; sp.cap = cap; sp.counter = &d_cnt->nrec; sp.pos_offset = pos_offset;
-  const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_L) * 4;
-  CU(cudaFuncSetAttribute(k_super,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
-  k_super<<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK();
+  const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_ROWS*SUP_RS) * 4;
+#define SUPER_LAUNCH(P2V) do { \
+    CU(cudaFuncSetAttribute(k_super<P2V>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
+    k_super<P2V><<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(sp); KCHECK(); } while (0)
+  if (g.p2 == 8) SUPER_LAUNCH(8);
+  else if (g.p2 == 16) SUPER_LAUNCH(16);
+  else if (g.p2 == 32) SUPER_LAUNCH(32);
+  else return set_err(FKGPU_E_UNSUPPORTED,"internal: minimizer window %d outside the super-mer kernel's range",g.w);
   return FKGPU_OK;
 }
 
@@ -879,7 +884,9 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 10;
       const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
     }
-  const u32 TS = (u32) ((bcvar == 8 || bcvar == 10 || bcvar == 11) ? std::min(tsv,384) : tsv);
+  int gcv = 512;                                    /* super-mers per piece of the chosen kernel geometry */
+  switch (bcvar) { case 8: case 10: case 11: gcv = 384; break; case 12: gcv = 192; break; case 13: gcv = 96; break; case 14: gcv = 256; break; default: gcv = 512; }
+  const u32 TS = (u32) std::min(tsv,gcv);
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -906,6 +913,9 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     else if (bcvar == 9) BC_LAUNCH(512,512,768,1024,2048);
     else if (bcvar == 10) BC_LAUNCH(512,384,768,1024,2048);
     else if (bcvar == 11) BC_LAUNCH(384,384,768,1024,2048);
+    else if (bcvar == 12) BC_LAUNCH(256,192,384,512,1024);
+    else if (bcvar == 13) BC_LAUNCH(128,96,192,256,512);
+    else if (bcvar == 14) BC_LAUNCH(256,256,512,512,1024);
     else BC_LAUNCH(512,512,1024,1024,4096);
   }
   stage_end(c,FKGPU_ST_BUCKET);

@@ -1086,7 +1086,6 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
  *  A super-mer starts at a legal k-mer that does not continue its predecessor (other bucket / illegal) or sits on
  *  a multiple of 64 (so no super-mer exceeds 64 k-mers and every thread can decide its starts locally).          */
 
-#define SUP_L     (SCAN_TILE + SCAN_TILE/32 + 64)   /* room for the +1-per-32 skew that keeps per-thread rows conflict-free */
 #define SUP_PBITS 36                                /* position field: global position over all ranks' read streams */
 #define SUP_LMAX  64
 #define SUP_BBITS 22                                /* most bucket-id bits (22 + 6 + 36 = 64)                        */
@@ -1107,83 +1106,120 @@ __device__ __forceinline__ u32 mix32(u32 x)   /* bijective (murmur3 finaliser) *
   return x;
 }
 
+#define SUP_ROWS  (SCAN_TPB + 2)                    /* rows of 32 positions: the tile + the (w-1) <= 40 position halo         */
+#define SUP_RS    33                                /* row stride in words: a thread's walk along its own row is conflict-free */
+
+/*  v[i] = min of the order keys of positions 32*row + i .. 32*row + i + P2 - 1  (valid for i < 32)  */
+template<int P2>
+__device__ __forceinline__ void window_min_row(const u32 *s_h, int row, u32 *v)
+{ constexpr int NV = 32 + P2 - 1;
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = s_h[(row + (i >> 5))*SUP_RS + (i & 31)];
+#pragma unroll
+  for (int st = 1; st < P2; st <<= 1)
+    {
+#pragma unroll
+      for (int i = 0; i < NV - st; i++) v[i] = v[i] < v[i+st] ? v[i] : v[i+st];
+    }
+}
+
+/*  One CTA per tile of SCAN_TILE positions, one thread per 32 consecutive k-mer starts.  The order keys of the canonical
+ *  m-mers go through shared memory once; the sliding-window minimum (width w = P2 + d, P2 <= w < 2*P2) is formed in
+ *  registers by doubling up to P2 and one combine at distance d; bucket ids, run detection and the hand-over to the next
+ *  thread's leading run stay in registers / warp shuffles.                                                            */
+template<int P2>
 __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
 { extern __shared__ u32 s_dyn[];
   u32 *s_seq = s_dyn;
   u32 *s_val = s_seq + SCAN_SEQW;
-  u32 *s_a   = s_val + SCAN_VALW;           /* [SUP_L] */
-  u32 *s_b   = s_a + SUP_L;                 /* [SUP_L] */
-  __shared__ u32 s_warp[SCAN_TPB/32], s_okw[SCAN_TPB+1];
+  u32 *s_h   = s_val + SCAN_VALW;           /* [SUP_ROWS][SUP_RS] order keys, later each thread's bucket ids */
+  u32 *s_c   = s_h + SUP_ROWS*SUP_RS;       /* [SUP_ROWS][SUP_RS] P2-window minima (only when d > 0)          */
+  __shared__ u32 s_warp[SCAN_TPB/32];
   __shared__ u64 s_base;
+  constexpr int NV = 32 + P2 - 1;
+  const int t = threadIdx.x;
 
   ScanParams sp; sp.seq = p.seq; sp.val = p.val; sp.nseqw = p.nseqw; sp.nvalw = p.nvalw;
   scan_load_tile(sp,blockIdx.x,s_seq,s_val);
   __syncthreads();
 
-  /* order key of the canonical m-mer at every tile position (each computed once per tile) */
-  const int m2 = 2*p.m;
-  const u32 mmask = (m2 == 32) ? 0xffffffffu : ((1u << m2) - 1u);
-  const int need = SCAN_TILE + p.w - 1;
-  for (int i = threadIdx.x; i < need; i += SCAN_TPB)
-    { const u32 *s = s_seq + SCAN_LHALO + (i >> 4);
-      u32 x = __funnelshift_l(s[1],s[0],2*(i & 15));          /* 16 bases starting at position i, left aligned */
-      u32 f = x >> (32 - m2);
-      u32 r = rc32(f << (32 - m2)) & mmask;
-      s_a[i] = mix32(f < r ? f : r);
-    }
+  /* order key of the canonical m-mer at every position of the tile and its halo (each computed once per tile) */
+  { const int m2 = 2*p.m, sh = 32 - m2;
+    const u32 mmask = (m2 == 32) ? 0xffffffffu : ((1u << m2) - 1u);
+    const int nrows = SCAN_TPB + (p.w - 1 + 31) / 32;
+    for (int row = t; row < nrows; row += SCAN_TPB)
+      { const u32 *s = s_seq + SCAN_LHALO + 2*row;
+        const u32 W0 = s[0], W1 = s[1], W2 = s[2];
+        u32 *h = s_h + row*SUP_RS;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          { const u32 x = (j < 16) ? __funnelshift_l(W1,W0,2*j) : __funnelshift_l(W2,W1,2*(j-16));   /* 16 bases from position j */
+            const u32 f = x >> sh;
+            const u32 r = rc32(x) & mmask;                   /* the first m bases reverse-complemented land in the low 2m bits */
+            h[j] = mix32(f < r ? f : r);
+          }
+      }
+  }
   __syncthreads();
-  /* sliding-window minimum of width w by doubling: after the loop cur[i] = min o[i .. i+p2) */
-  u32 *cur = s_a, *nxt = s_b;
-  int len = need;
-  for (int st = 1; 2*st <= p.w; st <<= 1)
-    { for (int i = threadIdx.x; i < len - st; i += SCAN_TPB)
-        { u32 a = cur[i], b = cur[i+st];
-          nxt[i] = a < b ? a : b;
+
+  u32 v[NV];
+  window_min_row<P2>(s_h,t,v);
+  const int d = p.w - P2;
+  if (d > 0)
+    { u32 *c = s_c + t*SUP_RS;
+#pragma unroll
+      for (int j = 0; j < 32; j++) c[j] = v[j];
+      if (t == 0)                                            /* the halo row: its first d entries are read by the last thread */
+        { u32 hv[NV];
+          window_min_row<P2>(s_h,SCAN_TPB,hv);
+          u32 *ch = s_c + SCAN_TPB*SUP_RS;
+#pragma unroll
+          for (int j = 0; j < 32; j++) ch[j] = hv[j];
         }
-      len -= st;
-      __syncthreads();
-      u32 *t = cur; cur = nxt; nxt = t;
     }
-  /* bucket id of every k-mer start, stored skewed (+1 word per 32) so that a thread's own row is conflict-free */
-  const int d = p.w - p.p2;
-  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_TPB)
-    { u32 a = cur[i], b = cur[i+d];
-      u32 mn = a < b ? a : b;
-      nxt[i + (i >> 5)] = (mn * 0x9E3779B1u) >> (32 - p.bbits);
+  __syncthreads();                                           /* every read of the order keys is done; s_c is complete */
+  if (d > 0)
+    {
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        { const int q = j + d;
+          const u32 u = s_c[(t + (q >> 5))*SUP_RS + (q & 31)];
+          v[j] = v[j] < u ? v[j] : u;
+        }
     }
-  V96 v; v.a = s_val[threadIdx.x]; v.b = s_val[threadIdx.x+1]; v.c = s_val[threadIdx.x+2];
-  const u32 ok = window_ok(v,p.k);                  /* bit 31-j = k-mer j of this thread is legal */
-  s_okw[threadIdx.x] = ok;
-  if (threadIdx.x == 0) s_okw[SCAN_TPB] = 0;
-  __syncthreads();
-  const u32 *bk = nxt + threadIdx.x * (SCAN_PPT + 1);
-  const int base = threadIdx.x * SCAN_PPT;
+  /* bucket id of every k-mer start; kept in the thread's own row for the emission loop's dynamic lookups */
+  u32 *bk = s_h + t*SUP_RS;
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    { v[j] = (v[j] * 0x9E3779B1u) >> (32 - p.bbits);
+      bk[j] = v[j];
+    }
+  V96 vv; vv.a = s_val[t]; vv.b = s_val[t+1]; vv.c = s_val[t+2];
+  const u32 ok = window_ok(vv,p.k);                 /* bit 31-j = k-mer j of this thread is legal */
 
   /* cont bit j: k-mer j continues the super-mer of k-mer j-1 (both legal, same bucket, not on a multiple of 64) */
   u32 same = 0;
-  { u32 prev = bk[0];
 #pragma unroll
-    for (int j = 1; j < SCAN_PPT; j++)
-      { u32 x = bk[j];
-        same |= (x == prev ? 1u : 0u) << (31-j);
-        prev = x;
-      }
-    if (threadIdx.x & 1)                             /* j = 0 of an odd thread is not a multiple of 64: may continue */
-      { const u32 pb = nxt[(base-1) + ((base-1) >> 5)];
-        if ((s_okw[threadIdx.x-1] & 1u) && pb == bk[0]) same |= 0x80000000u;
-      }
-  }
-  const u32 okprev = (ok >> 1) | ((threadIdx.x & 1) ? (s_okw[threadIdx.x-1] << 31) : 0u);
+  for (int j = 1; j < 32; j++) same |= (v[j] == v[j-1] ? 1u : 0u) << (31-j);
+  const u32 pb  = __shfl_up_sync(0xffffffffu,v[31],1);
+  const u32 pok = __shfl_up_sync(0xffffffffu,ok & 1u,1);
+  if ((t & 1) && pok && pb == v[0]) same |= 0x80000000u;     /* j = 0 of an odd thread is not a multiple of 64: may continue */
+  const u32 okprev = (ok >> 1) | ((t & 1) ? (pok << 31) : 0u);
   const u32 cont = ok & okprev & same;
   const u32 starts = ok & ~cont;                    /* bit 31-j = a super-mer starts at j */
+  /* length of this thread's leading run as seen from the previous thread (k-mer 0 legal, then cont bits from j = 1) */
+  const u32 lead = (ok >> 31) ? (u32) (1 + __clz(~(cont << 1))) : 0u;
+  const u32 nlead = __shfl_down_sync(0xffffffffu,lead,1);
+  const u32 nb0   = __shfl_down_sync(0xffffffffu,v[0],1);
+
   const u32 nrun = __popc(starts);
   u32 incl = nrun;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1)
     { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
-      if ((threadIdx.x & 31) >= o) incl += y;
+      if ((t & 31) >= o) incl += y;
     }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
   u32 nk = __popc(ok);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu,nk,o);
@@ -1191,32 +1227,28 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
   u32 woff = 0, tot = 0;
   for (int i = 0; i < SCAN_TPB/32; i++)
     { u32 x = s_warp[i];
-      if (i < (int) (threadIdx.x >> 5)) woff += x;
+      if (i < (t >> 5)) woff += x;
       tot += x;
     }
-  if ((threadIdx.x & 31) == 0 && nk) atomicAdd(p.counter + 1,(u64) nk);
-  if (threadIdx.x == 0) s_base = tot ? atomicAdd(p.counter,(u64) tot) : 0ull;
+  if ((t & 31) == 0 && nk) atomicAdd(p.counter + 1,(u64) nk);
+  if (t == 0) s_base = tot ? atomicAdd(p.counter,(u64) tot) : 0ull;
   __syncthreads();
   u64 pos = s_base + woff + incl - nrun;
   if (s_base + tot > p.cap) return;                      /* buffer too small: the host sees counter > cap and falls back */
 
   const u64 tile0 = p.pos_offset + (u64) blockIdx.x * SCAN_TILE;
+  const int base = t * SCAN_PPT;
   u32 todo = starts;
   while (todo)
     { const int j = __clz(todo);
       todo &= ~(0x80000000u >> j);
-      /* length: first within this thread's window by bit tricks, then (rarely far) into the following windows */
       const u32 after = (j == 31) ? 0u : (0xffffffffu >> (j+1));
       const u32 stop = ~cont & after;
-      int e = stop ? __clz(stop) : SCAN_PPT;             /* window-local end (exclusive) */
+      const int e = stop ? __clz(stop) : SCAN_PPT;       /* window-local end (exclusive) */
       int len = e - j;
-      if (e == SCAN_PPT)
-        { const u32 b = bk[j];
-          int q = base + SCAN_PPT;                       /* tile-local position of the next candidate */
-          while (q < SCAN_TILE && (q & 63) != 0 && ((s_okw[q >> 5] >> (31 - (q & 31))) & 1u) && nxt[q + (q >> 5)] == b)
-            { q++; len++; }
-        }
-      p.out[pos++] = ((u64) bk[j] << (64 - p.bbits)) | ((u64) (len-1) << SUP_PBITS) | (tile0 + (u64) (base + j));
+      const u32 b = bk[j];
+      if (e == SCAN_PPT && !(t & 1) && nlead && nb0 == b) len += (int) nlead;     /* runs on into the next thread's window */
+      p.out[pos++] = ((u64) b << (64 - p.bbits)) | ((u64) (len-1) << SUP_PBITS) | (tile0 + (u64) (base + j));
     }
 }
 
@@ -1293,7 +1325,7 @@ __device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
 }
 
 template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS>
-__global__ void __launch_bounds__(BC_TPB,3) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
+__global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
 { static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
