@@ -881,11 +881,11 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
   /* groups of whole buckets, ~TS super-mers each */
   static int bcvar = -1, tsv = 512;
   if (bcvar < 0)
-    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 10;
+    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 14;
       const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
     }
-  int gcv = 512;                                    /* super-mers per piece of the chosen kernel geometry */
-  switch (bcvar) { case 8: case 10: case 11: gcv = 384; break; case 12: gcv = 192; break; case 13: gcv = 96; break; case 14: gcv = 256; break; default: gcv = 512; }
+  int gcv = 384;                                    /* super-mers per piece of the chosen kernel geometry */
+  switch (bcvar) { case 14: gcv = 256; break; default: gcv = 384; }
   const u32 TS = (u32) std::min(tsv,gcv);
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
@@ -905,18 +905,15 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     bp.ent = ent; bp.ent_cap = ent_cap; bp.ent_counter = &d_cnt->nent;
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(g.k,km);
-#define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
+#define BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,KWV) do { \
       const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
-      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
-      k_bucket_count<TPB,GC,CH,DC,TSL><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[0],km[1],km[2],km[3]); KCHECK(); } while (0)
-    if (bcvar == 8) BC_LAUNCH(512,384,1024,1024,4096);
-    else if (bcvar == 9) BC_LAUNCH(512,512,768,1024,2048);
-    else if (bcvar == 10) BC_LAUNCH(512,384,768,1024,2048);
-    else if (bcvar == 11) BC_LAUNCH(384,384,768,1024,2048);
-    else if (bcvar == 12) BC_LAUNCH(256,192,384,512,1024);
-    else if (bcvar == 13) BC_LAUNCH(128,96,192,256,512);
-    else if (bcvar == 14) BC_LAUNCH(256,256,512,512,1024);
-    else BC_LAUNCH(512,512,1024,1024,4096);
+      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL,KWV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
+      k_bucket_count<TPB,GC,CH,DC,TSL,KWV><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
+#define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
+      if (kw == 2) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,2); else if (kw == 3) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,3); else BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,4); } while (0)
+    const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
+    if (bcvar == 14) BC_LAUNCH(256,256,512,512,1024);
+    else BC_LAUNCH(512,384,768,1024,2048);
   }
   stage_end(c,FKGPU_ST_BUCKET);
   CU(cudaMemcpyAsync(hc,d_cnt,sizeof(*hc),cudaMemcpyDeviceToHost,c->st));

@@ -1277,56 +1277,67 @@ struct BucketParams
     u32       *g_fail;                                   /* set if a group could not be counted */
   };
 
-/* both strands of k-mer number j of a super-mer whose base string is b[0..5] (192 bits, left aligned):
- * F = forward, G = reverse complement, each as four 32-bit words, most significant first, 2k bits used */
-__device__ __forceinline__ void supermer_strands(const u32 *b, int j, int k, const u32 *kmask, u32 *F, u32 *G)
+/*  Strand arithmetic on KW = ceil(2k/32) 32-bit words (most significant first; the 2k key bits left aligned, the
+ *  s = 32*KW - 2k < 32 low bits of the last word zero).  klast = mask of the used bits of the last word.          */
+
+/* both strands of k-mer number j of a super-mer whose base string is b[0..] (left aligned): F = forward, G = reverse complement */
+template<int KW>
+__device__ __forceinline__ void supermer_strands(const u32 *b, int j, int k, u32 klast, u32 *F, u32 *G)
 { const int q = j >> 4, sh = 2*(j & 15);
-  u32 Z[4];
 #pragma unroll
-  for (int t = 0; t < 4; t++) F[t] = __funnelshift_l(b[q+t+1],b[q+t],sh) & kmask[t];
-  /* reverse complement of the 64 base slots, then drop the (64-k) padding slots off the top */
+  for (int t = 0; t < KW; t++) F[t] = __funnelshift_l(b[q+t+1],b[q+t],sh);
+  F[KW-1] &= klast;
+  /* reverse complement of the 16*KW base slots, then drop the 16*KW - k padding slots off the top */
+  u32 Z[KW+1];
 #pragma unroll
-  for (int t = 0; t < 4; t++) Z[t] = rc32(F[3-t]);
-  const int s = 128 - 2*k, sq = s >> 5, sr = s & 31;
-  u32 Y[8];
+  for (int t = 0; t < KW; t++) Z[t] = rc32(F[KW-1-t]);
+  Z[KW] = 0;
+  const int s = 32*KW - 2*k;
 #pragma unroll
-  for (int t = 0; t < 4; t++) { Y[t] = Z[t]; Y[t+4] = 0; }
-#pragma unroll
-  for (int t = 0; t < 4; t++)
-    { u32 hi, lo;
-      if (sq == 0)      { hi = Y[t];   lo = Y[t+1]; }
-      else if (sq == 1) { hi = Y[t+1]; lo = Y[t+2]; }
-      else if (sq == 2) { hi = Y[t+2]; lo = Y[t+3]; }
-      else              { hi = Y[t+3]; lo = Y[t+4]; }
-      G[t] = __funnelshift_l(lo,hi,sr) & kmask[t];
-    }
+  for (int t = 0; t < KW; t++) G[t] = __funnelshift_l(Z[t+1],Z[t],s);
+  G[KW-1] &= klast;
 }
 
 /* slide both strands one base to the right: base code c enters the forward strand at its low end */
-__device__ __forceinline__ void strands_roll(u32 *F, u32 *G, u32 c, int k, const u32 *kmask)
-{ const int s = 128 - 2*k, iw = 3 - (s >> 5), is = s & 31;      /* word / shift of the last base slot */
-  F[0] = __funnelshift_l(F[1],F[0],2); F[1] = __funnelshift_l(F[2],F[1],2);
-  F[2] = __funnelshift_l(F[3],F[2],2); F[3] = F[3] << 2;
-  const u32 ins = c << is;
-  F[0] |= (iw == 0) ? ins : 0u; F[1] |= (iw == 1) ? ins : 0u; F[2] |= (iw == 2) ? ins : 0u; F[3] |= (iw == 3) ? ins : 0u;
-  G[3] = __funnelshift_r(G[3],G[2],2) & kmask[3]; G[2] = __funnelshift_r(G[2],G[1],2) & kmask[2];
-  G[1] = __funnelshift_r(G[1],G[0],2) & kmask[1]; G[0] = ((G[0] >> 2) | ((3u - c) << 30)) & kmask[0];
+template<int KW>
+__device__ __forceinline__ void strands_roll(u32 *F, u32 *G, u32 c, int s /* 32*KW - 2k */, u32 klast)
+{
+#pragma unroll
+  for (int t = 0; t < KW-1; t++) F[t] = __funnelshift_l(F[t+1],F[t],2);
+  F[KW-1] = (F[KW-1] << 2) | (c << s);
+#pragma unroll
+  for (int t = KW-1; t > 0; t--) G[t] = __funnelshift_r(G[t],G[t-1],2);
+  G[0] = (G[0] >> 2) | ((3u - c) << 30);
+  G[KW-1] &= klast;
 }
 
+/* canonical key = the smaller strand, as the 16-byte record key (words beyond KW are zero) */
+template<int KW>
 __device__ __forceinline__ Key<2> strands_canon(const u32 *F, const u32 *G)
-{ bool lt = false, dec = false;
-#pragma unroll
-  for (int t = 0; t < 4; t++)
-    if (!dec && F[t] != G[t]) { lt = G[t] < F[t]; dec = true; }
+{ const u64 f0 = ((u64) F[0] << 32) | F[1], g0 = ((u64) G[0] << 32) | G[1];
+  u64 f1 = 0, g1 = 0;
+  if (KW > 2) { f1 = (u64) F[2] << 32; g1 = (u64) G[2] << 32; }
+  if (KW > 3) { f1 |= F[KW > 3 ? 3 : 0]; g1 |= G[KW > 3 ? 3 : 0]; }
+  const bool lt = (g0 < f0) | ((g0 == f0) & (g1 < f1));
   Key<2> key;
-  key.w[0] = lt ? (((u64) G[0] << 32) | G[1]) : (((u64) F[0] << 32) | F[1]);
-  key.w[1] = lt ? (((u64) G[2] << 32) | G[3]) : (((u64) F[2] << 32) | F[3]);
+  key.w[0] = lt ? g0 : f0;
+  key.w[1] = lt ? g1 : f1;
   return key;
 }
 
-template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS>
-__global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 km0, u32 km1, u32 km2, u32 km3)
-{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS,"bucket kernel geometry");
+/* slot / round hash of a canonical key: one multiply-add per word and a finaliser */
+template<int KW>
+__device__ __forceinline__ u32 bucket_hash(const Key<2> &a)
+{ u32 h = (u32) (a.w[0] >> 32) * 0x9E3779B1u + (u32) a.w[0] * 0x85EBCA77u;
+  if (KW > 2) h += (u32) (a.w[1] >> 32) * 0xC2B2AE3Du;
+  if (KW > 3) h += (u32) a.w[1] * 0x27D4EB2Fu;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 16;
+  return h;
+}
+
+template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS, int KW>
+__global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 klast)
+{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS && KW >= 2 && KW <= 4,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
   Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
@@ -1343,7 +1354,7 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
   if (g >= p.nitems) return;
   const u64 r0 = p.starts[g], r1 = p.ends[g];
   if (r1 <= r0) return;
-  const u32 kmask[4] = { km0, km1, km2, km3 };
+  const int ks = 32*KW - 2*p.k;                  /* zero bits below the key in its last word */
 
   /* work stack of (rounds, residue) classes: a class whose distinct keys overflow the pool splits in two */
   u32 stR[28], stD[28];
@@ -1385,10 +1396,11 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
               for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
               /* both strands of the first k-mer: every loader thread does this together, so sliding onto the next
                  super-mer inside the insert loop is a plain load instead of a divergent recomputation           */
-              u32 F0[4], G0[4];
-              supermer_strands(d,0,p.k,kmask,F0,G0);
+              u32 F0[KW], G0[KW];
+              supermer_strands<KW>(d,0,p.k,klast,F0,G0);
               u32 *gq = sg0 + threadIdx.x*4;
-              gq[0] = G0[0]; gq[1] = G0[1]; gq[2] = G0[2]; gq[3] = G0[3];
+#pragma unroll
+              for (int t = 0; t < KW; t++) gq[t] = G0[t];
             }
           u32 incl = l;
 #pragma unroll
@@ -1427,8 +1439,8 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
                 while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= i0) lo = mid; else hi = mid; }
                 u32 sidx = lo, j = i0 - spre[lo], slen = spre[lo+1] - spre[lo];
                 const u32 *sb = sbase + sidx*8;
-                u32 F[4], G[4];
-                supermer_strands(sb,(int) j,p.k,kmask,F,G);
+                u32 F[KW], G[KW];
+                supermer_strands<KW>(sb,(int) j,p.k,klast,F,G);
                 for (u32 i = i0; i < i1; i++)
                   { if (i > i0)
                       { j++;
@@ -1437,15 +1449,16 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
                             sb = sbase + sidx*8;
                             const u32 *gq = sg0 + sidx*4;
 #pragma unroll
-                            for (int t = 0; t < 4; t++) { F[t] = sb[t] & kmask[t]; G[t] = gq[t]; }
+                            for (int t = 0; t < KW; t++) { F[t] = sb[t]; G[t] = gq[t]; }
+                            F[KW-1] &= klast;
                           }
                         else
                           { const u32 qb = j + p.k - 1;
-                            strands_roll(F,G,(sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u,p.k,kmask);
+                            strands_roll<KW>(F,G,(sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u,ks,klast);
                           }
                       }
-                    const Key<2> key = strands_canon(F,G);
-                    const u32 h = key_hash<2>(key);
+                    const Key<2> key = strands_canon<KW>(F,G);
+                    const u32 h = bucket_hash<KW>(key);
                     if (((h >> 20) & (rounds-1)) != rd) continue;
                     u32 x = h & (BC_TS-1);
                     for (u32 step = 0; ; step++)
