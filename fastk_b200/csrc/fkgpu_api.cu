@@ -427,6 +427,15 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax;
   sp.tab_off = L.tab_off; sp.srt_off = L.srt_off; sp.srt2_off = L.srt2_off;
   sp.weighted = (u32) c->weighted;
+  /* weighted + no profiles: every entry is distinct and already passed the cutoff in the bucket kernel, so entry i of
+     the key order is table record i -- the sort kernel writes the table itself (no staging, no compaction pass)       */
+  const bool direct = c->weighted && !c->cfg.do_profile && c->cfg.do_table > 0;
+  const int twd = c->kbytes + 2;
+  sp.direct = NULL; sp.kbytes = c->kbytes; sp.tab_bytes = L.srt_off - L.tab_off;
+  if (direct)
+    { if (c->table.ensure((size_t) nub * twd + 64)) return set_err(FKGPU_E_NOMEM,"out of device memory (table of %lld entries)",nub);
+      sp.direct = (uint8_t *) c->table.p;
+    }
   CU(cudaFuncSetAttribute(k_sortcount<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) L.total));
   k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK();
   stage_end(c,FKGPU_ST_SORTCOUNT);
@@ -570,7 +579,19 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   /* ---- table: scan the per-item pass counts, compact ------------------------------------------- */
   res->ntable = 0; res->table = NULL; res->table_dev = NULL;
   const int tw = c->kbytes + 2;
-  if (c->cfg.do_table > 0)
+  if (direct)
+    { u64 ntot_d;
+      CU(cudaMemcpyAsync(&ntot_d,(const u64 *) c->off1.p + nb1,8,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      res->ntable = (int64_t) ntot_d;
+      res->table_dev = (const uint8_t *) c->table.p;
+      if (fetch_table)
+        { if (c->h_table.ensure((size_t) ntot_d * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
+          CU(cudaMemcpyAsync(c->h_table.p,c->table.p,(size_t) ntot_d * tw,cudaMemcpyDeviceToHost,c->st));
+          res->table = (const uint8_t *) c->h_table.p;
+        }
+    }
+  else if (c->cfg.do_table > 0)
     { stage_begin(c,FKGPU_ST_COMPACT);
       int rc = run_large_scan<NW>(c,(const u32 *) c->epass.p,gmax,(u64 *) c->poff.p,&d_misc->total_pass);
       if (rc) return rc;
@@ -857,6 +878,7 @@ static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S
 static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
                              const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase,
                              Key<2> *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
+/*  entries below the table cutoff never leave the chip unless profiles need every count */
 { Misc *d_misc = (Misc *) c->misc.p;
   const int bbits = g.bbits;
   stage_begin(c,FKGPU_ST_SUPERPART);
@@ -903,6 +925,7 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
       }
     bp.g_hist = (u64 *) c->ghist.p; bp.g_maxinst = &d_misc->maxinst; bp.g_ndistinct = &d_misc->ndistinct;
     bp.ent = ent; bp.ent_cap = ent_cap; bp.ent_counter = &d_cnt->nent;
+    bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(g.k,km);
 #define BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,KWV) do { \

@@ -696,6 +696,10 @@ struct SortCountParams
     u32         weighted;                /* 1: records are distinct (key | count in the low 16 bits): sort only */
     u32         cutoff;
     long long   nitems;
+    uint8_t    *direct;                  /* weighted only: write the final [kbytes key][u16 LE count] table records of entry
+                                            r0 + q at direct + (r0 + q) * (kbytes + 2) (every entry passes the cutoff)      */
+    int         kbytes;
+    u32         tab_bytes;               /* bytes of the hash-table region (staging of the direct output)                   */
   };
 
 template<int NW> __device__ __forceinline__ u32 key_hash(const Key<NW> &a)
@@ -916,6 +920,49 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
     }
   const u64 *fin = srt;
   __syncthreads();
+
+  if (p.weighted && p.direct != NULL)
+    { /* the entries are distinct, all of them pass the cutoff and their final positions are known: write the table records
+         straight out (staged through the dead hash-table region so that the global stores are whole words)              */
+      const int tw = p.kbytes + 2;
+      uint8_t *gout = p.direct + r0 * (u64) tw;
+      const u32 a0 = (u32) ((uintptr_t) gout & 3u);
+      const u32 total = a0 + D * (u32) tw;
+      uint8_t *sout = (uint8_t *) table;
+      const bool staged = (total + 4 <= p.tab_bytes);
+      for (u32 q = threadIdx.x; q < D; q += SC_TPB)
+        { const u32 v = (u32) fin[q];
+          Key<NW> key = rec[v >> 16];
+          const u32 c = (u32) (key.w[NW-1] & 0xffffull);
+          key.w[NW-1] &= ~0xffffull;
+          if (staged && tw == 12 && a0 == 0 && NW == 2)
+            { u32 *o = (u32 *) sout + q*3;
+              o[0] = __byte_perm((u32) (key.w[0] >> 32),0,0x0123);
+              o[1] = __byte_perm((u32) key.w[0],0,0x0123);
+              o[2] = (u32) (key.w[NW-1] >> 56) | (((u32) (key.w[NW-1] >> 48) & 0xffu) << 8) | (c << 16);
+            }
+          else
+            { uint8_t *e = staged ? (sout + a0 + q * (u32) tw) : (gout + q * (u64) tw);
+              for (int b = 0; b < p.kbytes; b++)
+                e[b] = (uint8_t) (key.w[b >> 3] >> (56 - 8*(b & 7)));
+              e[p.kbytes]   = (uint8_t) (c & 0xffu);
+              e[p.kbytes+1] = (uint8_t) (c >> 8);
+            }
+        }
+      if (staged)
+        { __syncthreads();
+          u32 *gw = (u32 *) (gout - a0);
+          const u32 *sw = (const u32 *) sout;
+          for (u32 i = threadIdx.x; 4*i < total; i += SC_TPB)
+            { if (4*i >= a0 && 4*i + 4 <= total) gw[i] = sw[i];
+              else
+                for (u32 b = 4*i; b < 4*i + 4; b++)
+                  if (b >= a0 && b < total) ((uint8_t *) gw)[b] = sout[b];
+            }
+        }
+      if (threadIdx.x == 0) { p.e_all[g] = D; p.e_pass[g] = D; }
+      return;
+    }
 
   /* emit: staged (key,count), histogram */
   u32 npass = 0;
@@ -1274,6 +1321,7 @@ struct BucketParams
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
     Key<2>    *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL)  */
+    u32        ent_min;                                  /* only entries with (saturated) count >= ent_min are emitted */
     u32       *g_fail;                                   /* set if a group could not be counted */
   };
 
@@ -1337,7 +1385,7 @@ __device__ __forceinline__ u32 bucket_hash(const Key<2> &a)
 
 template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS, int KW>
 __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 klast)
-{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS && KW >= 2 && KW <= 4,"bucket kernel geometry");
+{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS && BC_DC <= 1024 && KW >= 2 && KW <= 4,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
   Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
@@ -1515,16 +1563,23 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
         }
       /* emit this class's distinct keys (pool entries of count 0 are holes) */
       u32 mine = 0;
-      for (u32 i = threadIdx.x; i < nd; i += BC_TPB) mine += (ocnt[i] != 0) ? 1u : 0u;
+      u32 mine_e = 0;                            /* of them, those that are emitted as entries */
+      for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
+        { const u32 c = ocnt[i];
+          mine += (c != 0) ? 1u : 0u;
+          mine_e += (c >= p.ent_min) ? 1u : 0u;
+        }
+      mine = (mine << 16) | mine_e;              /* both fit 16 bits: the pool holds <= 1024 keys */
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu,mine,o);
       if (threadIdx.x == 0) s_ecnt = 0;
       __syncthreads();
       if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_ecnt,mine);
       __syncthreads();
-      const u32 nreal = s_ecnt;
+      const u32 nreal = s_ecnt >> 16, nemit = s_ecnt & 0xffffu;
+      __syncthreads();
       if (threadIdx.x == 0)
-        { s_ebase = (p.ent != NULL && nreal) ? atomicAdd(p.ent_counter,(u64) nreal) : 0ull;
+        { s_ebase = (p.ent != NULL && nemit) ? atomicAdd(p.ent_counter,(u64) nemit) : 0ull;
           s_ecnt = 0;
         }
       __syncthreads();
@@ -1535,7 +1590,7 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
           if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
           else atomicAdd(p.g_hist + cs,1ull);
           if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
-          if (p.ent != NULL)
+          if (p.ent != NULL && cs >= p.ent_min)
             { const u64 at = s_ebase + atomicAdd(&s_ecnt,1u);
               if (at < p.ent_cap)
                 { Key<2> e = pool[i];
