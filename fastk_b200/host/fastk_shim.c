@@ -37,6 +37,7 @@ int64 *NUM_RID;
 
 static fkgpu_ctx   *CTX;
 static fkgpu_result RES;
+static int64        EST_POSITIONS;   /* estimate of the input size from the training block (as FastK.c:428 does) */
 
 static void fail(const char *what)
 { fprintf(stderr,"\n%s: %s: %s\n",Prog_Name,what,fkgpu_last_error());
@@ -44,8 +45,11 @@ static void fail(const char *what)
 }
 
 int Determine_Scheme(DATA_BLOCK *block)
-{ (void) block;
-  NPARTS = 1;                       /* one in-HBM batch: table.c's merge degenerates to a copy */
+{ NPARTS = 1;                       /* one in-HBM batch: table.c's merge degenerates to a copy */
+  /* bases + one terminator per read, scaled from the portion read to the whole data set; only a hint: it lets the
+     library size its buffers up front and pack + scan every chunk while io.c is still reading (an underestimate
+     just ends that overlap early)                                                                               */
+  EST_POSITIONS = (int64) ((block->totlen + (double) block->nreads) * block->ratio * 1.05) + (1 << 20);
   if (VERBOSE)
     fprintf(stderr,"  GPU path: canonical-prefix buckets on the device, no minimizer scheme\n");
   return (KMER > 5 ? KMER-4 : 1);   /* MAX_SUPER: only sizes fields this path never uses */
@@ -68,6 +72,7 @@ void Split_Kmers(Input_Partition *io, char *root)
   cfg.kmer = KMER; cfg.do_table = DO_TABLE; cfg.do_profile = DO_PROFILE; cfg.bc_prefix = BC_PREFIX;
   cfg.device = getenv("FASTK_GPU") ? atoi(getenv("FASTK_GPU")) : 0;
   cfg.nthreads = ITHREADS;
+  cfg.reserve_bases = EST_POSITIONS;
   if (fkgpu_create(&cfg,&CTX) != 0) fail("fkgpu_create");
   NUM_RID = (int64 *) calloc(ITHREADS > 0 ? ITHREADS : 1,sizeof(int64));
   Scan_All_Input(io);

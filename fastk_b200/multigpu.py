@@ -49,16 +49,15 @@ def splitters_from_hist(ghist, world):
     """ghist: 1-D int64 tensor/array of global per-prefix counts.  -> list beg[0..world] of prefix cut points:
     rank r owns prefixes [beg[r], beg[r+1]).  Same rule as msd_sort's panel split (MSDsort.c:330-352)."""
     h = np.asarray(ghist.cpu() if torch.is_tensor(ghist) else ghist, dtype=np.int64)
-    total = int(h.sum())
-    beg = [0]
-    n, s = 0, 0
-    thr = total // world
-    for x in range(len(h)):
-        s += int(h[x])
-        if s >= thr and n < world - 1:
-            n += 1
-            beg.append(x + 1)
-            thr = (total * (n + 1)) // world
+    cs = np.cumsum(h)
+    total = int(cs[-1]) if len(cs) else 0
+    beg, prev = [0], -1
+    for n in range(1, world):                      # the n-th cut falls after the first bin whose running sum reaches n/world
+        x = max(int(np.searchsorted(cs, (total * n) // world, side="left")), prev + 1)
+        if x >= len(h):
+            break
+        beg.append(x + 1)
+        prev = x
     while len(beg) < world:
         beg.append(len(h))
     beg.append(len(h))

@@ -1,0 +1,11 @@
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
+python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('1 GPU', round(d['value'],2),'Gbases/s', round(d['ms_per_step'],1),'ms', {k:v['ms'] for k,v in d['roofline']['stages'].items() if v['ms']>0})"
+FKGPU_MG_TIMING=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus 2 --steps 3 --warmup 2 2>&1 | grep -E "metric|rror|\[mg\]" | tail -2 | python -c "
+import sys,json
+for l in sys.stdin:
+    try:
+        d=json.loads(l); print('2 GPU', round(d['value'],2),'Gbases/s', round(d['ms_per_step'],1),'ms dev', round(d['device_ms_per_step'],1), d['config']['pipeline'], {k:v['ms'] for k,v in d['roofline']['stages'].items()})
+    except Exception as e: print(l[:700])
+"
