@@ -1064,21 +1064,32 @@ static int stream_begin(fkgpu_ctx *c)
   static int off = -1;
   if (off < 0) { const char *e = getenv("FKGPU_NOSTREAM"); off = (e && atoi(e)) ? 1 : 0; }
   if (c->cfg.reserve_bases <= 0 || off) return FKGPU_OK;
-  if (ascii_reserve(c,1)) return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot reserve the device read buffer");
-  long long cap = std::min<long long>((long long) c->ascii.cap - 256,c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20));
-  cap &= ~63ll;
-  int64_t sw, vw;
-  fkgpu_packed_words(cap,&sw,&vw);
-  if (c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4))
-    return set_err(FKGPU_E_NOMEM,"out of device memory (packed reads)");
+  /* reserve_bases is only a hint (the reference-hosted shim extrapolates it from the first block): if the device
+     cannot hold buffers of that size, forget the hint and let the buffers grow with what actually arrives          */
+  bool ok = (ascii_reserve(c,1) == 0);
+  long long cap = 0;
+  if (ok)
+    { cap = std::min<long long>((long long) c->ascii.cap - 256,c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20));
+      cap &= ~63ll;
+      int64_t sw, vw;
+      fkgpu_packed_words(cap,&sw,&vw);
+      ok = !(c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4));
+    }
+  const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0;
+  if (scan)
+    { c->sgeom = super_geom(c->cfg.kmer,cap);
+      ok = (prepare_common(c,cap,std::max(c->sgeom.P1,1),true,2) == 0) && !c->segs.ensure(sizeof(SuperCounters));
+    }
+  if (!ok)
+    { c->ascii.release(); c->seq.release(); c->val.release(); c->bufA.release(); c->bufB.release();
+      c->cfg.reserve_bases = 0;
+      g_err[0] = 0;
+      return FKGPU_OK;
+    }
   c->stream_cap = cap;
   c->stream_on = true;
-  if (super_path_ok(c) && c->cfg.bc_prefix == 0)
-    { c->sgeom = super_geom(c->cfg.kmer,cap);
-      int rc = prepare_common(c,cap,std::max(c->sgeom.P1,1),true,2);
-      if (rc) return rc;
-      if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
-      CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
+  if (scan)
+    { CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
       c->stream_scan = true;
     }
   return FKGPU_OK;
