@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <vector>
 #include <mutex>
+#include <shared_mutex>
 #include <algorithm>
 
 #include "fastk_gpu.h"
@@ -74,6 +75,11 @@ struct TidState
     std::vector<int>       rlen;      /* read length (without terminator)           */
     std::vector<char>      rcont;     /* 1 = this read continues the previous one (rem > 0 carry) */
     int     carry = 0;                /* previous block ended with rem > 0          */
+    /* direct path (the caller's DATA_BLOCK is page-locked): blocks are DMA'd straight into a device region of chunk_bytes */
+    cudaStream_t str = nullptr;       /* this tid's copy stream                      */
+    cudaEvent_t  rdone = nullptr;     /* region complete (copies + tail memset)      */
+    long long    reg_off = -1;        /* open region, -1 = none                      */
+    size_t       reg_fill = 0;
   };
 
 struct fkgpu_ctx
@@ -89,6 +95,7 @@ struct fkgpu_ctx
 
     /* ingest */
     std::mutex   mu;
+    std::shared_mutex buf_mu;         /* shared: a direct copy into c->ascii is in flight; exclusive: c->ascii is being moved */
     std::vector<TidState> tids;
     DevBuf       ascii;               /* device copy of the ingested blocks           */
     long long    ascii_used = 0;
@@ -176,6 +183,8 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
   for (auto &t : c->tids)
     { if (t.pin) cudaFreeHost(t.pin);
       if (t.done) cudaEventDestroy(t.done);
+      if (t.rdone) cudaEventDestroy(t.rdone);
+      if (t.str) cudaStreamDestroy(t.str);
     }
   DevBuf *bufs[] = { &c->ctah,&c->ctao,&c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
                      &c->eall,&c->epass,&c->poff,&c->bsum,&c->ghist,&c->misc,&c->table,&c->segs,&c->child,&c->pcl,
@@ -195,7 +204,10 @@ extern "C" int fkgpu_reset(fkgpu_ctx *c)
   CU(cudaStreamSynchronize(c->cst));
   CU(cudaStreamSynchronize(c->st));
   for (auto &t : c->tids)
-    { t.fill = 0; t.inflight = false; t.chunks.clear(); t.rstart.clear(); t.rlen.clear(); t.rcont.clear(); t.carry = 0; }
+    { t.fill = 0; t.inflight = false; t.chunks.clear(); t.rstart.clear(); t.rlen.clear(); t.rcont.clear(); t.carry = 0;
+      if (t.str) CU(cudaStreamSynchronize(t.str));
+      t.reg_off = -1; t.reg_fill = 0;
+    }
   c->ascii_used = 0; c->nreads = 0; c->nbases = 0; c->finished = false;
   c->stream_started = c->stream_on = c->stream_scan = false;
   return FKGPU_OK;
@@ -240,6 +252,7 @@ static int ascii_reserve(fkgpu_ctx *c, long long need)      /* c->mu held */
     want = std::max(want,(size_t) (c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20)));
   void *np = nullptr;
   if (cudaMalloc(&np,want) != cudaSuccess) { cudaGetLastError(); return 1; }
+  std::unique_lock<std::shared_mutex> moving(c->buf_mu);      /* no direct copy may be in flight while the buffer moves */
   if (c->ascii.p)
     { cudaStreamSynchronize(c->cst);
       cudaMemcpy(np,c->ascii.p,(size_t) c->ascii_used,cudaMemcpyDeviceToDevice);
@@ -250,7 +263,7 @@ static int ascii_reserve(fkgpu_ctx *c, long long need)      /* c->mu held */
 }
 
 static int stream_begin(fkgpu_ctx *c);
-static int stream_chunk(fkgpu_ctx *c, long long off, long long len);
+static int stream_chunk(fkgpu_ctx *c, long long off, long long len, long long scan_len);
 
 static int flush_tid(fkgpu_ctx *c, TidState &t)
 { if (t.fill == 0) return FKGPU_OK;
@@ -272,7 +285,7 @@ static int flush_tid(fkgpu_ctx *c, TidState &t)
     CU(cudaEventRecord(t.done,c->cst));
     if (c->stream_on)
       { CU(cudaStreamWaitEvent(c->st,t.done,0));
-        int rc = stream_chunk(c,off,(long long) padded);
+        int rc = stream_chunk(c,off,(long long) padded,(long long) padded);
         if (rc) return rc;
       }
   }
@@ -285,6 +298,60 @@ static int flush_tid(fkgpu_ctx *c, TidState &t)
     }
   t.fill = 0;
   return FKGPU_OK;
+}
+
+/*  Direct path: the caller's block is page-locked (cudaMallocHost / cudaHostRegister), so it is DMA'd straight to its
+ *  place in the device read buffer -- no staging memcpy on the host.  Each tid fills device regions of chunk_bytes; a
+ *  complete region gets its tail zeroed (invalid positions) and is packed + scanned like a staged chunk.  The copy is
+ *  waited for before returning: the caller reuses the block immediately (io.c:552,565).                            */
+static int close_region(fkgpu_ctx *c, TidState &t)
+{ if (t.reg_off < 0) return FKGPU_OK;
+  const size_t tail = c->chunk_bytes - t.reg_fill;
+  { std::shared_lock<std::shared_mutex> stable(c->buf_mu);
+    if (tail) CU(cudaMemsetAsync((char *) c->ascii.p + t.reg_off + t.reg_fill,0,tail,t.str));
+    CU(cudaEventRecord(t.rdone,t.str));
+    CU(cudaStreamSynchronize(t.str));
+  }
+  { std::lock_guard<std::mutex> lk(c->mu);
+    if (c->stream_on)
+      { int rc = stream_chunk(c,t.reg_off,(long long) c->chunk_bytes,(long long) ((t.reg_fill + 63) & ~(size_t) 63));
+        if (rc) return rc;
+      }
+  }
+  t.chunks.push_back(std::make_pair(t.reg_off,(long long) t.reg_fill));
+  t.reg_off = -1; t.reg_fill = 0;
+  return FKGPU_OK;
+}
+
+/*  -> 1 if the block was taken (its device position in *pos0), 0 if the caller must use the staging path */
+static int direct_ingest(fkgpu_ctx *c, TidState &t, const char *src, size_t len, long long *pos0)
+{ static int off = -1;
+  if (off < 0) { const char *e = getenv("FKGPU_NODIRECT"); off = (e && atoi(e)) ? 1 : 0; }
+  if (off || !c->stream_on) return 0;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr,src) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (attr.type != cudaMemoryTypeHost) return 0;
+  if (t.str == nullptr)
+    { if (cudaStreamCreateWithFlags(&t.str,cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&t.rdone,cudaEventDisableTiming) != cudaSuccess)
+        { cudaGetLastError(); return 0; }
+    }
+  if (t.reg_off < 0 || t.reg_fill + len > c->chunk_bytes)
+    { int rc = close_region(c,t);
+      if (rc) return rc;
+      std::lock_guard<std::mutex> lk(c->mu);
+      if (!c->stream_on || c->ascii_used + (long long) c->chunk_bytes > c->stream_cap) return 0;
+      t.reg_off = c->ascii_used;
+      c->ascii_used += (long long) c->chunk_bytes;
+      t.reg_fill = 0;
+    }
+  { std::shared_lock<std::shared_mutex> stable(c->buf_mu);
+    if (cudaMemcpyAsync((char *) c->ascii.p + t.reg_off + t.reg_fill,src,len,cudaMemcpyHostToDevice,t.str) != cudaSuccess
+        || cudaStreamSynchronize(t.str) != cudaSuccess)
+      return set_err(FKGPU_E_CUDA,"fkgpu_ingest: direct copy failed: %s",cudaGetErrorString(cudaGetLastError()));
+  }
+  *pos0 = t.reg_off + (long long) t.reg_fill;
+  t.reg_fill += len;
+  return 1;
 }
 
 extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int32_t *boff, int32_t nreads, int32_t rem)
@@ -309,20 +376,44 @@ extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int3
     }
   const size_t len = (size_t) boff[nreads] - (size_t) boff[0];
   if (len > c->chunk_bytes) return set_err(FKGPU_E_ARG,"fkgpu_ingest: block of %zu bytes exceeds the %zu byte staging chunk",len,c->chunk_bytes);
-  if (t.fill + len > c->chunk_bytes)
+  long long dpos = -1;
+  { int took = 0;
+    if (c->stream_on)
+      { if (t.fill > 0 && t.reg_off < 0)                 /* keep this tid's pieces in arrival order */
+          { cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr,bases) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+              { int rc = flush_tid(c,t);
+                if (rc) return rc;
+              }
+            else cudaGetLastError();
+          }
+        if (t.fill == 0)
+          { took = direct_ingest(c,t,bases + boff[0],len,&dpos);
+            if (took < 0) return took;
+          }
+      }
+    if (!took)
+      { dpos = -1;
+        int rc = close_region(c,t);                      /* a tid that falls back to staging finishes its open region first */
+        if (rc) return rc;
+      }
+  }
+  if (dpos < 0 && t.fill + len > c->chunk_bytes)
     { int rc = flush_tid(c,t);
       if (rc) return rc;
     }
-  if (t.inflight && t.fill == 0)
-    { CU(cudaEventSynchronize(t.done));      /* the chunk is being reused: previous copy must be out */
-      t.inflight = false;
+  if (dpos < 0)
+    { if (t.inflight && t.fill == 0)
+        { CU(cudaEventSynchronize(t.done));      /* the chunk is being reused: previous copy must be out */
+          t.inflight = false;
+        }
+      memcpy(t.pin + t.fill,bases + boff[0],len);
     }
-  memcpy(t.pin + t.fill,bases + boff[0],len);
   long long nb = 0;
   for (int i = 0; i < nreads; i++)
-    { long long s = (long long) t.fill + (boff[i] - boff[0]);
+    { long long s = (dpos >= 0 ? dpos : (long long) t.fill) + (boff[i] - boff[0]);
       int rl = boff[i+1] - boff[i] - 1;
-      t.rstart.push_back(-(s + 1));            /* chunk relative, fixed up at flush */
+      t.rstart.push_back(dpos >= 0 ? s : -(s + 1));      /* staged: chunk relative, fixed up at flush */
       t.rlen.push_back(rl);
       t.rcont.push_back((i == 0 && t.carry) ? 1 : 0);
       nb += rl;
@@ -331,7 +422,7 @@ extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int3
   long long nr = nreads;
   if (t.carry) { nr -= 1; nb -= (c->cfg.kmer - 1); }
   t.carry = (rem > 0);
-  t.fill += len;
+  if (dpos < 0) t.fill += len;
   { std::lock_guard<std::mutex> lk(c->mu);
     c->nreads += nr;
     c->nbases += nb;
@@ -1095,7 +1186,7 @@ static int stream_begin(fkgpu_ctx *c)
   return FKGPU_OK;
 }
 
-static int stream_chunk(fkgpu_ctx *c, long long off, long long len)       /* off, len: multiples of 64 positions */
+static int stream_chunk(fkgpu_ctx *c, long long off, long long len, long long scan_len)   /* multiples of 64 positions; scan_len <= len */
 { u32 *seq = (u32 *) c->seq.p + (off >> 4), *val = (u32 *) c->val.p + (off >> 5);
   const long long vw = len >> 5;
   if (vw <= 0) return FKGPU_OK;
@@ -1103,7 +1194,7 @@ static int stream_chunk(fkgpu_ctx *c, long long off, long long len)       /* off
   KCHECK();
   if (c->stream_scan)
     { const SuperBufs sb = super_bufs(c,c->stream_cap);
-      return super_scan_stage(c,seq,val,len,c->sgeom,(u64) off,(u64 *) sb.SA,sb.scap,(SuperCounters *) c->segs.p);
+      return super_scan_stage(c,seq,val,scan_len,c->sgeom,(u64) off,(u64 *) sb.SA,sb.scap,(SuperCounters *) c->segs.p);
     }
   return FKGPU_OK;
 }
@@ -1162,6 +1253,8 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
   init_result(c,res);
   for (auto &t : c->tids)
     { int rc = flush_tid(c,t);
+      if (rc) return rc;
+      rc = close_region(c,t);
       if (rc) return rc;
     }
   CU(cudaStreamSynchronize(c->cst));

@@ -80,6 +80,41 @@ def test_streamed_front_end(oracle_lib, monkeypatch, k, bc, reserve_frac):
     check(oracle_lib, reads, k, bc=bc, nthreads=3, block_bytes=40_000, reserve=int(total * reserve_frac))
 
 
+@pytest.mark.parametrize("k,reserve_frac,profile", [(40, 1.3, False), (21, 1.3, False), (40, 0.5, False), (63, 1.3, False), (40, 1.3, True)])
+def test_direct_ingest_from_page_locked_blocks(oracle_lib, monkeypatch, k, reserve_frac, profile):
+    """DATA_BLOCKs in page-locked host memory are DMA'd straight into device regions (no staging memcpy); each complete
+    region is packed + scanned.  3 ingest threads with interleaved regions; reserve_frac < 1 runs out of reserved space
+    half way, so later blocks fall back to the staging path and the stream is abandoned."""
+    import torch
+    monkeypatch.setenv("FKGPU_CHUNK_BYTES", str(128 << 10))
+    genome = synth.random_genome(150_000, 71)
+    reads = synth.sample_reads(genome, 20_000, 150, 0.003, 72, n_rate=0.001, len_jitter=60)
+    total = sum(len(r) + 1 for r in reads)
+    nthreads = 3
+    want = oracle_lib.count(reads, k, cutoff=1, profiles=profile)
+    g = FastKGPU(k=k, table_cutoff=1, profile=profile, nthreads=nthreads, reserve_bases=int(total * reserve_frac))
+    try:
+        slabs = [torch.empty(64 << 10, dtype=torch.uint8, pin_memory=True) for _ in range(nthreads)]
+        for t in range(nthreads):                      # tid-major read order, as io.c delivers it
+            mine = reads[len(reads) * t // nthreads: len(reads) * (t + 1) // nthreads]
+            for bases, boff in synth.blocks(mine, max_bytes=40_000):
+                slab = slabs[t]
+                slab[:len(bases)] = torch.frombuffer(bytearray(bases), dtype=torch.uint8)
+                b32 = np.ascontiguousarray(boff, dtype=np.int32)
+                g.ingest_ptr(slab.data_ptr(), b32.ctypes.data, len(b32) - 1, tid=t)
+        got = g.finish(fetch_table=True)
+        assert got.nkmers == want["nkmers"] and got.ndistinct == want["ndistinct"] and got.max_inst == want["max_inst"]
+        assert np.array_equal(got.hist[1:], want["hist"][1:])
+        assert np.array_equal(got.table, want["table"])
+        if profile:
+            off, prof = g.profiles()
+            assert len(off) == len(reads) + 1
+            for r in range(len(reads)):
+                assert np.array_equal(prof[off[r]:off[r + 1]], want["profiles"][r]), f"profile of read {r} differs"
+    finally:
+        g.close()
+
+
 def test_long_reads_hifi_like(oracle_lib):
     genome = synth.random_genome(300_000, 31)
     reads = synth.sample_reads(genome, 400, 15_000, 0.001, 32)
