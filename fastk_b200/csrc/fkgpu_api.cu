@@ -63,7 +63,7 @@ struct PinBuf
 
 #define CHUNK_BYTES (8u << 20)         /* pinned staging chunk per ingest thread; also the granule of the streamed pack + scan */
 
-struct SuperGeom { int k, m, w, p2, bbits, P1, P2; };
+struct SuperGeom { int k, m, w, p2, bbits, P1, P2, pbits; };
 
 struct TidState
   { char   *pin = nullptr;            /* pinned staging chunk                       */
@@ -917,7 +917,12 @@ static SuperGeom super_geom(int k, long long npos_total)
   g.p2 = 1; while (2*g.p2 <= g.w) g.p2 <<= 1;
   const long long sest = std::max<long long>(1,npos_total / 10);        /* expected # of super-mers */
   int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
-  if (bbits > SUP_BBITS) bbits = SUP_BBITS;
+  /* record = [bucket : bbits][# k-mers - 1 : 6][global position : pbits].  The bucket count grows with the input (22 bits up
+     to 4 G positions, one more per doubling) so that buckets keep ~40 super-mers however many GPUs feed them.            */
+  g.pbits = std::max(SUP_PBITS_MIN,ilog2_ceil((unsigned long long) npos_total + 1));
+  int bcap = 22 + std::max(0,g.pbits - 32);
+  bcap = std::min(bcap,std::min(SUP_BBITS,64 - SUP_LBITS - g.pbits));
+  if (bbits > bcap) bbits = bcap;
   static int sp1 = -1, sbb = -1;
   if (sp1 < 0) { const char *e = getenv("FKGPU_SP1"); sp1 = e ? atoi(e) : 11; const char *f = getenv("FKGPU_SBB"); sbb = f ? atoi(f) : 0; }
   if (sbb > 0 && bbits > sbb) bbits = sbb;
@@ -933,7 +938,7 @@ static int super_scan_stage(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
   SuperParams sp;
   sp.seq = d_seq; sp.val = d_val; sp.npos = npos; sp.nvalw = (npos + 31) / 32; sp.nseqw = 2 * sp.nvalw;
   sp.k = g.k; sp.m = g.m; sp.w = g.w; sp.p2 = g.p2; sp.lmax = SUP_LMAX; sp.bbits = g.bbits ? g.bbits : 1;
-  sp.out = out; sp.cap = cap; sp.counter = &d_cnt->nrec; sp.pos_offset = pos_offset;
+  sp.out = out; sp.cap = cap; sp.counter = &d_cnt->nrec; sp.pos_offset = pos_offset; sp.pbits = g.pbits;
   const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW + 2*SUP_ROWS*SUP_RS) * 4;
 #define SUPER_LAUNCH(P2V) do { \
     CU(cudaFuncSetAttribute(k_super<P2V>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
@@ -967,7 +972,7 @@ static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S
  *  (key | count) entries to ent[0..ent_cap) when ent != NULL.  The records may point into the read streams of several
  *  ranks (seqr/pbase, nranks > 1): the bucket kernel then gathers the bases from peer memory over NVLink.             */
 static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
-                             const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase,
+                             const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase, const void *payload, void *wait_event,
                              Key<2> *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
 /*  entries below the table cutoff never leave the chip unless profiles need every count */
 { Misc *d_misc = (Misc *) c->misc.p;
@@ -1006,10 +1011,12 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
   k_fill_u64<<<(unsigned) ((gmax + 1 + 255) / 256),256,0,c->st>>>(gstart,gmax + 1,offs + mbuckets); KCHECK();
   k_groups<<<(unsigned) ((mbuckets + 1 + 255) / 256),256,0,c->st>>>(offs,mbuckets,TS,gstart,gmax); KCHECK();
 
+  /* the payload may still be in flight (its all-to-all overlaps the partition above): order the counting kernel behind it */
+  if (wait_event != NULL) CU(cudaStreamWaitEvent(c->st,(cudaEvent_t) wait_event,0));
   stage_begin(c,FKGPU_ST_BUCKET);
   { BucketParams bp;
     bp.recs = (const u64 *) recs; bp.seq = d_seq; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = g.k;
-    bp.nranks = nranks;
+    bp.nranks = nranks; bp.pbits = g.pbits; bp.payload = (const uint4 *) payload;
     for (int r = 0; r < SUP_MAXRANKS; r++)
       { bp.seqr[r] = (nranks > 1 && r < nranks) ? seqr[r] : d_seq;
         bp.pbase[r] = (nranks > 1 && r < nranks) ? pbase[r] : 0;
@@ -1115,13 +1122,13 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   Misc hm;
   long long gmax = 0;
-  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
+  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   static int verbose = -1;
   if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose)
-    fprintf(stderr,"[fkgpu] super-mer path: k=%d m=%d w=%d bbits=%d supermers=%llu (%.2f k-mers each) kmers=%llu distinct=%llu groups=%lld\n",
-            g.k,g.m,g.w,g.bbits,hc.nrec,hc.nrec ? (double) hc.nkmers / hc.nrec : 0.,hc.nkmers,hm.ndistinct,gmax);
+    fprintf(stderr,"[fkgpu] super-mer path: k=%d m=%d w=%d bbits=%d supermers=%llu (%.2f k-mers each) kmers=%llu distinct=%llu groups=%lld overflow classes=%u\n",
+            g.k,g.m,g.w,g.bbits,hc.nrec,hc.nrec ? (double) hc.nkmers / hc.nrec : 0.,hc.nkmers,hm.ndistinct,gmax,hc.pad);
 
   res->ntable = 0; res->table = NULL; res->table_dev = NULL;
   c->ptab_n = 0;
@@ -1429,8 +1436,9 @@ extern "C" int fkgpu_super_scan(fkgpu_ctx *c, const uint32_t *d_seq, const uint3
       || hist_bits == NULL || npos < 0 || (npos > 0 && (d_seq == NULL || d_val == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_scan: bad argument");
   if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
-  if ((unsigned long long) (pos_offset + npos) >= (1ull << SUP_PBITS))
-    return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: global position %lld exceeds the %d-bit record field",(long long) (pos_offset + npos),SUP_PBITS);
+  if (pos_offset + npos > npos_total || super_geom(c->cfg.kmer,npos_total).pbits > 64 - SUP_LBITS - 1)
+    return set_err(FKGPU_E_ARG,"fkgpu_super_scan: positions [%lld,%lld) do not fit the declared total of %lld",(long long) pos_offset,
+                   (long long) (pos_offset + npos),(long long) npos_total);
   CU(cudaSetDevice(c->cfg.device));
   memset(c->used,0,sizeof(c->used));
   const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
@@ -1465,11 +1473,27 @@ extern "C" int fkgpu_super_scan(fkgpu_ctx *c, const uint32_t *d_seq, const uint3
   return FKGPU_OK;
 }
 
+extern "C" int fkgpu_super_payload(fkgpu_ctx *c, const uint32_t *d_seq, int64_t pos_offset, int64_t npos_total,
+                                   const uint64_t *d_records, int64_t nrecords, void *d_payload)
+{ if (c == NULL || nrecords < 0 || (nrecords > 0 && (d_seq == NULL || d_records == NULL || d_payload == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_super_payload: bad argument");
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_payload: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  CU(cudaSetDevice(c->cfg.device));
+  const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
+  if (nrecords > 0)
+    { k_materialise<<<(unsigned) ((nrecords + 255) / 256),256,0,c->st>>>((const u64 *) d_records,(long long) nrecords,g.pbits,(u64) pos_offset,
+                                                                        g.k,d_seq,(uint4 *) d_payload); KCHECK();
+    }
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
 extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrecords, int64_t npos_total, int32_t nranks,
-                                 const uint32_t *const *seq_of_rank, const int64_t *pos_base, int want_entries,
-                                 fkgpu_result *res, const void **d_entries, int64_t *nentries)
-{ if (c == NULL || res == NULL || nrecords < 0 || (nrecords > 0 && d_records == NULL) || nranks < 1 || nranks > SUP_MAXRANKS
-      || seq_of_rank == NULL || pos_base == NULL || (want_entries && (d_entries == NULL || nentries == NULL)))
+                                 const uint32_t *const *seq_of_rank, const int64_t *pos_base, const void *d_payload,
+                                 void *payload_ready_event, int want_entries, fkgpu_result *res, const void **d_entries, int64_t *nentries)
+{ if (c == NULL || res == NULL || nrecords < 0 || (nrecords > 0 && d_records == NULL)
+      || (d_payload == NULL && (nranks < 1 || nranks > SUP_MAXRANKS || seq_of_rank == NULL || pos_base == NULL))
+      || (want_entries && (d_entries == NULL || nentries == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_count: bad argument");
   if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_count: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
   CU(cudaSetDevice(c->cfg.device));
@@ -1486,7 +1510,7 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
   u64 nk = 0;
   CU(cudaMemsetAsync(c->bsum.p,0,8,c->st));
   if (nrecords > 0)
-    { k_sum_lengths<<<c->sms * 4,256,0,c->st>>>((const u64 *) d_records,(long long) nrecords,(u64 *) c->bsum.p); KCHECK(); }
+    { k_sum_lengths<<<c->sms * 4,256,0,c->st>>>((const u64 *) d_records,(long long) nrecords,super_geom(c->cfg.kmer,npos_total).pbits,(u64 *) c->bsum.p); KCHECK(); }
   CU(cudaMemcpyAsync(&nk,c->bsum.p,8,cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
   Key<2> *ent = NULL;
@@ -1496,15 +1520,22 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
     }
   const u32 *seqr[SUP_MAXRANKS]; u64 pb[SUP_MAXRANKS];
   for (int r = 0; r < SUP_MAXRANKS; r++)
-    { seqr[r] = seq_of_rank[r < nranks ? r : 0]; pb[r] = (u64) pos_base[r < nranks ? r : 0]; }
+    { seqr[r] = d_payload ? NULL : seq_of_rank[r < nranks ? r : 0]; pb[r] = d_payload ? 0 : (u64) pos_base[r < nranks ? r : 0]; }
+  if (d_payload != NULL && nrecords > 0)
+    { k_reindex<<<(unsigned) ((nrecords + 255) / 256),256,0,c->st>>>((u64 *) d_records,(long long) nrecords,g.pbits); KCHECK(); }
   SuperCounters hc; Misc hm; long long gmax = 0;
-  rc = super_count_stage(c,g,(Key<1> *) d_records,(Key<1> *) c->bufA.p,(long long) nrecords,seqr[0],nranks,seqr,pb,
-                         ent,nk,d_cnt,&hc,&hm,&gmax);
+  rc = super_count_stage(c,g,(Key<1> *) d_records,(Key<1> *) c->bufA.p,(long long) nrecords,seqr[0],d_payload ? 1 : nranks,seqr,pb,d_payload,
+                         d_payload ? payload_ready_event : NULL,ent,nk,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
   collect_times(c,res);
+  { const char *e = getenv("FKGPU_VERBOSE");
+    if (e && atoi(e))
+      fprintf(stderr,"[fkgpu] super_count: records=%lld kmers=%llu distinct=%llu entries=%llu groups=%lld overflow classes=%u bucket %.2f ms\n",
+              (long long) nrecords,nk,hm.ndistinct,hc.nent,gmax,hc.pad,c->ms[FKGPU_ST_BUCKET]);
+  }
   res->hist = c->h_hist;
   res->max_inst = (int64_t) hm.maxinst;
   res->ndistinct = (int64_t) hm.ndistinct;

@@ -1133,9 +1133,9 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
  *  A super-mer starts at a legal k-mer that does not continue its predecessor (other bucket / illegal) or sits on
  *  a multiple of 64 (so no super-mer exceeds 64 k-mers and every thread can decide its starts locally).          */
 
-#define SUP_PBITS 36                                /* position field: global position over all ranks' read streams */
+#define SUP_PBITS_MIN 32                            /* position field width (run time, SuperGeom.pbits): global position over all ranks' read streams */
 #define SUP_LMAX  64
-#define SUP_BBITS 22                                /* most bucket-id bits (22 + 6 + 36 = 64)                        */
+#define SUP_BBITS 24                                /* most bucket-id bits (bucket + 6 + position bits <= 64; two partition levels of <= 11 + 13 bits) */
 #define SUP_LBITS 6
 #define SUP_MAXRANKS 8                              /* read streams (one per GPU of the node) a record can point into */
 
@@ -1143,6 +1143,7 @@ struct SuperParams
   { const u32 *seq; const u32 *val;
     long long  npos, nseqw, nvalw;
     int        k, m, w, p2, lmax, bbits;      /* w = k-m+1 window of m-mers, p2 = largest power of two <= w */
+    int        pbits;                         /* width of the position field of a record                    */
     u64       *out; u64 cap;
     u64       *counter;                       /* [0] records emitted, [1] k-mers covered                    */
     u64        pos_offset;                    /* global position of this stream's position 0 (multi-GPU: sum of the lower ranks' lengths) */
@@ -1295,7 +1296,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
       int len = e - j;
       const u32 b = bk[j];
       if (e == SCAN_PPT && !(t & 1) && nlead && nb0 == b) len += (int) nlead;     /* runs on into the next thread's window */
-      p.out[pos++] = ((u64) b << (64 - p.bbits)) | ((u64) (len-1) << SUP_PBITS) | (tile0 + (u64) (base + j));
+      p.out[pos++] = ((u64) b << (64 - p.bbits)) | ((u64) (len-1) << p.pbits) | (tile0 + (u64) (base + j));
     }
 }
 
@@ -1317,6 +1318,9 @@ struct BucketParams
     const u32 *seqr[SUP_MAXRANKS];                       /* multi-GPU: packed reads of every rank (peer memory over NVLink) */
     u64        pbase[SUP_MAXRANKS];                      /* global position of rank r's position 0                          */
     int        nranks;                                   /* 1: every record points into seq                                 */
+    int        pbits;                                    /* width of the position field of a record                         */
+    const uint4 *payload;                                /* != NULL: position field = index of the super-mer's 32-byte left-aligned
+                                                            base string in this array (multi-GPU: exchanged with the records)   */
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
@@ -1412,6 +1416,7 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
     { sp--;
       const u32 rounds = stR[sp], rd = stD[sp];
       bool failed = false;
+      if (threadIdx.x == 0 && rounds > 1) atomicAdd(p.g_fail + 1,1u);      /* statistics: residue classes run after a pool overflow */
       for (u32 i = threadIdx.x; i < BC_TS; i += BC_TPB) slot[i] = BC_EMPTY;
       for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB) s_hist[i] = 0;
       if (threadIdx.x == 0) { s_nnew[0] = 0; s_nnew[1] = 0; s_ovf = 0; }
@@ -1423,25 +1428,31 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
           u32 l = 0;
           if (threadIdx.x < ns)
             { const u64 sm = p.recs[q0 + threadIdx.x];
-              l = (u32) ((sm >> SUP_PBITS) & 63u) + 1u;
-              u64 ps = sm & ((1ull << SUP_PBITS) - 1ull);
-              const u32 *sq = p.seq;
-              if (p.nranks > 1)
-                { int r = 0;                          /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
-#pragma unroll 1
-                  for (int q = 1; q < p.nranks; q++)
-                    if (ps >= p.pbase[q]) r = q;
-                  ps -= p.pbase[r]; sq = p.seqr[r];
-                }
-              const u32 *g = sq + (ps >> 4);
-              const int sh = 2*(int) (ps & 15ull);
-              const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
-              u32 x[9];
-#pragma unroll
-              for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(g + t) : 0u;
+              l = (u32) ((sm >> p.pbits) & 63u) + 1u;
+              u64 ps = sm & ((1ull << p.pbits) - 1ull);
               u32 *d = sbase + threadIdx.x*8;
+              if (p.payload != NULL)
+                { const uint4 a = __ldg(p.payload + 2*ps), b = __ldg(p.payload + 2*ps + 1);
+                  *(uint4 *) d = a; *(uint4 *) (d + 4) = b;
+                }
+              else
+                { const u32 *sq = p.seq;
+                  if (p.nranks > 1)
+                    { int r = 0;                          /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
+#pragma unroll 1
+                      for (int q = 1; q < p.nranks; q++)
+                        if (ps >= p.pbase[q]) r = q;
+                      ps -= p.pbase[r]; sq = p.seqr[r];
+                    }
+                  const u32 *g = sq + (ps >> 4);
+                  const int sh = 2*(int) (ps & 15ull);
+                  const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
+                  u32 x[9];
 #pragma unroll
-              for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
+                  for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(g + t) : 0u;
+#pragma unroll
+                  for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
+                }
               /* both strands of the first k-mer: every loader thread does this together, so sliding onto the next
                  super-mer inside the insert loop is a plain load instead of a divergent recomputation           */
               u32 F0[KW], G0[KW];
@@ -1508,9 +1519,10 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
                     const Key<2> key = strands_canon<KW>(F,G);
                     const u32 h = bucket_hash<KW>(key);
                     if (((h >> 20) & (rounds-1)) != rd) continue;
+                    if (*(volatile u32 *) &s_ovf) break;           /* the class is being abandoned: do not grind on in a full table */
                     u32 x = h & (BC_TS-1);
                     for (u32 step = 0; ; step++)
-                      { if (step >= BC_TS) { s_ovf = 1; break; }
+                      { if (step >= 64) { s_ovf = 1; break; }      /* a probe this long means the table is (nearly) full: split the class */
                         u32 v = ((volatile u32 *) slot)[x];
                         if (v == BC_EMPTY)
                           { if (myrec == 0xffffffffu)
@@ -1609,11 +1621,37 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
     }
 }
 
+/*  multi-GPU exchange: the 32-byte left-aligned base string (<= 64 + k - 1 <= 128 bases) of every super-mer record, in record
+ *  order, gathered out of the sender's own packed reads -- it travels beside the 8-byte records in the all-to-all.       */
+__global__ void __launch_bounds__(256) k_materialise(const u64 *recs, long long n, int pbits, u64 pos_offset, int k, const u32 *seq, uint4 *payload)
+{ const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 sm = recs[i];
+  const u32 l = (u32) ((sm >> pbits) & 63u) + 1u;
+  const u64 ps = (sm & ((1ull << pbits) - 1ull)) - pos_offset;
+  const u32 *g = seq + (ps >> 4);
+  const int sh = 2*(int) (ps & 15ull);
+  const int nw = (int) ((2*(l + k - 1) + sh + 31) >> 5);
+  u32 x[9], d[8];
+#pragma unroll
+  for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(g + t) : 0u;
+#pragma unroll
+  for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
+  payload[2*i]   = make_uint4(d[0],d[1],d[2],d[3]);
+  payload[2*i+1] = make_uint4(d[4],d[5],d[6],d[7]);
+}
+
+/*  after the exchange the position field of received record i becomes i, the index of its payload */
+__global__ void __launch_bounds__(256) k_reindex(u64 *recs, long long n, int pbits)
+{ const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) recs[i] = (recs[i] & ~((1ull << pbits) - 1ull)) | (u64) i;
+}
+
 /* total k-mers covered by n super-mer records (sizes the distinct-entry buffer of a rank after the exchange) */
-__global__ void __launch_bounds__(256) k_sum_lengths(const u64 *recs, long long n, u64 *total)
+__global__ void __launch_bounds__(256) k_sum_lengths(const u64 *recs, long long n, int pbits, u64 *total)
 { u64 s = 0;
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
-    s += ((recs[i] >> SUP_PBITS) & 63ull) + 1ull;
+    s += ((recs[i] >> pbits) & 63ull) + 1ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(total,s);

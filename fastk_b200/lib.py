@@ -100,7 +100,9 @@ def load_library(path=None):
     lib.fkgpu_ipc_close.restype = C.c_int
     lib.fkgpu_super_scan.argtypes = [vp, vp, vp, i64, i64, i64, pp, C.POINTER(i64), C.POINTER(i64), pp, pp, C.POINTER(i32)]
     lib.fkgpu_super_scan.restype = C.c_int
-    lib.fkgpu_super_count.argtypes = [vp, vp, i64, i64, i32, pp, C.POINTER(i64), C.c_int, C.POINTER(_Result), pp,
+    lib.fkgpu_super_payload.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+    lib.fkgpu_super_payload.restype = C.c_int
+    lib.fkgpu_super_count.argtypes = [vp, vp, i64, i64, i32, pp, C.POINTER(i64), vp, vp, C.c_int, C.POINTER(_Result), pp,
                                       C.POINTER(i64)]
     lib.fkgpu_super_count.restype = C.c_int
     lib.fkgpu_entries_partition.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp]
@@ -117,7 +119,7 @@ EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
            "fkgpu_super_supported", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
-           "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort"]
+           "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_payload", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort"]
 
 
 class FkResult:
@@ -248,15 +250,20 @@ class FastKGPU:
                   "fkgpu_super_scan")
         return dict(records=rec.value or 0, n=n.value, nkmers=nk.value, hist=hist.value, offsets=offs.value, bits=bits.value)
 
-    def super_count(self, d_rec_ptr, n, npos_total, seq_ptrs, pos_base, want_entries):
+    def super_payload(self, d_seq_ptr, pos_offset, npos_total, d_rec_ptr, n, d_payload_ptr):
+        self._chk(self.lib.fkgpu_super_payload(self.h, d_seq_ptr, pos_offset, npos_total, d_rec_ptr, n, d_payload_ptr),
+                  "fkgpu_super_payload")
+
+    def super_count(self, d_rec_ptr, n, npos_total, seq_ptrs, pos_base, want_entries, d_payload_ptr=None, ready_event=None):
         """-> (FkResult with the histogram of this rank's buckets, entries device ptr, # entries)"""
         nr = len(seq_ptrs)
-        sp = (C.c_void_p * nr)(*seq_ptrs)
+        sp = (C.c_void_p * max(nr, 1))(*seq_ptrs)
         pb = (C.c_int64 * (nr + 1))(*pos_base)
         r = _Result()
         ent, ne = C.c_void_p(), C.c_int64()
-        self._chk(self.lib.fkgpu_super_count(self.h, d_rec_ptr, n, npos_total, nr, sp, pb, 1 if want_entries else 0,
-                                             C.byref(r), C.byref(ent), C.byref(ne)), "fkgpu_super_count")
+        self._chk(self.lib.fkgpu_super_count(self.h, d_rec_ptr, n, npos_total, nr, sp, pb, d_payload_ptr, ready_event,
+                                             1 if want_entries else 0, C.byref(r), C.byref(ent), C.byref(ne)),
+                  "fkgpu_super_count")
         return FkResult(r, False), (ent.value or 0), ne.value
 
     def entries_partition(self, d_ent_ptr, n, bits, d_out_ptr, d_hist_ptr, d_off_ptr):

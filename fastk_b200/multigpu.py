@@ -5,9 +5,12 @@ Super-mer path (k in 18..56, the default; `MultiGPUCounter._count_super`):
      partitioned by bucket                                                          (fkgpu_super_scan, CUDA)
   2. all-reduce(sum) of the 2^11-bin bucket histogram; contiguous bucket ranges per rank by the cumulative-threshold
      rule of the reference's thread split (MSDsort.c:330-352)                        (plumbing, torch.distributed)
-  3. ONE all-to-all of the 8-byte records over NVLink (~0.6 B per k-mer instead of 16) (dist.all_to_all_single, NCCL)
-  4. the owner expands + hash-counts its buckets on chip; the bases of a super-mer are gathered straight out of the
-     SOURCE rank's packed reads in peer HBM over NVLink (CUDA IPC pointers)           (fkgpu_super_count, CUDA)
+  3. all-to-all of the 8-byte records and of their 32-byte left-aligned base strings (fkgpu_super_payload gathers them
+     from the rank's own reads) over NVLink: ~3.7 B per k-mer instead of 16         (dist.all_to_all_single, NCCL)
+  4. the owner expands + hash-counts its buckets on chip from the received base strings (fkgpu_super_count, CUDA).
+     FKGPU_MG=peer instead exchanges ONLY the records and lets the counting kernel gather the bases straight out of the
+     source rank's packed reads in peer HBM (CUDA IPC pointers): fine at 2 GPUs, but small random NVLink reads from
+     three or more peers collapse (measured: 22 ms -> 490 ms for the kernel at 4 GPUs), hence not the default
      -> histogram / scalars complete per rank (a canonical k-mer lives in exactly one bucket): all-reduce(sum)
   5. only when a sorted table is wanted: the distinct (key | count) entries are partitioned by key prefix, exchanged
      with a second all-to-all and put in key order locally (fkgpu_entries_partition / fkgpu_entries_sort, CUDA);
@@ -71,15 +74,17 @@ def exchange_plan(local_offsets, beg):
     return [int(lo[beg[r + 1]] - lo[beg[r]]) for r in range(len(beg) - 1)]
 
 
-def exchange_records(records, send_counts, group=None):
+def exchange_records(records, send_counts, group=None, recv_counts=None):
     """records: [n, w] int64 tensor ordered by destination rank.  One all-to-all of the variable-size slices.
-    -> (received [m, w] tensor, recv_counts)."""
+    -> (received [m, w] tensor, recv_counts).  recv_counts may be passed when a previous exchange with the same plan
+    already learnt them."""
     world = dist.get_world_size(group)
     dev = records.device
-    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-    rc = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.cpu()]
+    if recv_counts is None:
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        rc = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rc, sc, group=group)
+        recv_counts = [int(x) for x in rc.cpu()]
     out = torch.empty((sum(recv_counts) + 8, records.shape[1]), dtype=records.dtype, device=dev)   # +8 records of slack
     dist.all_to_all_single(out[:sum(recv_counts)], records[:sum(send_counts)], recv_counts, list(send_counts), group=group)
     return out, recv_counts
@@ -152,13 +157,15 @@ class MultiGPUCounter:
             dist.all_gather_into_tensor(allh, mine)
             allh = allh.cpu().numpy().tobytes()
             self.peer_seq = [seq if r == self.rank else eng.ipc_open(allh[64 * r:64 * r + 64]) for r in range(self.world)]
+            self._opened = [p for r, p in enumerate(self.peer_seq) if r != self.rank]
+            if os.environ.get("FKGPU_DIAG_LOCALSEQ"):      # timing diagnostic only (wrong counts): every gather stays local
+                self.peer_seq = [seq] * self.world
         return seq, val
 
     def close_peers(self):
-        if getattr(self, "peer_seq", None):
-            for r, p in enumerate(self.peer_seq):
-                if r != self.rank and p:
-                    self.eng.ipc_close(p)
+        for p in getattr(self, "_opened", []):
+            self.eng.ipc_close(p)
+        self._opened = []
         self.peer_seq = None
 
     def count_packed(self, d_seq, d_val, npos, fetch_table=False):
@@ -204,15 +211,37 @@ class MultiGPUCounter:
         send_counts = exchange_plan(device_view(sc["offsets"], nb + 1, dev), beg)
         recs = device_view(sc["records"], sc["n"], dev).view(-1, 1)
         tm.lap("hist all-reduce + splitters")
+        mode = os.environ.get("FKGPU_MG", "")
+        peer_mode = (mode == "peer") or (mode != "payload" and self.world <= 2)
+        payload = None
+        if not peer_mode:
+            # the base string of every super-mer (32 bytes, left aligned), in record order: travels beside the records
+            payload = torch.empty((sc["n"] + 8, 4), dtype=torch.int64, device=dev)
+            eng.super_payload(sp, self.pos_base[self.rank], total, sc["records"], sc["n"], payload.data_ptr())
+            tm.lap("payload gather")
         recv, recv_counts = exchange_records(recs, send_counts)
         torch.cuda.current_stream().synchronize()      # NCCL wrote `recv` on torch's stream; the library runs on its own
         tm.lap("record all-to-all")
         nrecv = sum(recv_counts)
+        recv_pl, ready = None, None
+        if payload is not None:
+            # asynchronous: the payload crosses NVLink while the library partitions the records; the counting kernel is
+            # ordered behind `ready` on the device, the host never waits for it
+            recv_pl = torch.empty((nrecv + 8, 4), dtype=torch.int64, device=dev)
+            work = dist.all_to_all_single(recv_pl[:nrecv], payload[:sum(send_counts)], recv_counts, list(send_counts),
+                                          async_op=True)
+            work.wait()
+            ready = torch.cuda.Event()
+            ready.record()
         want_entries = eng_wants_entries(eng)
-        res, ent_ptr, nent = eng.super_count(recv.data_ptr(), nrecv, total, self.peer_seq, self.pos_base, want_entries)
+        res, ent_ptr, nent = eng.super_count(recv.data_ptr(), nrecv, total, self.peer_seq, self.pos_base, want_entries,
+                                             d_payload_ptr=None if recv_pl is None else recv_pl.data_ptr(),
+                                             ready_event=None if ready is None else ready.cuda_event)
+        del recv_pl, payload
         tm.lap("super_count")
         out = MultiResult()
         out.path = "super-mer"
+        out.exchange = "peer-gather" if peer_mode else "payload"
         out.sent_records = sc["n"] - send_counts[self.rank]
         out.supermers, out.entries = sc["n"], nent
         out.owned_buckets = (beg[self.rank], beg[self.rank + 1])

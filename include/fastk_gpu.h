@@ -152,6 +152,10 @@ int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int 
  *   fkgpu_super_bucket_bits bucket-id width every rank derives from the GLOBAL position count
  *   fkgpu_super_scan        reads -> records, partitioned by the top *hist_bits bucket bits; all outputs are device
  *                           pointers into context memory, valid until the next call on this context
+ *   fkgpu_super_payload     the 32-byte left-aligned base string of every record, in record order, gathered from the rank's own
+ *                           reads: exchanged beside the records (default; bulk NVLink transfers).  With d_payload == NULL in
+ *                           fkgpu_super_count the bases are instead gathered from peer HBM inside the counting kernel
+ *                           (measured: fine at 2 GPUs, collapses at 4 -- small random NVLink reads; FKGPU_MG=peer keeps it)
  *   fkgpu_super_count       received records (consumed; room for nrecords + 8) -> histogram / scalars in res and, if
  *                           want_entries, the distinct (16-byte key | count in the low 16 bits) entries on the device
  *   fkgpu_entries_partition entries -> d_out ordered by the top `bits` key bits; d_hist [2^bits], d_offsets [2^bits+1]
@@ -166,9 +170,13 @@ int  fkgpu_ipc_close (fkgpu_ctx *ctx, void *d_ptr);
 int  fkgpu_super_scan(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos, int64_t npos_total,
                       int64_t pos_offset, const uint64_t **d_records, int64_t *nrecords, int64_t *nkmers,
                       const uint64_t **d_bucket_hist, const uint64_t **d_bucket_offsets, int32_t *hist_bits);
+int  fkgpu_super_payload(fkgpu_ctx *ctx, const uint32_t *d_seq, int64_t pos_offset, int64_t npos_total,
+                         const uint64_t *d_records, int64_t nrecords, void *d_payload /* nrecords x 32 bytes */);
 int  fkgpu_super_count(fkgpu_ctx *ctx, uint64_t *d_records, int64_t nrecords, int64_t npos_total, int32_t nranks,
-                       const uint32_t *const *seq_of_rank, const int64_t *pos_base, int want_entries,
-                       fkgpu_result *res, const void **d_entries, int64_t *nentries);
+                       const uint32_t *const *seq_of_rank, const int64_t *pos_base, const void *d_payload,
+                       void *payload_ready_event /* cudaEvent_t or NULL: the counting kernel waits for it, so the payload's
+                                                    all-to-all can overlap the partition of the records */,
+                       int want_entries, fkgpu_result *res, const void **d_entries, int64_t *nentries);
 int  fkgpu_entries_partition(fkgpu_ctx *ctx, const void *d_entries, int64_t n, int bits, void *d_out,
                              uint64_t *d_hist, uint64_t *d_offsets);
 int  fkgpu_entries_sort(fkgpu_ctx *ctx, void *d_entries, int64_t n, int fetch_table, fkgpu_result *res);
