@@ -923,6 +923,10 @@ static SuperGeom super_geom(int k, long long npos_total)
   int bcap = 22 + std::max(0,g.pbits - 32);
   bcap = std::min(bcap,std::min(SUP_BBITS,64 - SUP_LBITS - g.pbits));
   if (bbits > bcap) bbits = bcap;
+  { static int forced = -2;                 /* FKGPU_BBITS: force the bucket-id width (tests exercise the 8-GPU geometry on one GPU) */
+    if (forced == -2) { const char *e = getenv("FKGPU_BBITS"); forced = e ? atoi(e) : -1; }
+    if (forced >= 0) bbits = std::min(forced,std::min(SUP_BBITS,64 - SUP_LBITS - g.pbits));
+  }
   static int sp1 = -1, sbb = -1;
   if (sp1 < 0) { const char *e = getenv("FKGPU_SP1"); sp1 = e ? atoi(e) : 11; const char *f = getenv("FKGPU_SBB"); sbb = f ? atoi(f) : 0; }
   if (sbb > 0 && bbits > sbb) bbits = sbb;

@@ -115,6 +115,24 @@ def test_direct_ingest_from_page_locked_blocks(oracle_lib, monkeypatch, k, reser
         g.close()
 
 
+@pytest.mark.parametrize("bbits", [24, 3])
+def test_forced_bucket_geometry(bbits):
+    """The bucket-id width is a run-time property of the record layout (it grows with the global input at 4 / 8 GPUs:
+    24 bits, 13-bit second partition level).  Force the extremes on one GPU -- in a fresh process, the override is read
+    once -- and re-run two parity tests: almost-empty buckets (24) and heavily overflowing ones (3: every group
+    exceeds the on-chip pool and is re-run in residue classes)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, FKGPU_BBITS=str(bbits))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x",
+                        os.path.join(here, "test_gpu_parity.py") + "::test_medium_30x",
+                        os.path.join(here, "test_gpu_parity.py") + "::test_long_reads_hifi_like"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_long_reads_hifi_like(oracle_lib):
     genome = synth.random_genome(300_000, 31)
     reads = synth.sample_reads(genome, 400, 15_000, 0.001, 32)
