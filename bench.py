@@ -357,6 +357,7 @@ def main():
         st = dict(path=1 if res.path == "super-mer" else 0, supermers=getattr(res, "supermers", 0),
                   entries=getattr(res, "entries", 0), groups=0)
         N, U = N // world, U // world
+    ntab = res.ntable // world
     if st["path"] == 1:
         # super-mer path: 8-byte super-mer pointers (bucket|len|position) through the partition (histogram read, scatter
         # read+write, refine 2 reads + write = 6 passes), base gather + 16-byte (key|count) entries out of the bucket
@@ -367,15 +368,15 @@ def main():
                "bucket_count": S * 8 + (N + S * (k - 1)) * 0.25 + E * 16,
                "entry_partition": 3 * E * 16,
                "refine": 3 * E * 16,
-               "sortcount": E * 16 + E * 20,
-               "compact": E * 20 + res.ntable * (res.kmer_bytes + 2)}
+               # the weighted sort writes the final table records itself (no staging, no compaction pass)
+               "sortcount": E * 16 + ntab * (res.kmer_bytes + 2)}
         W = 16
     else:
         alg = {"scan_hist": nbases * 0.375,
                "scan_scatter": nbases * 0.375 + N * W,
                "refine": 3 * N * W,
                "sortcount": N * W + U * (W + 4),
-               "compact": U * (W + 4) + res.ntable * (res.kmer_bytes + 2)}
+               "compact": U * (W + 4) + ntab * (res.kmer_bytes + 2)}
     per_stage = {}
     for s, b in alg.items():
         ms = stage_ms.get(s, 0.0) / args.steps

@@ -1519,10 +1519,11 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
                     const Key<2> key = strands_canon<KW>(F,G);
                     const u32 h = bucket_hash<KW>(key);
                     if (((h >> 20) & (rounds-1)) != rd) continue;
-                    if (*(volatile u32 *) &s_ovf) break;           /* the class is being abandoned: do not grind on in a full table */
                     u32 x = h & (BC_TS-1);
                     for (u32 step = 0; ; step++)
-                      { if (step >= 64) { s_ovf = 1; break; }      /* a probe this long means the table is (nearly) full: split the class */
+                      { /* a long probe means the table is (nearly) full, or the class is already being abandoned: split it
+                           instead of grinding on (checked off the common path, after 16 steps)                              */
+                        if (step >= 16 && (step >= 64 || *(volatile u32 *) &s_ovf)) { s_ovf = 1; break; }
                         u32 v = ((volatile u32 *) slot)[x];
                         if (v == BC_EMPTY)
                           { if (myrec == 0xffffffffu)
