@@ -1030,10 +1030,12 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(g.k,km);
-#define BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,KWV) do { \
+#define BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,PAYV) do { \
       const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
-      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL,KWV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
-      k_bucket_count<TPB,GC,CH,DC,TSL,KWV><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
+      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL,KWV,PAYV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
+      k_bucket_count<TPB,GC,CH,DC,TSL,KWV,PAYV><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
+#define BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,KWV) do { \
+      if (payload != NULL) BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,true); else BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,false); } while (0)
 #define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
       if (kw == 2) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,2); else if (kw == 3) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,3); else BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,4); } while (0)
     const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */

@@ -19,6 +19,9 @@
  *    k_compact        staged entries -> [KMER_BYTES key][u16 count] records    (count.c:564-616 table_write_thread)
  */
 #pragma once
+#ifndef FKGPU_PROBE_CAP
+#define FKGPU_PROBE_CAP 64          /* linear-probe steps after which a hash class counts as overflowing */
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1319,7 +1322,7 @@ struct BucketParams
     u64        pbase[SUP_MAXRANKS];                      /* global position of rank r's position 0                          */
     int        nranks;                                   /* 1: every record points into seq                                 */
     int        pbits;                                    /* width of the position field of a record                         */
-    const uint4 *payload;                                /* != NULL: position field = index of the super-mer's 32-byte left-aligned
+    const uint4 *payload;                                /* PAY instantiation: position field = index of the super-mer's 32-byte left-aligned
                                                             base string in this array (multi-GPU: exchanged with the records)   */
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
@@ -1387,7 +1390,7 @@ __device__ __forceinline__ u32 bucket_hash(const Key<2> &a)
   return h;
 }
 
-template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS, int KW>
+template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS, int KW, bool PAY>
 __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 klast)
 { static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS && BC_DC <= 1024 && KW >= 2 && KW <= 4,"bucket kernel geometry");
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1431,7 +1434,7 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
               l = (u32) ((sm >> p.pbits) & 63u) + 1u;
               u64 ps = sm & ((1ull << p.pbits) - 1ull);
               u32 *d = sbase + threadIdx.x*8;
-              if (p.payload != NULL)
+              if (PAY)
                 { const uint4 a = __ldg(p.payload + 2*ps), b = __ldg(p.payload + 2*ps + 1);
                   *(uint4 *) d = a; *(uint4 *) (d + 4) = b;
                 }
@@ -1521,9 +1524,8 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
                     if (((h >> 20) & (rounds-1)) != rd) continue;
                     u32 x = h & (BC_TS-1);
                     for (u32 step = 0; ; step++)
-                      { /* a long probe means the table is (nearly) full, or the class is already being abandoned: split it
-                           instead of grinding on (checked off the common path, after 16 steps)                              */
-                        if (step >= 16 && (step >= 64 || *(volatile u32 *) &s_ovf)) { s_ovf = 1; break; }
+                      { /* a probe this long means the table is (nearly) full: split the class instead of grinding on */
+                        if (step >= FKGPU_PROBE_CAP) { s_ovf = 1; break; }
                         u32 v = ((volatile u32 *) slot)[x];
                         if (v == BC_EMPTY)
                           { if (myrec == 0xffffffffu)

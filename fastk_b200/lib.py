@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfastk_gpu.so")
+LIB_PATH = os.environ.get("FKGPU_LIB") or os.path.join(HERE, "lib", "libfastk_gpu.so")
 
 HIST_BINS = 32768
 NSTAGES = 12

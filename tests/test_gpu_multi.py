@@ -16,7 +16,7 @@ def _ngpu():
     return fastk_b200.load_library().fkgpu_device_count()
 
 
-@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (21, "super-mer", {}), (40, "super-mer", {"FKGPU_MG": "peer"}),
+@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (21, "super-mer", {"FKGPU_MG": "payload"}), (40, "super-mer", {"FKGPU_MG": "peer"}),
                                         (40, "records", {"FKGPU_MG": "records"}), (63, "records", {})])
 def test_multi_gpu_equals_single_gpu(k, path, env):
     n = _ngpu()
@@ -29,8 +29,8 @@ def test_multi_gpu_equals_single_gpu(k, path, env):
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (50, "super-mer", {"FKGPU_MG": "peer"}),
-                                        (40, "records", {"FKGPU_MG": "records"})])
+@pytest.mark.parametrize("k,path,env", [(40, "super-mer", {"FKGPU_MG": "payload"}), (50, "super-mer", {"FKGPU_MG": "peer"}),
+                                        (21, "super-mer", {"FKGPU_MG": "payload"}), (40, "records", {"FKGPU_MG": "records"})])
 def test_multi_gpu_stages_world1(k, path, env):
     """The same staged pipeline (scan -> exchange -> count -> entry exchange -> sort) with a world of ONE rank: runs on a
     single-GPU box, so every stage entry point of the multi-GPU path is parity-checked there too."""
