@@ -8,6 +8,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <vector>
+#include <atomic>
 #include <mutex>
 #include <shared_mutex>
 #include <algorithm>
@@ -104,7 +105,7 @@ struct fkgpu_ctx
     /* streamed front end (cfg.reserve_bases > 0): every staging chunk is packed -- and, on the super-mer path, scanned
        into super-mer records -- as soon as its host-to-device copy lands, overlapping the ingest                       */
     size_t       chunk_bytes = CHUNK_BYTES;   /* FKGPU_CHUNK_BYTES overrides (tests force many small chunks) */
-    bool         stream_started = false, stream_on = false, stream_scan = false;
+    std::atomic<bool> stream_started{false}, stream_on{false}, stream_scan{false};   /* written under mu, polled without it */
     long long    stream_cap = 0;      /* positions the device buffers were sized for */
     SuperGeom    sgeom;
 
@@ -209,7 +210,7 @@ extern "C" int fkgpu_reset(fkgpu_ctx *c)
       t.reg_off = -1; t.reg_fill = 0;
     }
   c->ascii_used = 0; c->nreads = 0; c->nbases = 0; c->finished = false;
-  c->stream_started = c->stream_on = c->stream_scan = false;
+  c->stream_started = false; c->stream_on = false; c->stream_scan = false;
   return FKGPU_OK;
 }
 
@@ -275,7 +276,7 @@ static int flush_tid(fkgpu_ctx *c, TidState &t)
     if (c->stream_on && c->ascii_used + (long long) padded > c->stream_cap)
       { /* more reads than reserved: the buffers must grow, so the rest is packed and scanned at finish instead */
         CU(cudaStreamSynchronize(c->st));
-        c->stream_on = c->stream_scan = false;
+        c->stream_on = false; c->stream_scan = false;
       }
     if (ascii_reserve(c,c->ascii_used + (long long) padded))
       return set_err(FKGPU_E_NOMEM,"fkgpu_ingest: cannot grow the device read buffer to %lld bytes",c->ascii_used + (long long) padded);
@@ -367,6 +368,7 @@ extern "C" int fkgpu_ingest(fkgpu_ctx *c, int tid, const char *bases, const int3
       if (!c->stream_started)
         { int rc = stream_begin(c);
           if (rc) return rc;
+          c->stream_started = true;                 /* published last: the buffers and flags above are final */
         }
     }
   if (t.pin == nullptr)
@@ -1164,7 +1166,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
  *  chunk and, on the super-mer path, appends its super-mer records: chunks are self-contained (whole 0-terminated reads,
  *  a continued read re-delivers its k-1 overlap), so no k-mer spans two chunks.                                        */
 static int stream_begin(fkgpu_ctx *c)
-{ c->stream_started = true; c->stream_on = c->stream_scan = false;
+{ c->stream_on = false; c->stream_scan = false;
   static int off = -1;
   if (off < 0) { const char *e = getenv("FKGPU_NOSTREAM"); off = (e && atoi(e)) ? 1 : 0; }
   if (c->cfg.reserve_bases <= 0 || off) return FKGPU_OK;

@@ -81,3 +81,40 @@ def test_splitters_rule_matches_reference_panel_split():
     assert multigpu.splitters_from_hist(h, 2) == [0, 4, 8]         # 10 >= 21//2 after bin 3
     assert multigpu.splitters_from_hist(h, 3) == [0, 3, 7, 8]      # thr 7 -> bin 2 (8); thr 14 -> bin 6 (20)
     assert multigpu.splitters_from_hist(np.zeros(4, np.int64), 3) == [0, 1, 2, 4]
+
+
+def _panel_split_loop(h, world):
+    """msd_sort's panel split (MSDsort.c:330-352) written as the reference writes it: one pass over the bins."""
+    total = int(sum(h))
+    beg, n, s, thr = [0], 0, 0, total // world
+    for x in range(len(h)):
+        s += int(h[x])
+        if s >= thr and n < world - 1:
+            n += 1
+            beg.append(x + 1)
+            thr = (total * (n + 1)) // world
+    while len(beg) < world:
+        beg.append(len(h))
+    beg.append(len(h))
+    return beg
+
+
+def test_splitters_equal_the_one_pass_rule_on_random_histograms():
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        nb = int(rng.integers(1, 70))
+        world = int(rng.integers(1, 9))
+        kind = trial % 4
+        if kind == 0:
+            h = rng.integers(0, 50, nb)
+        elif kind == 1:
+            h = (rng.random(nb) ** 6 * 1000).astype(np.int64)           # a few heavy bins
+        elif kind == 2:
+            h = np.zeros(nb, np.int64)
+            h[rng.integers(0, nb)] = 1000                                # everything in one bin
+        else:
+            h = rng.integers(0, 3, nb)
+        got = multigpu.splitters_from_hist(h.astype(np.int64), world)
+        assert got == _panel_split_loop(h, world), (list(h), world, got)
+        assert got[0] == 0 and got[-1] == nb and len(got) == world + 1
+        assert all(got[i] <= got[i + 1] for i in range(world))
