@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--sub-rate", type=float, default=0.001)
     ap.add_argument("--cutoff", type=int, default=1, help="-t<cutoff>")
     ap.add_argument("--cpu-sample-gbases", type=float, default=0.45)
+    ap.add_argument("--ingest-threads", type=int, default=0, help="e2e arm: ingest threads (0 = host cores, at most 16)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
@@ -238,7 +239,7 @@ def main():
 
     # ---- build the batch: ASCII on the device -> packed (device-resident arm) and pinned host copy (e2e arm)
     ascii_dev = gen_reads_ascii(torch, dev, genome_bp, nreads, args.read_len, args.sub_rate, args.seed + 7919 * rank)
-    nthr = max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
+    nthr = args.ingest_threads or max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
     eng = FastKGPU(k=k, table_cutoff=args.cutoff, device=local, nthreads=nthr, reserve_bases=npos)
     runner = None
     if world > 1:
@@ -336,6 +337,7 @@ def main():
                "ingest_ms_per_step": e2e_split["ingest_ms"] / args.steps,
                "finish_ms_per_step": e2e_split["finish_ms"] / args.steps,
                "finish_device_ms": r2.ms_total,
+               "finish_stage_ms": {kn: round(v, 3) for kn, v in eng.stage_times().items() if v > 0},
                "path": f"fkgpu_ingest ({nthr} threads, DATA_BLOCKs in pinned host memory; chunks packed + scanned on the device as "
                        "they land) -> fkgpu_finish(fetch_table=1)"}
         assert r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct, "e2e and device-resident arms disagree"

@@ -106,7 +106,9 @@ struct fkgpu_ctx
        into super-mer records -- as soon as its host-to-device copy lands, overlapping the ingest                       */
     size_t       chunk_bytes = CHUNK_BYTES;   /* FKGPU_CHUNK_BYTES overrides (tests force many small chunks) */
     std::atomic<bool> stream_started{false}, stream_on{false}, stream_scan{false};   /* written under mu, polled without it */
-    long long    stream_cap = 0;      /* positions the device buffers were sized for */
+    long long    stream_cap = 0;      /* positions the device read buffers (ascii / seq / val) were sized for: the reservation
+                                         plus room for the zero gaps that end chunks and direct regions               */
+    long long    stream_nub = 0;      /* bases the record buffers (super-mers, entries) were sized for                */
     SuperGeom    sgeom;
 
     /* device working set */
@@ -1099,7 +1101,7 @@ static SuperBufs super_bufs(fkgpu_ctx *c, long long nub)
  *  zeroed the counters and scanned every chunk into super-mer records during the ingest                                  */
 static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
                               bool own_total, bool *fell_back, bool prescanned)
-{ const long long nub = prescanned ? c->stream_cap : npos;
+{ const long long nub = prescanned ? c->stream_nub : npos;
   const SuperGeom g = prescanned ? c->sgeom : super_geom(c->cfg.kmer,npos);
   *fell_back = false;
   int rc;
@@ -1172,19 +1174,19 @@ static int stream_begin(fkgpu_ctx *c)
   if (c->cfg.reserve_bases <= 0 || off) return FKGPU_OK;
   /* reserve_bases is only a hint (the reference-hosted shim extrapolates it from the first block): if the device
      cannot hold buffers of that size, forget the hint and let the buffers grow with what actually arrives          */
-  bool ok = (ascii_reserve(c,1) == 0);
-  long long cap = 0;
+  const long long nub = (c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20)) & ~63ll;
+  /* position space: a direct region ends when the next block does not fit, so up to one block per region is a zero gap */
+  long long cap = (nub + c->cfg.reserve_bases/8 + (long long) c->tids.size() * (long long) c->chunk_bytes) & ~63ll;
+  bool ok = (ascii_reserve(c,cap + 192) == 0);
   if (ok)
-    { cap = std::min<long long>((long long) c->ascii.cap - 256,c->cfg.reserve_bases + c->cfg.reserve_bases/50 + (1 << 20));
-      cap &= ~63ll;
-      int64_t sw, vw;
+    { int64_t sw, vw;
       fkgpu_packed_words(cap,&sw,&vw);
       ok = !(c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4));
     }
   const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0;
   if (scan)
     { c->sgeom = super_geom(c->cfg.kmer,cap);
-      ok = (prepare_common(c,cap,std::max(c->sgeom.P1,1),true,2) == 0) && !c->segs.ensure(sizeof(SuperCounters));
+      ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,2) == 0) && !c->segs.ensure(sizeof(SuperCounters));
     }
   if (!ok)
     { c->ascii.release(); c->seq.release(); c->val.release(); c->bufA.release(); c->bufB.release();
@@ -1192,7 +1194,7 @@ static int stream_begin(fkgpu_ctx *c)
       g_err[0] = 0;
       return FKGPU_OK;
     }
-  c->stream_cap = cap;
+  c->stream_cap = cap; c->stream_nub = nub;
   c->stream_on = true;
   if (scan)
     { CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
@@ -1208,7 +1210,7 @@ static int stream_chunk(fkgpu_ctx *c, long long off, long long len, long long sc
   k_pack_ascii<<<(unsigned) ((vw + 255) / 256),256,0,c->st>>>((const uint4 *) ((const char *) c->ascii.p + off),len,seq,val,vw);
   KCHECK();
   if (c->stream_scan)
-    { const SuperBufs sb = super_bufs(c,c->stream_cap);
+    { const SuperBufs sb = super_bufs(c,c->stream_nub);
       return super_scan_stage(c,seq,val,scan_len,c->sgeom,(u64) off,(u64 *) sb.SA,sb.scap,(SuperCounters *) c->segs.p);
     }
   return FKGPU_OK;

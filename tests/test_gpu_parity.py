@@ -68,7 +68,7 @@ def test_medium_30x(oracle_lib):
     check(oracle_lib, reads, 21, cutoff=4, nthreads=3)
 
 
-@pytest.mark.parametrize("k,bc,reserve_frac", [(40, 0, 1.2), (21, 0, 1.2), (40, 0, 0.4), (63, 0, 1.2), (40, 10, 1.2)])
+@pytest.mark.parametrize("k,bc,reserve_frac", [(40, 0, 1.2), (21, 0, 1.2), (40, 0, 0.25), (63, 0, 1.2), (40, 10, 1.2)])
 def test_streamed_front_end(oracle_lib, monkeypatch, k, bc, reserve_frac):
     """reserve_bases > 0: every staging chunk is packed (and, on the super-mer path, scanned into super-mer records) as
     soon as it lands on the device.  Many small chunks from 3 ingest threads; reserve_frac < 1 makes the reservation too
@@ -80,7 +80,7 @@ def test_streamed_front_end(oracle_lib, monkeypatch, k, bc, reserve_frac):
     check(oracle_lib, reads, k, bc=bc, nthreads=3, block_bytes=40_000, reserve=int(total * reserve_frac))
 
 
-@pytest.mark.parametrize("k,reserve_frac,profile", [(40, 1.3, False), (21, 1.3, False), (40, 0.5, False), (63, 1.3, False), (40, 1.3, True)])
+@pytest.mark.parametrize("k,reserve_frac,profile", [(40, 1.3, False), (21, 1.3, False), (40, 0.25, False), (63, 1.3, False), (40, 1.3, True)])
 def test_direct_ingest_from_page_locked_blocks(oracle_lib, monkeypatch, k, reserve_frac, profile):
     """DATA_BLOCKs in page-locked host memory are DMA'd straight into device regions (no staging memcpy); each complete
     region is packed + scanned.  3 ingest threads with interleaved regions; reserve_frac < 1 runs out of reserved space
