@@ -425,8 +425,11 @@ def main():
                            "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
                            "supermer_records": st["supermers"], "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),
-                           "parallelism": ("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, bases gathered from "
-                                           "peer HBM over NVLink in the count kernel, second all-to-all of the distinct entries"
+                           "parallelism": (("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, "
+                                            + ("bases gathered from peer HBM over NVLink inside the count kernel"
+                                               if getattr(res, "exchange", "") == "peer-gather" else
+                                               "their 32-byte base strings in a second all-to-all overlapped with the record partition")
+                                            + ", then all-to-all of the distinct entries by key prefix")
                                            if st["path"] == 1 else "1 process/GPU; prefix-range all-to-all of k-mer records over NCCL")
                            if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}

@@ -150,16 +150,39 @@ class MultiGPUCounter:
         self.pos_base = [0]
         for x in sizes:
             self.pos_base.append(self.pos_base[-1] + ((x + 63) // 64) * 64)
-        self.peer_seq = None
-        if eng.super_supported() and self.world <= MAX_SUPER_RANKS:
-            mine = torch.frombuffer(bytearray(eng.ipc_export(seq)), dtype=torch.uint8).to(self.dev)
+        self.peer_seq, self._opened = None, []
+        self.super_ok = eng.super_supported()
+        mode = os.environ.get("FKGPU_MG", "")
+        if self.super_ok and self.world <= MAX_SUPER_RANKS and (mode == "peer" or (mode != "payload" and self.world <= 2)):
+            # peer variant: every rank maps every other rank's packed reads (CUDA IPC).  Collective, so all ranks agree on
+            # whether it worked; if any rank cannot export / map, everyone uses the payload exchange instead.
+            ok = 1
+            try:
+                mine = torch.frombuffer(bytearray(eng.ipc_export(seq)), dtype=torch.uint8).to(self.dev)
+            except Exception:
+                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device=self.dev)
             allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=self.dev)
             dist.all_gather_into_tensor(allh, mine)
             allh = allh.cpu().numpy().tobytes()
-            self.peer_seq = [seq if r == self.rank else eng.ipc_open(allh[64 * r:64 * r + 64]) for r in range(self.world)]
-            self._opened = [p for r, p in enumerate(self.peer_seq) if r != self.rank]
-            if os.environ.get("FKGPU_DIAG_LOCALSEQ"):      # timing diagnostic only (wrong counts): every gather stays local
-                self.peer_seq = [seq] * self.world
+            flag = torch.tensor([ok], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            peers = []
+            if int(flag.item()):
+                try:
+                    for r in range(self.world):
+                        peers.append(seq if r == self.rank else eng.ipc_open(allh[64 * r:64 * r + 64]))
+                        if r != self.rank:
+                            self._opened.append(peers[-1])
+                except Exception:
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                self.peer_seq = peers
+                if os.environ.get("FKGPU_DIAG_LOCALSEQ"):      # timing diagnostic only (wrong counts): every gather stays local
+                    self.peer_seq = [seq] * self.world
+            else:
+                self.close_peers()
         return seq, val
 
     def close_peers(self):
@@ -172,7 +195,7 @@ class MultiGPUCounter:
         """d_seq / d_val: torch tensors or raw device pointers.  The super-mer path needs the buffers of alloc_reads()."""
         sp = d_seq if isinstance(d_seq, int) else d_seq.data_ptr()
         vp = d_val if isinstance(d_val, int) else d_val.data_ptr()
-        if getattr(self, "peer_seq", None) and sp == self.seq_ptr and npos == self.npos and os.environ.get("FKGPU_MG") != "records":
+        if getattr(self, "super_ok", False) and sp == self.seq_ptr and npos == self.npos and os.environ.get("FKGPU_MG") != "records":
             return self._count_super(sp, vp, npos, fetch_table)
         return self._count_records(sp, vp, npos, fetch_table)
 
@@ -212,7 +235,7 @@ class MultiGPUCounter:
         recs = device_view(sc["records"], sc["n"], dev).view(-1, 1)
         tm.lap("hist all-reduce + splitters")
         mode = os.environ.get("FKGPU_MG", "")
-        peer_mode = (mode == "peer") or (mode != "payload" and self.world <= 2)
+        peer_mode = self.peer_seq is not None and ((mode == "peer") or (mode != "payload" and self.world <= 2))
         payload = None
         if not peer_mode:
             # the base string of every super-mer (32 bytes, left aligned), in record order: travels beside the records
@@ -234,7 +257,8 @@ class MultiGPUCounter:
             ready = torch.cuda.Event()
             ready.record()
         want_entries = eng_wants_entries(eng)
-        res, ent_ptr, nent = eng.super_count(recv.data_ptr(), nrecv, total, self.peer_seq, self.pos_base, want_entries,
+        res, ent_ptr, nent = eng.super_count(recv.data_ptr(), nrecv, total, self.peer_seq if peer_mode else [sp],
+                                             self.pos_base if peer_mode else [0, total], want_entries,
                                              d_payload_ptr=None if recv_pl is None else recv_pl.data_ptr(),
                                              ready_event=None if ready is None else ready.cuda_event)
         del recv_pl, payload
