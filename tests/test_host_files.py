@@ -23,6 +23,9 @@ def fkfiles(tmp_path_factory):
     L.fk_write_prof.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                 C.POINTER(C.c_uint16)]
     L.fk_idx_bytes.argtypes = [C.c_int64, C.c_int]
+    L.fk_encode_profile.argtypes = [C.POINTER(C.c_uint16), C.c_int64, C.POINTER(C.c_uint8)]
+    L.fk_encode_profile.restype = C.c_int64
+    L.fk_table_split.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -61,3 +64,64 @@ def test_idx_bytes_rule(fkfiles):
     assert fkfiles.fk_idx_bytes(0x4000001, 40) == 3
     assert fkfiles.fk_idx_bytes(0x4000001, 11) == 2
     assert fkfiles.fk_idx_bytes(0x4000001, 7) == 1
+
+
+def _profile_vectors():
+    rng = np.random.default_rng(3)
+    yield np.zeros(0, np.uint16)
+    yield np.array([0], np.uint16)
+    yield np.array([127], np.uint16)
+    yield np.array([128], np.uint16)                                   # first count needs the 2-byte form (merge.c:541-562)
+    yield np.array([32767] * 5, np.uint16)                             # saturated, zero forward differences
+    yield np.zeros(200, np.uint16)                                     # zero runs longer than 63 (count.c:886-899)
+    yield np.array([5] * 63 + [6] + [6] * 64 + [7], np.uint16)         # runs of exactly 62 / 63 / 64 equal counts
+    yield np.array([100, 131, 100, 69, 100, 132, 100, 68], np.uint16)  # |d| = 31 / 32 on both sides of the 1-byte limit
+    yield np.array([0, 32767, 0, 16384, 1, 32766], np.uint16)          # largest 15-bit differences, both signs
+    for _ in range(60):
+        n = int(rng.integers(1, 400))
+        base = rng.integers(0, 32768)
+        steps = rng.choice([0, 0, 0, 1, -1, 3, -7, 31, -31, 32, -32, 500, -500, 20000, -20000], n)
+        v = np.clip(base + np.cumsum(steps), 0, 32767).astype(np.uint16)
+        v[rng.random(n) < 0.05] = 0                                    # N-intervals: counts drop to 0
+        yield v
+
+
+def test_profile_code_round_trip_and_equals_the_restated_encoder(oracle_lib, fkfiles):
+    """fk_encode_profile (product, host C) against the oracle's restatement of the reference encoder (count.c:886-921,
+    merge.c:534-716) and decoder (libfastk.c:1707-1803): same bytes, and decode(encode(x)) == x."""
+    for v in _profile_vectors():
+        out = np.zeros(2 * len(v) + 8, np.uint8)
+        nb = fkfiles.fk_encode_profile(v.ctypes.data_as(C.POINTER(C.c_uint16)), len(v), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        code = out[:nb].tobytes()
+        assert code == oracle_lib.encode_profile(v), list(v[:20])
+        dec = oracle_lib.decode_profile(code, cap=len(v) + 4)
+        assert len(dec) == len(v) and np.array_equal(dec, v), list(v[:20])
+
+
+def test_table_split_rule(fkfiles):
+    """fk_table_split cuts table parts on first-byte boundaries by the cumulative-threshold rule of MSDsort.c:330-352
+    (Appendix C of SURVEY.md), here checked against a direct restatement on the first-byte histogram."""
+    rng = np.random.default_rng(4)
+    tw = 12
+    for nparts in (1, 2, 4, 7):
+        first = np.sort((rng.random(5000) ** 2 * 256).astype(np.uint8))       # skewed like canonical k-mers
+        ent = np.zeros((len(first), tw), np.uint8)
+        ent[:, 0] = first
+        beg = (C.c_int * (nparts + 1))()
+        fkfiles.fk_table_split(ent.ctypes.data_as(C.POINTER(C.c_uint8)), len(ent), tw, nparts, beg)
+        part = np.bincount(first, minlength=256).astype(np.int64) * tw
+        asize, n, s, b, want = int(part.sum()), 0, 0, 0, []
+        thr = asize // nparts
+        for x in range(256):
+            s += int(part[x])
+            if s >= thr and n < nparts:
+                want.append(b)
+                n += 1
+                thr = asize * (n + 1) // nparts
+                b = x + 1
+        while len(want) < nparts:
+            want.append(256)
+        want.append(256)
+        got = list(beg)
+        assert got[0] == 0 and got[-1] == 256 and all(got[i] <= got[i + 1] for i in range(nparts)), got
+        assert got == want, (nparts, got, want)
