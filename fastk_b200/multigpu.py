@@ -179,8 +179,6 @@ class MultiGPUCounter:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()):
                 self.peer_seq = peers
-                if os.environ.get("FKGPU_DIAG_LOCALSEQ"):      # timing diagnostic only (wrong counts): every gather stays local
-                    self.peer_seq = [seq] * self.world
             else:
                 self.close_peers()
         return seq, val
