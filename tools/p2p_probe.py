@@ -1,5 +1,6 @@
 """Diagnostic (torchrun): random 8-byte reads out of every peer's IPC-mapped buffer, one peer at a time and all at once."""
 import os, sys, time
+os.environ["FKGPU_MG"] = "peer"          # map every peer's buffer (CUDA IPC) whatever the world size
 import torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
