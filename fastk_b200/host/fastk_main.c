@@ -132,31 +132,48 @@ typedef struct
   } Parser;
 enum { QAT, HSKP, QSEQ, QPLS, QSKP, AEOL, ASEQ };
 
-static inline void seq_add(Parser *P, char c)
-{ if (P->slen >= P->smax)
-    { P->smax = 2*P->smax + 65536;
+static inline void seq_append(Parser *P, const char *s, int64_t n)
+{ if (P->slen + n > P->smax)
+    { P->smax = 2*(P->slen + n) + 65536;
       P->seq = (char *) realloc(P->seq,P->smax);
     }
-  P->seq[P->slen++] = c;
+  memcpy(P->seq + P->slen,s,(size_t) n);
+  P->slen += n;
 }
 
+/* Same transitions as the byte-at-a-time automaton of io.c:678-734, taken a line segment at a time: header and
+   quality lines are skipped with memchr, sequence lines are appended with one memcpy each.                      */
 static void parse_bytes(Reader *R, Block *B, Parser *P, const char *buf, int64_t n)
-{ int64_t b;
-  for (b = 0; b < n; b++)
-    { char c = buf[b];
-      switch (P->state)
-      { case QAT:  P->state = HSKP; break;
-        case HSKP: if (c == '\n') P->state = P->fastq ? QSEQ : ASEQ; break;
-        case QSEQ: if (c != '\n') seq_add(P,c);
-                   else { block_add(R,B,P->seq,P->slen); P->slen = 0; P->state = QPLS; }
-                   break;
-        case QPLS: if (c == '\n') P->state = QSKP; break;
-        case QSKP: if (c == '\n') P->state = QAT; break;
-        case AEOL: if (c == '>') { block_add(R,B,P->seq,P->slen); P->slen = 0; P->state = HSKP; }
-                   else if (c != '\n') { seq_add(P,c); P->state = ASEQ; }
-                   break;
-        case ASEQ: if (c == '\n') P->state = AEOL; else seq_add(P,c); break;
-      }
+{ const char *p = buf, *e = buf + n, *q;
+  while (p < e)
+    switch (P->state)
+    { case QAT:  P->state = HSKP; p++; break;                      /* the '@' / '>' that opens a record */
+      case HSKP: q = (const char *) memchr(p,'\n',(size_t) (e-p));
+                 if (q == NULL) { p = e; break; }
+                 P->state = P->fastq ? QSEQ : ASEQ; p = q+1;
+                 break;
+      case QSEQ: q = (const char *) memchr(p,'\n',(size_t) (e-p));
+                 seq_append(P,p,(q ? q : e) - p);
+                 if (q == NULL) { p = e; break; }
+                 block_add(R,B,P->seq,P->slen); P->slen = 0; P->state = QPLS; p = q+1;
+                 break;
+      case QPLS: q = (const char *) memchr(p,'\n',(size_t) (e-p));
+                 if (q == NULL) { p = e; break; }
+                 P->state = QSKP; p = q+1;
+                 break;
+      case QSKP: q = (const char *) memchr(p,'\n',(size_t) (e-p));
+                 if (q == NULL) { p = e; break; }
+                 P->state = QAT; p = q+1;
+                 break;
+      case AEOL: if (*p == '>') { block_add(R,B,P->seq,P->slen); P->slen = 0; P->state = HSKP; p++; }
+                 else if (*p == '\n') p++;
+                 else P->state = ASEQ;                              /* first base of the next sequence line: ASEQ takes it */
+                 break;
+      case ASEQ: q = (const char *) memchr(p,'\n',(size_t) (e-p));
+                 seq_append(P,p,(q ? q : e) - p);
+                 if (q == NULL) { p = e; break; }
+                 P->state = AEOL; p = q+1;
+                 break;
     }
 }
 
