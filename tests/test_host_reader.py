@@ -99,3 +99,38 @@ def test_long_reads_arrive_in_overlapping_pieces(stub_cli, tmp_path):
         assert [len(r) for r in got] == [len(r) for r in reads]
         assert got == reads                                      # the stub stitched the pieces on their k-1 overlap
         assert all(m[b"maxblock"] <= 1_000_000 for m in meta)
+
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def refhost_stub(tmp_path_factory):
+    """The REFERENCE's own driver + io.c + table.c + libfastk.c (compiled where they lie) with fastk_shim.c, linked
+    against the recording stand-in: what the reference's input module hands to Distribute_Block, without a GPU."""
+    if not os.path.exists(os.path.join(REF, "FastK.c")):
+        pytest.skip("needs the reference sources")
+    d = str(tmp_path_factory.mktemp("refstub"))
+    exe = os.path.join(d, "FastK_refhost_stub")
+    srcs = [os.path.join(REF, f) for f in ("FastK.c", "io.c", "table.c", "libfastk.c")]
+    subprocess.check_call(["gcc", "-O2", "-w", "-I" + REF, "-I" + os.path.join(REF, "HTSLIB"), "-I" + os.path.join(ROOT, "include"),
+                           "-I" + HOST, "-o", exe] + srcs +
+                          [os.path.join(HOST, "fastk_shim.c"), os.path.join(HOST, "fk_files.c"),
+                           os.path.join(ROOT, "oracle", "ref_thirdparty_stubs.c"),
+                           os.path.join(ROOT, "tests", "hoststub", "fkgpu_stub.c"), "-lpthread", "-lz", "-lm"])
+    return exe
+
+
+def test_reference_io_module_through_the_shim(refhost_stub, tmp_path):
+    """io.c's own blocks (ITHREADS producers, long reads cut with rem > 0 and the k-1 overlap, io.c:296-333) forwarded
+    by fastk_shim.c's Distribute_Block: the stand-in must receive exactly the reads of the file."""
+    reads = make_reads(3, 2_300_000, 31, n_rate=0.0) + make_reads(6000, 400, 37, jitter=300)
+    src = os.path.join(str(tmp_path), "mix.fasta")
+    synth.write_fasta(reads, src, width=100)
+    out = os.path.join(str(tmp_path), "delivered.txt")
+    r = subprocess.run([refhost_stub, "-k40", "-T4", "-P" + str(tmp_path), "-N" + os.path.join(str(tmp_path), "o"), src],
+                       capture_output=True, text=True, env=dict(os.environ, FKSTUB_OUT=out))
+    assert r.returncode == 0, r.stderr
+    got = [ln for ln in open(out, "rb").read().split(b"\n")[:-1] if not ln.startswith(b"#tid")]
+    assert sorted(len(x) for x in got) == sorted(len(x) for x in reads)
+    assert got == reads
