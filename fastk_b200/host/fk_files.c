@@ -5,6 +5,7 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/stat.h>
+#include <pthread.h>
 #include "fk_files.h"
 
 static int put(int f, const void *buf, int64_t n)
@@ -23,17 +24,25 @@ int fk_idx_bytes(int64_t nentries, int kmer)
   return 1;
 }
 
+/* index of the first entry whose first key byte is >= x (entries are sorted) */
+static int64_t first_byte_lower_bound(const uint8_t *entries, int64_t n, int tw, int x)
+{ int64_t lo = 0, hi = n;
+  while (lo < hi)
+    { int64_t mid = (lo+hi) >> 1;
+      if (entries[mid*tw] < x) lo = mid+1; else hi = mid;
+    }
+  return lo;
+}
+
 void fk_table_split(const uint8_t *entries, int64_t n, int tw, int nparts, int *beg)
-{ int64_t part[256], asize = 0, sum = 0, thr, i;
+{ int64_t asize = n * tw, sum = 0, thr, prev = 0;
   int     x, m = 0;
-  memset(part,0,sizeof(part));
-  for (i = 0; i < n; i++)
-    part[entries[i*tw]] += tw;
-  asize = n * tw;
   thr = asize / nparts;
   beg[0] = 0;
   for (x = 0; x < 256; x++)
-    { sum += part[x];
+    { int64_t next = first_byte_lower_bound(entries,n,tw,x+1);       /* part[x] = (next - prev) * tw */
+      sum += (next - prev) * tw;
+      prev = next;
       if (sum >= thr && m < nparts)
         { beg[++m] = x+1;
           thr = (asize * (m+1)) / nparts;
@@ -59,42 +68,69 @@ int fk_write_hist(const char *dir, const char *root, int kmer, const int64_t *hi
   return bad;
 }
 
+/* one hidden table part per thread: parts are separate files, and because they are cut on first-byte boundaries no
+   prefix-index slot is shared between two parts (table.c:257 relies on the same fact)                              */
+typedef struct
+  { const char *dir, *root; const uint8_t *entries;
+    int64_t i, j; int64_t *pindex;
+    int kmer, tw, ib, t, bad;
+  } Ktab_Job;
+
+static void *ktab_part_thread(void *arg)
+{ Ktab_Job *J = (Ktab_Job *) arg;
+  const int pw = J->tw - J->ib;
+  const size_t cap = 1 << 22;
+  size_t   fill = 0;
+  uint8_t *buf = (uint8_t *) malloc(cap + 64);
+  char     name[4096];
+  int64_t  i, m = J->j - J->i;
+  int      f;
+  snprintf(name,sizeof(name),"%s/.%s.ktab.%d",J->dir,J->root,J->t+1);
+  f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0700);
+  if (f < 0 || buf == NULL) { J->bad = 1; free(buf); if (f >= 0) close(f); return NULL; }
+  J->bad |= put(f,&J->kmer,sizeof(int));
+  J->bad |= put(f,&m,sizeof(int64_t));
+  for (i = J->i; i < J->j; i++)
+    { const uint8_t *e = J->entries + i*J->tw;
+      int64_t idx = 0;
+      int b;
+      for (b = 0; b < J->ib; b++) idx = (idx << 8) | e[b];
+      J->pindex[idx] += 1;
+      memcpy(buf+fill,e+J->ib,pw);
+      fill += pw;
+      if (fill + pw > cap) { J->bad |= put(f,buf,fill); fill = 0; }
+    }
+  J->bad |= put(f,buf,fill);
+  free(buf);
+  close(f);
+  return NULL;
+}
+
 int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int nparts, const uint8_t *entries, int64_t n)
 { const int kb = (2*kmer+7) >> 3, tw = kb+2;
-  const int ib = fk_idx_bytes(n,kmer), pw = tw-ib;
+  const int ib = fk_idx_bytes(n,kmer);
   const int64_t ilen = 1ll << (8*ib);
-  int64_t *pindex = (int64_t *) calloc((size_t) ilen,sizeof(int64_t));
-  int     *beg = (int *) malloc(sizeof(int)*(nparts+1));
+  int64_t  *pindex = (int64_t *) calloc((size_t) ilen,sizeof(int64_t));
+  int      *beg = (int *) malloc(sizeof(int)*(nparts+1));
+  Ktab_Job *job = (Ktab_Job *) calloc((size_t) nparts,sizeof(Ktab_Job));
+  pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t)*(size_t) nparts);
   char     name[4096];
-  int64_t  i = 0, x;
+  int64_t  x;
   int      f, t, bad = 0;
 
-  if (pindex == NULL || beg == NULL) { free(pindex); free(beg); return 1; }
+  if (pindex == NULL || beg == NULL || job == NULL || th == NULL) { free(pindex); free(beg); free(job); free(th); return 1; }
   fk_table_split(entries,n,tw,nparts,beg);
-  for (t = 0; t < nparts && !bad; t++)
-    { int64_t j = i, m;
-      size_t  cap = 1 << 22, fill = 0;
-      uint8_t *buf = (uint8_t *) malloc(cap + 64);
-      while (j < n && entries[j*tw] < beg[t+1]) j++;
-      m = j-i;
-      snprintf(name,sizeof(name),"%s/.%s.ktab.%d",dir,root,t+1);
-      f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0700);
-      if (f < 0 || buf == NULL) { bad = 1; free(buf); break; }
-      bad |= put(f,&kmer,sizeof(int));
-      bad |= put(f,&m,sizeof(int64_t));
-      for ( ; i < j; i++)
-        { const uint8_t *e = entries + i*tw;
-          int64_t idx = 0;
-          int b;
-          for (b = 0; b < ib; b++) idx = (idx << 8) | e[b];
-          pindex[idx] += 1;
-          memcpy(buf+fill,e+ib,pw);
-          fill += pw;
-          if (fill + pw > cap) { bad |= put(f,buf,fill); fill = 0; }
-        }
-      bad |= put(f,buf,fill);
-      free(buf);
-      close(f);
+  for (t = 0; t < nparts; t++)
+    { Ktab_Job *J = job+t;
+      J->dir = dir; J->root = root; J->entries = entries; J->pindex = pindex;
+      J->kmer = kmer; J->tw = tw; J->ib = ib; J->t = t; J->bad = 0;
+      J->i = first_byte_lower_bound(entries,n,tw,beg[t]);
+      J->j = first_byte_lower_bound(entries,n,tw,beg[t+1]);
+      if (pthread_create(th+t,NULL,ktab_part_thread,J) != 0) { ktab_part_thread(J); th[t] = 0; J->t = -1; }
+    }
+  for (t = 0; t < nparts; t++)
+    { if (job[t].t >= 0) pthread_join(th[t],NULL);
+      bad |= job[t].bad;
     }
   for (x = 1; x < ilen; x++) pindex[x] += pindex[x-1];
   snprintf(name,sizeof(name),"%s/%s.ktab",dir,root);
@@ -108,7 +144,7 @@ int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int n
       bad |= put(f,pindex,sizeof(int64_t)*ilen);
       close(f);
     }
-  free(pindex); free(beg);
+  free(pindex); free(beg); free(job); free(th);
   return bad;
 }
 
@@ -137,50 +173,77 @@ int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out)
   return (int64_t) (o-out);
 }
 
+typedef struct
+  { const char *dir, *root; const int64_t *off; const uint16_t *prof;
+    int64_t first, n; int kmer, t, bad;
+  } Prof_Job;
+
+static void *prof_part_thread(void *arg)
+{ Prof_Job *J = (Prof_Job *) arg;
+  const int64_t first = J->first, n = J->n;
+  const int64_t *off = J->off;
+  char     name[4096];
+  int64_t  r, len = 0, maxp = 1;
+  int64_t *idx = (int64_t *) malloc(sizeof(int64_t)*(size_t) (n > 0 ? n : 1));
+  uint8_t *code;
+  size_t   cap = 1 << 22, fill = 0;
+  uint8_t *buf = (uint8_t *) malloc(cap);
+  int      f, g;
+  for (r = first; r < first+n; r++)
+    if (off[r+1]-off[r] > maxp) maxp = off[r+1]-off[r];
+  code = (uint8_t *) malloc((size_t) (2*maxp+4));
+  snprintf(name,sizeof(name),"%s/.%s.prof.%d",J->dir,J->root,J->t+1);
+  g = open(name,O_WRONLY|O_CREAT|O_TRUNC,0755);
+  if (g < 0 || idx == NULL || code == NULL || buf == NULL)
+    { J->bad = 1; free(idx); free(code); free(buf); if (g >= 0) close(g); return NULL; }
+  for (r = first; r < first+n; r++)
+    { int64_t nb = fk_encode_profile(J->prof+off[r],off[r+1]-off[r],code);
+      if (fill + (size_t) nb > cap) { J->bad |= put(g,buf,fill); fill = 0; }
+      if ((size_t) nb > cap) J->bad |= put(g,code,nb);
+      else { memcpy(buf+fill,code,(size_t) nb); fill += nb; }
+      len += nb;
+      idx[r-first] = len;
+    }
+  J->bad |= put(g,buf,fill);
+  close(g);
+  snprintf(name,sizeof(name),"%s/.%s.pidx.%d",J->dir,J->root,J->t+1);
+  f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0755);
+  if (f < 0) J->bad = 1;
+  else
+    { J->bad |= put(f,&J->kmer,sizeof(int));
+      J->bad |= put(f,&first,sizeof(int64_t));
+      J->bad |= put(f,&n,sizeof(int64_t));
+      J->bad |= put(f,idx,sizeof(int64_t)*n);
+      close(f);
+    }
+  free(idx); free(code); free(buf);
+  return NULL;
+}
+
 int fk_write_prof(const char *dir, const char *root, int kmer, int nparts, const int64_t *rbeg,
                   const int64_t *off, const uint16_t *prof)
 { char name[4096];
-  int  f, g, t, bad = 0;
+  int  f, t, bad = 0;
+  Prof_Job  *job = (Prof_Job *) calloc((size_t) (nparts > 0 ? nparts : 1),sizeof(Prof_Job));
+  pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t)*(size_t) (nparts > 0 ? nparts : 1));
+  if (job == NULL || th == NULL) { free(job); free(th); return 1; }
   snprintf(name,sizeof(name),"%s/%s.prof",dir,root);
   f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0755);
-  if (f < 0) return 1;
+  if (f < 0) { free(job); free(th); return 1; }
   bad |= put(f,&kmer,sizeof(int));
   bad |= put(f,&nparts,sizeof(int));
   close(f);
-  for (t = 0; t < nparts && !bad; t++)
-    { int64_t r, first = rbeg[t], n = rbeg[t+1]-rbeg[t], len = 0, maxp = 1;
-      int64_t *idx = (int64_t *) malloc(sizeof(int64_t)*(size_t) (n > 0 ? n : 1));
-      uint8_t *code;
-      size_t   cap = 1 << 22, fill = 0;
-      uint8_t *buf = (uint8_t *) malloc(cap);
-      for (r = first; r < first+n; r++)
-        if (off[r+1]-off[r] > maxp) maxp = off[r+1]-off[r];
-      code = (uint8_t *) malloc((size_t) (2*maxp+4));
-      snprintf(name,sizeof(name),"%s/.%s.prof.%d",dir,root,t+1);
-      g = open(name,O_WRONLY|O_CREAT|O_TRUNC,0755);
-      if (g < 0 || idx == NULL || code == NULL || buf == NULL) { bad = 1; free(idx); free(code); free(buf); break; }
-      for (r = first; r < first+n; r++)
-        { int64_t nb = fk_encode_profile(prof+off[r],off[r+1]-off[r],code);
-          if (fill + (size_t) nb > cap) { bad |= put(g,buf,fill); fill = 0; }
-          if ((size_t) nb > cap) bad |= put(g,code,nb);
-          else { memcpy(buf+fill,code,(size_t) nb); fill += nb; }
-          len += nb;
-          idx[r-first] = len;
-        }
-      bad |= put(g,buf,fill);
-      close(g);
-      snprintf(name,sizeof(name),"%s/.%s.pidx.%d",dir,root,t+1);
-      f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0755);
-      if (f < 0) bad = 1;
-      else
-        { bad |= put(f,&kmer,sizeof(int));
-          bad |= put(f,&first,sizeof(int64_t));
-          bad |= put(f,&n,sizeof(int64_t));
-          bad |= put(f,idx,sizeof(int64_t)*n);
-          close(f);
-        }
-      free(idx); free(code); free(buf);
+  for (t = 0; t < nparts; t++)               /* the parts are separate files: one encoder thread each */
+    { Prof_Job *J = job+t;
+      J->dir = dir; J->root = root; J->off = off; J->prof = prof; J->kmer = kmer; J->t = t; J->bad = 0;
+      J->first = rbeg[t]; J->n = rbeg[t+1]-rbeg[t];
+      if (pthread_create(th+t,NULL,prof_part_thread,J) != 0) { prof_part_thread(J); J->t = -1; }
     }
+  for (t = 0; t < nparts; t++)
+    { if (job[t].t >= 0) pthread_join(th[t],NULL);
+      bad |= job[t].bad;
+    }
+  free(job); free(th);
   return bad;
 }
 

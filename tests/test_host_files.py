@@ -16,7 +16,7 @@ ROOT = util.ROOT
 def fkfiles(tmp_path_factory):
     d = tmp_path_factory.mktemp("fkfiles")
     so = os.path.join(str(d), "libfkfiles.so")
-    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "fastk_b200", "host", "fk_files.c")])
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "fastk_b200", "host", "fk_files.c"), "-lpthread"])
     L = C.CDLL(so)
     L.fk_write_hist.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int64]
     L.fk_write_ktab.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int64]
