@@ -136,6 +136,7 @@ static inline void seq_append(Parser *P, const char *s, int64_t n)
 { if (P->slen + n > P->smax)
     { P->smax = 2*(P->slen + n) + 65536;
       P->seq = (char *) realloc(P->seq,P->smax);
+      if (P->seq == NULL) { fprintf(stderr,"%s: Out of memory (sequence buffer of %lld bytes)\n",Prog_Name,(long long) P->smax); exit(1); }
     }
   memcpy(P->seq + P->slen,s,(size_t) n);
   P->slen += n;

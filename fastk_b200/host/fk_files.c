@@ -6,6 +6,7 @@
 #include <unistd.h>
 #include <sys/stat.h>
 #include <pthread.h>
+#include <dirent.h>
 #include "fk_files.h"
 
 static int put(int f, const void *buf, int64_t n)
@@ -248,8 +249,28 @@ int fk_write_prof(const char *dir, const char *root, int kmer, int nparts, const
 }
 
 void fk_remove_outputs(const char *dir, const char *root)
-{ char cmd[8300];
-  snprintf(cmd,sizeof(cmd),"rm -f %s/%s.hist %s/%s.ktab %s/.%s.ktab.* %s/%s.prof %s/.%s.pidx.* %s/.%s.prof.*",
-           dir,root,dir,root,dir,root,dir,root,dir,root,dir,root);
-  if (system(cmd)) {}
+{ /* <root>.hist / .ktab / .prof and the hidden parts .<root>.ktab.<n> / .pidx.<n> / .prof.<n>; no shell involved */
+  static const char *plain[] = { "hist", "ktab", "prof", NULL };
+  static const char *hidden[] = { "ktab", "pidx", "prof", NULL };
+  char   name[4200], pre[4200];
+  DIR   *d;
+  struct dirent *e;
+  int    i;
+  for (i = 0; plain[i]; i++)
+    { snprintf(name,sizeof(name),"%s/%s.%s",dir,root,plain[i]);
+      unlink(name);
+    }
+  d = opendir(dir);
+  if (d == NULL) return;
+  while ((e = readdir(d)) != NULL)
+    for (i = 0; hidden[i]; i++)
+      { size_t L;
+        snprintf(pre,sizeof(pre),".%s.%s.",root,hidden[i]);
+        L = strlen(pre);
+        if (strncmp(e->d_name,pre,L) == 0 && e->d_name[L] != '\0' && strspn(e->d_name+L,"0123456789") == strlen(e->d_name+L))
+          { snprintf(name,sizeof(name),"%s/%s",dir,e->d_name);
+            unlink(name);
+          }
+      }
+  closedir(d);
 }

@@ -125,3 +125,17 @@ def test_table_split_rule(fkfiles):
         got = list(beg)
         assert got[0] == 0 and got[-1] == 256 and all(got[i] <= got[i + 1] for i in range(nparts)), got
         assert got == want, (nparts, got, want)
+
+
+def test_remove_outputs_only_touches_its_own_files(fkfiles, tmp_path):
+    """Clean_Exit's removal of partial outputs (FastK.c:181-221): exactly <root>.{hist,ktab,prof} and the numbered
+    hidden parts, whatever characters the directory name holds."""
+    d = os.path.join(str(tmp_path), "dir with space;echo")
+    os.makedirs(d)
+    mine = ["r.hist", "r.ktab", "r.prof", ".r.ktab.1", ".r.ktab.12", ".r.pidx.3", ".r.prof.3"]
+    other = ["r.histx", "rr.hist", ".r.ktab.x", ".r.ktab.", ".rr.ktab.1", "keep.txt", ".r.prof.3a"]
+    for f in mine + other:
+        open(os.path.join(d, f), "w").write("x")
+    fkfiles.fk_remove_outputs.argtypes = [C.c_char_p, C.c_char_p]
+    fkfiles.fk_remove_outputs(d.encode(), b"r")
+    assert sorted(os.listdir(d)) == sorted(other)
