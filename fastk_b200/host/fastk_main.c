@@ -372,8 +372,8 @@ int main(int argc, char *argv[])
       anyzip |= F[i].zipd;
     }
   { char *src = strdup(OUT_NAME ? OUT_NAME : F[0].path), *s2 = strdup(src);
-    strcpy(OUT_DIR,dirname(src));
-    strcpy(OUT_ROOT,basename(s2));
+    snprintf(OUT_DIR,sizeof(OUT_DIR),"%s",dirname(src));
+    snprintf(OUT_ROOT,sizeof(OUT_ROOT),"%s",basename(s2));
     if (!OUT_NAME) strip_suffix(OUT_ROOT);
     free(src); free(s2);
   }
