@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- Gbases/sec counted (k=40) on B200, the BASELINE.json metric.
+"""bench.py -- Gbases/sec counted on B200, the BASELINE.json metric.
 
-One "step" = one pass of the whole counting hot path (encode+canonicalise -> prefix split -> MSD refine ->
-in-smem sort/count -> histogram -> table) over one batch of synthetic HiFi-like reads.
+One "step" = one pass of the whole counting hot path (encode + canonicalise -> minimizer super-mers -> bucket
+partition -> on-chip count -> key-order sort of the distinct entries -> histogram + table) over one batch of
+synthetic reads of the shape BASELINE.json names (`--config`, 1-based index into its `configs`: 2 = HiFi-like k=40 -t1
+(default, the configuration the metric is quoted on), 3 = Illumina-like k=21 -t4, 4 = k=40 -t1 -p, 5 = k=63 -t1).
 
-  value   device-resident: packed reads already in HBM when the timed region starts, results left in HBM
-  e2e     the same batch through the reference-facing C ABI with HOST buffers: fkgpu_ingest of DATA_BLOCKs from
-          pinned host memory (one ingest thread per host core up to 16, like io.c's ITHREADS), H2D, count, D2H of the table + histogram
-  roofline  dominant kernel (k_bucket_count on the super-mer path): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
-  cpu_baseline  the reference FastK (oracle/_ref, built from the reference's own sources) on a bounded sample
+  value   packed reads already resident in HBM when the timed region starts; it ends with the sorted [key][count] runs
+          and the histogram resident in PINNED HOST memory
+  e2e     the same batch through the reference-facing C ABI with HOST buffers: fkgpu_ingest of DATA_BLOCKs from pinned
+          host memory (one ingest thread per host core up to 16, like io.c's ITHREADS), H2D, count, D2H
+  parity  outside the timed region, at every N: the GPU result for the reads of the reference arm's FASTA is compared
+          byte for byte (every .hist bin, max_inst, the .ktab prefix index and every suffix + count byte) with the files
+          the reference FastK (oracle/_ref) writes for that FASTA; a mismatch exits non-zero
+  roofline  dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+  cpu_baseline  that same reference run, timed (N=1): the same reads, the same box
 
-`--impl reference` times only that CPU reference arm.  Under torchrun (N>1) every rank owns 1/N of the reads
-and the canonical-prefix ranges are exchanged with one NCCL all-to-all (fastk_b200/multigpu.py).
+`--impl reference` times only the CPU reference arm on the same FASTA.  Under torchrun (N>1) every rank owns its own
+reads of the same shape (weak scaling) and minimizer buckets / key ranges are exchanged over NCCL (fastk_b200/multigpu.py).
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -25,6 +32,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONFIGS = {
+    2: dict(name="configs[1]", desc="synthetic HiFi-like", read_len=15000, coverage=50.0, genome_mbp=40.0, sub_rate=0.001,
+            kmer=40, cutoff=1, profile=False),
+    3: dict(name="configs[2]", desc="synthetic Illumina-like", read_len=150, coverage=50.0, genome_mbp=40.0, sub_rate=0.002,
+            kmer=21, cutoff=4, profile=False),
+    4: dict(name="configs[3]", desc="synthetic HiFi-like", read_len=15000, coverage=50.0, genome_mbp=40.0, sub_rate=0.001,
+            kmer=40, cutoff=1, profile=True),
+    5: dict(name="configs[4]", desc="synthetic HiFi-like", read_len=15000, coverage=100.0, genome_mbp=20.0, sub_rate=0.001,
+            kmer=63, cutoff=1, profile=False),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -32,46 +50,39 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("-k", "--kmer", type=int, default=40)
-    ap.add_argument("--genome-mbp", type=float, default=40.0, help="random genome size per GPU (Mbp)")
-    ap.add_argument("--coverage", type=float, default=50.0)
-    ap.add_argument("--read-len", type=int, default=15000)
-    ap.add_argument("--sub-rate", type=float, default=0.001)
-    ap.add_argument("--cutoff", type=int, default=1, help="-t<cutoff>")
-    ap.add_argument("--cpu-sample-gbases", type=float, default=0.45)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="1-based index into BASELINE.json configs")
+    ap.add_argument("-k", "--kmer", type=int, default=None)
+    ap.add_argument("--genome-mbp", type=float, default=None, help="random genome size per GPU (Mbp)")
+    ap.add_argument("--coverage", type=float, default=None)
+    ap.add_argument("--read-len", type=int, default=None)
+    ap.add_argument("--sub-rate", type=float, default=None)
+    ap.add_argument("--cutoff", type=int, default=None, help="-t<cutoff>")
     ap.add_argument("--ingest-threads", type=int, default=0, help="e2e arm: ingest threads (0 = host cores, at most 16)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the reference run: no cpu_baseline and NO parity check")
     ap.add_argument("--seed", type=int, default=1234)
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    for key in ("kmer", "genome_mbp", "coverage", "read_len", "sub_rate", "cutoff"):
+        if getattr(a, key) is None:
+            setattr(a, key, cfg[key])
+    a.profile = cfg["profile"]
+    a.cfg_name, a.cfg_desc = cfg["name"], cfg["desc"]
+    a.nreads = max(1, int(a.genome_mbp * 1e6 * a.coverage / a.read_len))
+    a.genome_bp = max(int(a.genome_mbp * 1e6), 2 * a.read_len)
+    return a
 
 
-# ----------------------------------------------------------------------------------------------------------
-# synthetic reads (same model as fastk_b200/synth.py, generated on the device for the big batch)
+def workload_name(a):
+    return (f"{a.cfg_name} scaled to one in-HBM batch per GPU: {a.cfg_desc} {a.read_len} bp reads, "
+            f"{a.coverage:g}x of a {a.genome_bp/1e6:g} Mbp random genome ({a.nreads * a.read_len / 1e9:.2f} Gbases/GPU), "
+            f"{a.sub_rate*100:g}% subs, FastK -k{a.kmer} -t{a.cutoff}" + (" -p" if a.profile else ""))
 
-def gen_reads_ascii(torch, dev, genome_bp, nreads, read_len, sub_rate, seed):
-    """-> uint8 tensor [nreads, read_len+1] of ASCII reads, each row 0-terminated (DATA_BLOCK layout)."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    genome = torch.randint(0, 4, (genome_bp,), dtype=torch.uint8, device=dev, generator=g)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    out = torch.zeros((nreads, read_len + 1), dtype=torch.uint8, device=dev)
-    ar = torch.arange(read_len, device=dev)
-    chunk = max(1, (64 << 20) // read_len)
-    for r0 in range(0, nreads, chunk):
-        r1 = min(nreads, r0 + chunk)
-        n = r1 - r0
-        st = torch.randint(0, genome_bp - read_len + 1, (n,), device=dev, generator=g)
-        r = genome[(st[:, None] + ar[None, :])]
-        if sub_rate > 0:
-            m = torch.rand((n, read_len), device=dev, generator=g) < sub_rate
-            add = torch.randint(1, 4, (n, read_len), dtype=torch.uint8, device=dev, generator=g)
-            r = torch.where(m, (r + add) % 4, r)
-        flip = torch.rand((n,), device=dev, generator=g) < 0.5
-        rc = (3 - r).flip(1)
-        r = torch.where(flip[:, None], rc, r)
-        out[r0:r1, :read_len] = lut[r.long()]
-    return out
+
+def make_rows(a, rank, out=None):
+    """the reads of rank `rank`: the ONE generator both arms and the parity check use (fastk_b200/synth.py)"""
+    from fastk_b200 import synth
+    return synth.workload_rows(a.genome_bp, a.nreads, a.read_len, a.sub_rate, a.seed + 7919 * rank, out=out)
 
 
 class ClockSampler:
@@ -123,103 +134,103 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU reference arm
+# CPU reference arm: oracle/_ref/FastK (the reference's own sources, compiled by oracle/Makefile) on the FASTA of rank 0's reads
 
 def ref_binary():
     p = os.path.join(ROOT, "oracle", "_ref", "FastK")
     return p if os.path.exists(p) else None
 
 
-def write_sample_fasta(args, path, gbases):
-    """Bounded sample of the same workload for the CPU arms (numpy, same read model)."""
-    import numpy as np
-    from fastk_b200 import synth
-    nreads = max(1, int(gbases * 1e9 / args.read_len))
-    gsize = max(args.read_len * 2, int(nreads * args.read_len / args.coverage))
-    rng = np.random.default_rng(args.seed)
-    genome = rng.integers(0, 4, gsize, dtype=np.uint8)
-    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    with open(path, "wb") as f:
-        for i in range(nreads):
-            s = int(rng.integers(0, gsize - args.read_len + 1))
-            r = genome[s:s + args.read_len].copy()
-            m = rng.random(args.read_len) < args.sub_rate
-            r[m] = (r[m] + rng.integers(1, 4, int(m.sum()))) % 4
-            if rng.random() < 0.5:
-                r = (3 - r)[::-1]
-            f.write(b">r%d\n" % i + lut[r].tobytes() + b"\n")
-    return nreads * args.read_len, nreads, gsize
+def scratch_dir(prefix):
+    return tempfile.mkdtemp(prefix=prefix, dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
 
 
-def run_reference_once(args, fasta, tmpdir, cores):
+def run_reference_once(a, fasta, tmpdir, cores):
+    """-> (seconds, kind, cores used); leaves <tmpdir>/cpu_out.{hist,ktab} (+ hidden parts) behind"""
     exe = ref_binary()
+    out = os.path.join(tmpdir, "cpu_out")
     t0 = time.perf_counter()
     if exe is not None:
         kind = "reference"
-        cmd = [exe, f"-k{args.kmer}", f"-t{args.cutoff}", f"-T{cores}", "-M16", f"-P{tmpdir}",
-               f"-N{os.path.join(tmpdir, 'cpu_out')}", fasta]
-        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        cmd = [exe, f"-k{a.kmer}", f"-t{a.cutoff}", f"-T{cores}", "-M16", f"-P{tmpdir}", f"-N{out}"]
+        if a.profile:
+            cmd.append("-p")
+        subprocess.check_call(cmd + [fasta], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     else:
         kind = "port"
         cores = 1
         exe = os.path.join(ROOT, "oracle", "fastk_oracle")
-        subprocess.check_call([exe, f"-k{args.kmer}", f"-t{args.cutoff}", f"-N{os.path.join(tmpdir, 'cpu_out')}", fasta],
+        subprocess.check_call([exe, f"-k{a.kmer}", f"-t{a.cutoff}", f"-N{out}", fasta],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return time.perf_counter() - t0, kind, cores
 
 
-def workload_name(args, per_gpu_gbases):
-    return (f"config[1] scaled to one in-HBM batch per GPU: synthetic HiFi-like {args.read_len} bp reads, "
-            f"{args.coverage:g}x of a {args.genome_mbp:g} Mbp random genome ({per_gpu_gbases:.2f} Gbases/GPU), "
-            f"{args.sub_rate*100:g}% subs, FastK -k{args.kmer} -t{args.cutoff}")
+def sample_text(a, cores, extra=""):
+    return (f"{a.nreads} reads x {a.read_len} bp = {a.nreads * a.read_len / 1e9:.3f} Gbases ({a.coverage:g}x of "
+            f"{a.genome_bp/1e6:.1f} Mbp): the FASTA of rank 0's reads (the whole workload at N=1), on tmpfs, "
+            f"FastK -k{a.kmer} -t{a.cutoff}{' -p' if a.profile else ''} -T{cores} -M16{extra}")
 
 
-def reference_arm(args, rank):
+def reference_arm(a, rank):
     if rank != 0:
         return
+    from fastk_b200 import synth
     cores = os.cpu_count() or 1
-    tmpdir = tempfile.mkdtemp(prefix="fastk_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    fasta = os.path.join(tmpdir, "sample.fasta")
-    nb, nreads, gsize = write_sample_fasta(args, fasta, args.cpu_sample_gbases)
-    for _ in range(args.warmup):
-        run_reference_once(args, fasta, tmpdir, cores)
-    ts = []
-    kind = "reference"
-    for _ in range(args.steps):
-        t, kind, used = run_reference_once(args, fasta, tmpdir, cores)
-        ts.append(t)
-    subprocess.call(["rm", "-rf", tmpdir])
+    tmpdir = scratch_dir("fastk_ref_")
+    try:
+        fasta = os.path.join(tmpdir, "reads.fasta")
+        nb = synth.write_rows_fasta(make_rows(a, 0), fasta)
+        for _ in range(a.warmup):
+            run_reference_once(a, fasta, tmpdir, cores)
+        ts, kind, used = [], "reference", cores
+        for _ in range(a.steps):
+            t, kind, used = run_reference_once(a, fasta, tmpdir, cores)
+            ts.append(t)
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
     tot = sum(ts)
-    val = nb * args.steps / tot / 1e9
-    per_gpu = args.genome_mbp * args.coverage / 1e3
-    line = {"impl": "reference", "metric": "Gbases/sec counted (k=%d)" % args.kmer, "value": val, "unit": "Gbases/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+    val = nb * a.steps / tot / 1e9
+    line = {"impl": "reference", "metric": "Gbases/sec counted (k=%d)" % a.kmer, "value": val, "unit": "Gbases/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args, per_gpu)},
+            "config": {"workload": workload_name(a)},
             "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": used, "kind": kind,
-                             "sample": f"{nreads} reads x {args.read_len} bp = {nb/1e9:.3f} Gbases "
-                                       f"({args.coverage:g}x of {gsize/1e6:.1f} Mbp) per step, FASTA on tmpfs, "
-                                       f"FastK -k{args.kmer} -t{args.cutoff} -T{used}"},
+                             "sample": sample_text(a, used, " per step; FASTA parse and file writes included")},
             "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------
 
+def invariants(res_hist, max_inst, nkmers, ndistinct):
+    """size-independent properties of any correct count: sum of the histogram = distinct k-mers; sum of c * hist[c]
+    below saturation + max_inst = k-mer instances"""
+    import numpy as np
+    h = np.asarray(res_hist, dtype=np.int64)
+    c = np.arange(len(h), dtype=np.int64)
+    inst = int((h[:32767] * c[:32767]).sum()) + int(max_inst)
+    bad = []
+    if int(h[1:].sum()) != int(ndistinct):
+        bad.append(f"sum(hist) {int(h[1:].sum())} != distinct {int(ndistinct)}")
+    if inst != int(nkmers):
+        bad.append(f"sum(c*hist)+max_inst {inst} != k-mer instances {int(nkmers)}")
+    return bad
+
+
 def main():
-    args = parse()
+    a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "reference":
-        reference_arm(args, rank)
+    if a.impl == "reference":
+        reference_arm(a, rank)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
-    from fastk_b200 import FastKGPU
+    from fastk_b200 import FastKGPU, formats, synth
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -231,16 +242,16 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    genome_bp = int(args.genome_mbp * 1e6)
-    nreads = int(genome_bp * args.coverage / args.read_len)
-    k = args.kmer
-    nbases = nreads * args.read_len
-    npos = nreads * (args.read_len + 1)
+    k, L, nreads = a.kmer, a.read_len, a.nreads
+    nbases = nreads * L
+    npos = nreads * (L + 1)
 
-    # ---- build the batch: ASCII on the device -> packed (device-resident arm) and pinned host copy (e2e arm)
-    ascii_dev = gen_reads_ascii(torch, dev, genome_bp, nreads, args.read_len, args.sub_rate, args.seed + 7919 * rank)
-    nthr = args.ingest_threads or max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
-    eng = FastKGPU(k=k, table_cutoff=args.cutoff, device=local, nthreads=nthr, reserve_bases=npos)
+    # ---- the batch: rank r's reads in pinned host memory (DATA_BLOCK layout), then ASCII on the device -> packed
+    host_ascii = torch.empty((nreads, L + 1), dtype=torch.uint8, pin_memory=True)
+    make_rows(a, rank, out=host_ascii.numpy())
+    ascii_dev = host_ascii.to(dev, non_blocking=True)
+    nthr = a.ingest_threads or max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
+    eng = FastKGPU(k=k, table_cutoff=a.cutoff, profile=a.profile, device=local, nthreads=nthr, reserve_bases=npos)
     runner = None
     if world > 1:
         # packed reads live in library-owned buffers that every peer maps over CUDA IPC (NVLink gathers in the count kernel)
@@ -254,22 +265,27 @@ def main():
         seq_ptr, val_ptr = d_seq.data_ptr(), d_val.data_ptr()
     eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, seq_ptr, val_ptr)
     torch.cuda.synchronize()
-    host_ascii = None
-    if not args.no_e2e and world == 1:
-        host_ascii = torch.empty((nreads, args.read_len + 1), dtype=torch.uint8, pin_memory=True)
-        host_ascii.copy_(ascii_dev)
     del ascii_dev
     torch.cuda.empty_cache()
 
+    want_table = a.cutoff > 0
     if world > 1:
         def one_step():
-            return runner.count_packed(seq_ptr, val_ptr, npos)
+            return runner.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
+    elif a.profile:
+        rstart = np.arange(nreads, dtype=np.int64) * (L + 1)
+        rlen = np.full(nreads, L, dtype=np.int32)
+
+        def one_step():
+            r = eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
+            r.prof_off, r.prof = eng.profiles_packed(seq_ptr, val_ptr, npos, rstart, rlen, copy=False)
+            return r
     else:
         def one_step():
-            return eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=False)
+            return eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
 
-    # ---- device-resident arm ---------------------------------------------------------------------------
-    for _ in range(args.warmup):
+    # ---- device-resident arm: packed reads in HBM -> table + histogram in pinned host memory ---------------------
+    for _ in range(a.warmup):
         res = one_step()
     l0 = eng.launch_count()
     barrier()
@@ -277,7 +293,7 @@ def main():
     t0 = time.perf_counter()
     stage_ms = {}
     dev_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(a.steps):
         res = one_step()
         dev_ms += res.ms_total
         for kname, v in (res.stage_ms if world > 1 else eng.stage_times()).items():
@@ -290,22 +306,26 @@ def main():
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed = float(el.item())
-    value = nbases * world * args.steps / elapsed / 1e9
+    value = nbases * world * a.steps / elapsed / 1e9
+    problems = invariants(res.hist, res.max_inst, res.nkmers, res.ndistinct)
+    stats = eng.last_stats() if world == 1 else None
 
-    # ---- e2e arm (single GPU): host DATA_BLOCKs -> fkgpu_ingest x8 threads -> finish -> table in pinned host memory
-    e2e = None
-    if host_ascii is not None:
-        rows_per_block = max(1, min(10000, (1_000_000 - 1) // (args.read_len + 1)))
-        boff_full = (np.arange(rows_per_block + 1, dtype=np.int64) * (args.read_len + 1)).astype(np.int32)
+    # ---- e2e arm (single GPU): host DATA_BLOCKs -> fkgpu_ingest x nthr threads -> finish -> table in pinned host memory
+    e2e, r2 = None, None
+    if not a.no_e2e and world == 1:
+        rows_per_block = max(1, min(10000, (1_000_000 - 1) // (L + 1)))
+        boff_full = (np.arange(rows_per_block + 1, dtype=np.int64) * (L + 1)).astype(np.int32)
         base_ptr = host_ascii.data_ptr()
         blocks = [(r0, min(nreads, r0 + rows_per_block)) for r0 in range(0, nreads, rows_per_block)]
 
         def worker(tid):
-            for bi in range(tid, len(blocks), nthr):
+            # tid-major read order, contiguous block ranges per thread (io.c hands each thread a contiguous file range)
+            b0, b1 = len(blocks) * tid // nthr, len(blocks) * (tid + 1) // nthr
+            for bi in range(b0, b1):
                 r0, r1 = blocks[bi]
-                eng.ingest_ptr(base_ptr + r0 * (args.read_len + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
+                eng.ingest_ptr(base_ptr + r0 * (L + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
 
-        e2e_split = {"ingest_ms": 0.0, "finish_ms": 0.0}
+        e2e_split = {"ingest_ms": 0.0, "finish_ms": 0.0, "profile_ms": 0.0}
 
         def e2e_step():
             ta = time.perf_counter()
@@ -316,31 +336,105 @@ def main():
             for t in th:
                 t.join()
             tb = time.perf_counter()
-            r = eng.finish(fetch_table=True, copy_table=False)
+            r = eng.finish(fetch_table=want_table, copy_table=False)
             tc = time.perf_counter()
+            if a.profile:
+                r.prof_off, r.prof = eng.profiles(copy=False)
+            td = time.perf_counter()
             e2e_split["ingest_ms"] += 1e3 * (tb - ta)
             e2e_split["finish_ms"] += 1e3 * (tc - tb)
+            e2e_split["profile_ms"] += 1e3 * (td - tc)
             return r
 
-        for _ in range(max(1, args.warmup - 1)):
+        for _ in range(max(1, a.warmup - 1)):
             r2 = e2e_step()
         torch.cuda.synchronize()
-        e2e_split["ingest_ms"] = e2e_split["finish_ms"] = 0.0
+        for key in e2e_split:
+            e2e_split[key] = 0.0
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(a.steps):
             r2 = e2e_step()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        e2e = {"value": nbases * args.steps / (t1 - t0) / 1e9, "unit": "Gbases/s",
-               "h2d_bytes_per_step": int(npos), "d2h_bytes_per_step": int(r2.ntable * (r2.kmer_bytes + 2) + 32768 * 8),
-               "ms_per_step": 1e3 * (t1 - t0) / args.steps,
-               "ingest_ms_per_step": e2e_split["ingest_ms"] / args.steps,
-               "finish_ms_per_step": e2e_split["finish_ms"] / args.steps,
+        d2h = int(r2.ntable * (r2.kmer_bytes + 2) + 32768 * 8)
+        if a.profile:
+            d2h += int(len(r2.prof) * 2 + len(r2.prof_off) * 8)
+        e2e = {"value": nbases * a.steps / (t1 - t0) / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(npos), "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * (t1 - t0) / a.steps,
+               "ingest_ms_per_step": e2e_split["ingest_ms"] / a.steps,
+               "finish_ms_per_step": e2e_split["finish_ms"] / a.steps,
+               "profile_ms_per_step": e2e_split["profile_ms"] / a.steps,
                "finish_device_ms": r2.ms_total,
                "finish_stage_ms": {kn: round(v, 3) for kn, v in eng.stage_times().items() if v > 0},
                "path": f"fkgpu_ingest ({nthr} threads, DATA_BLOCKs in pinned host memory; chunks packed + scanned on the device as "
-                       "they land) -> fkgpu_finish(fetch_table=1)"}
-        assert r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct, "e2e and device-resident arms disagree"
+                       f"they land) -> fkgpu_finish(fetch_table={int(want_table)})" + (" -> fkgpu_profiles" if a.profile else "")}
+        if not (r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct and np.array_equal(r2.hist, res.hist)):
+            problems.append("e2e and device-resident arms disagree")
+
+    # ---- parity against the reference FastK on the FASTA of rank 0's reads, and the CPU baseline (the same run) --------
+    cpu, parity = None, {"checked": False}
+    if not a.no_cpu and ref_binary() is not None:
+        tmpdir = scratch_dir("fastk_cpu_") if rank == 0 else None
+        try:
+            if rank == 0:
+                fasta = os.path.join(tmpdir, "reads.fasta")
+                synth.write_rows_fasta(host_ascii.numpy(), fasta)
+                cores = os.cpu_count() or 1
+                t, kind, used = run_reference_once(a, fasta, tmpdir, cores)
+                os.remove(fasta)
+                if world == 1:
+                    cpu = {"value": nbases / t / 1e9, "unit": "Gbases/s", "cores": used, "kind": kind,
+                           "sample": sample_text(a, used, f", one run, {t:.1f} s wall; FASTA parse and file writes included")}
+            if world == 1:
+                got = r2 if r2 is not None else eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
+                table = got.view_table() if want_table else None
+                ghist, gmax = got.hist, got.max_inst
+                via = "fkgpu_ingest/fkgpu_finish (the e2e arm's last step)" if r2 is not None else "fkgpu_count_packed"
+            else:
+                # the SAME FASTA at every N: rank 0's reads, dealt out in contiguous slices to the N ranks, through the
+                # multi-GPU pipeline; the rank-ordered tables are gathered to rank 0
+                full = host_ascii.to(dev) if rank == 0 else torch.empty((nreads, L + 1), dtype=torch.uint8, device=dev)
+                dist.broadcast(full, 0)
+                r0, r1 = nreads * rank // world, nreads * (rank + 1) // world
+                mine = full[r0:r1].contiguous()
+                del full
+                np2 = (r1 - r0) * (L + 1)
+                pad = torch.zeros(64, dtype=torch.uint8, device=dev)
+                mine = torch.cat([mine.view(-1), pad])
+                s2, v2 = runner.alloc_reads(np2)
+                eng.pack_ascii_dev(mine.data_ptr(), np2, s2, v2)
+                torch.cuda.synchronize()
+                got = runner.count_packed(s2, v2, np2, fetch_table=want_table, copy_table=False)
+                del mine
+                ghist, gmax = got.hist, got.max_inst
+                table = None
+                if want_table:
+                    tw = got.kmer_bytes + 2
+                    mx = max(got.table_sizes)
+                    loc = torch.zeros((mx, tw), dtype=torch.uint8, device=dev)
+                    if got.local.ntable:
+                        loc[:got.local.ntable] = torch.from_numpy(got.local.view_table()).to(dev)
+                    parts = [torch.zeros((mx, tw), dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+                    dist.gather(loc, parts, dst=0)
+                    if rank == 0:
+                        table = np.concatenate([parts[r][:got.table_sizes[r]].cpu().numpy() for r in range(world)])
+                    del loc, parts
+                via = f"multigpu.count_packed over {world} ranks (exchange: {getattr(got, 'exchange', got.path)})"
+            if rank == 0:
+                bad = formats.compare_with_fastk_files(tmpdir, "cpu_out", k, a.cutoff, ghist, gmax, table)
+                parity = {"checked": True, "ok": not bad, "against": "oracle/_ref/FastK (.hist bins + max_inst, .ktab prefix index, "
+                          "every suffix + count byte of the hidden parts)", "via": via,
+                          "gbases": round(nbases / 1e9, 3), "table_records": int(0 if table is None else table.shape[0]),
+                          "mismatches": bad}
+                problems += bad
+                if a.profile and r2 is not None:
+                    pb = compare_profiles(tmpdir, "cpu_out", r2, nreads)
+                    parity["profiles"] = "decoded .prof of every read identical" if not pb else pb
+                    problems += pb
+        finally:
+            if tmpdir:
+                shutil.rmtree(tmpdir, ignore_errors=True)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peaks = {}
@@ -353,7 +447,7 @@ def main():
     W = 8 if k <= 32 else 16
     N, U = res.nkmers, res.ndistinct
     if world == 1:
-        st = eng.last_stats()
+        st = stats
     else:
         # rank 0's share of the job: its own stage times against its own record / entry counts
         st = dict(path=1 if res.path == "super-mer" else 0, supermers=getattr(res, "supermers", 0),
@@ -362,17 +456,18 @@ def main():
     ntab = res.ntable // world
     if st["path"] == 1:
         # super-mer path: 8-byte super-mer pointers (bucket|len|position) through the partition (histogram read, scatter
-        # read+write, refine 2 reads + write = 6 passes), base gather + 16-byte (key|count) entries out of the bucket
+        # read+write, refine 2 reads + write = 6 passes), base gather + (key|count) entries out of the bucket
         # kernel, entries through the weighted key-order sort
         S, E = st["supermers"], st["entries"]
+        EB = 16 if k <= 56 else 24
         alg = {"super_scan": nbases * 0.375 + S * 8,
                "super_partition": 6 * S * 8,
-               "bucket_count": S * 8 + (N + S * (k - 1)) * 0.25 + E * 16,
-               "entry_partition": 3 * E * 16,
-               "refine": 3 * E * 16,
+               "bucket_count": S * 8 + (N + S * (k - 1)) * 0.25 + E * EB,
+               "entry_partition": 3 * E * EB,
+               "refine": 3 * E * EB,
                # the weighted sort writes the final table records itself (no staging, no compaction pass)
-               "sortcount": E * 16 + ntab * (res.kmer_bytes + 2)}
-        W = 16
+               "sortcount": E * EB + ntab * (res.kmer_bytes + 2)}
+        W = EB
     else:
         alg = {"scan_hist": nbases * 0.375,
                "scan_scatter": nbases * 0.375 + N * W,
@@ -381,7 +476,7 @@ def main():
                "compact": U * (W + 4) + ntab * (res.kmer_bytes + 2)}
     per_stage = {}
     for s, b in alg.items():
-        ms = stage_ms.get(s, 0.0) / args.steps
+        ms = stage_ms.get(s, 0.0) / a.steps
         per_stage[s] = {"ms": round(ms, 3), "alg_gbytes": round(b / 1e9, 3), "gbs": round(b / 1e9 / (ms / 1e3), 1) if ms > 0 else None}
     dom = max(alg.keys(), key=lambda s: per_stage[s]["ms"])
     traffic = None
@@ -389,7 +484,7 @@ def main():
     if os.path.exists(tj):
         try:
             tr = json.load(open(tj))
-            if dom in tr and tr.get("kmers"):
+            if dom in tr and tr.get("kmers") and tr.get("kmer", 40) == k:
                 traffic = int(tr[dom] * (N / tr["kmers"]))       # ncu capture of a smaller batch, scaled by k-mers
         except Exception:
             traffic = None
@@ -397,33 +492,21 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650",
                 "pipeline": {"alg_bytes_per_kmer": round(sum(alg.values()) / max(N, 1), 2),
-                             "gbs": round(sum(alg.values()) / 1e9 / (dev_ms / args.steps / 1e3), 1) if dev_ms > 0 else None,
-                             "frac": round(sum(alg.values()) / 1e9 / (dev_ms / args.steps / 1e3) / peak, 4) if dev_ms > 0 else None},
+                             "gbs": round(sum(alg.values()) / 1e9 / (dev_ms / a.steps / 1e3), 1) if dev_ms > 0 else None,
+                             "frac": round(sum(alg.values()) / 1e9 / (dev_ms / a.steps / 1e3) / peak, 4) if dev_ms > 0 else None},
                 "stages": per_stage}
 
-    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        tmpdir = tempfile.mkdtemp(prefix="fastk_cpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-        fasta = os.path.join(tmpdir, "sample.fasta")
-        nb, nr, gsize = write_sample_fasta(args, fasta, args.cpu_sample_gbases)
-        t, kind, used = run_reference_once(args, fasta, tmpdir, cores)
-        subprocess.call(["rm", "-rf", tmpdir])
-        cpu = {"value": nb / t / 1e9, "unit": "Gbases/s", "cores": used, "kind": kind,
-               "sample": f"{nr} reads x {args.read_len} bp = {nb/1e9:.3f} Gbases ({args.coverage:g}x of {gsize/1e6:.1f} Mbp), "
-                         f"FASTA on tmpfs, one run of FastK -k{k} -t{args.cutoff} -T{used} -M16, {t:.1f} s wall"}
-
     if rank == 0:
-        per_gpu = nbases / 1e9
         line = {"metric": "Gbases/sec counted (k=%d)" % k, "value": value, "unit": "Gbases/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
-                "device_ms_per_step": dev_ms / args.steps,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
+                "device_ms_per_step": dev_ms / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": workload_name(args, per_gpu), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
+                "config": {"workload": workload_name(a), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),
                            "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
-                           "supermer_records": st["supermers"], "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
+                           "supermer_records": st["supermers"],
+                           "timed_region": "packed reads resident in HBM -> sorted [key][count] table + histogram in pinned host memory",
+                           "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),
                            "parallelism": (("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, "
                                             + ("bases gathered from peer HBM over NVLink inside the count kernel"
@@ -432,14 +515,40 @@ def main():
                                             + ", then all-to-all of the distinct entries by key prefix")
                                            if st["path"] == 1 else "1 process/GPU; prefix-range all-to-all of k-mer records over NCCL")
                            if world > 1 else "single GPU"},
-                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "parity_checked": bool(parity.get("checked") and parity.get("ok") and not problems), "parity": parity,
+                "invariant_violations": problems}
         print(json.dumps(line), flush=True)
+    fail = torch.tensor([1 if (rank == 0 and problems) else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(fail, op=dist.ReduceOp.MAX)
     if runner is not None:
         dist.barrier(device_ids=[local])
         runner.close_peers()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if int(fail.item()):
+        if rank == 0:
+            print("bench.py: PARITY FAILURE: " + "; ".join(problems), file=sys.stderr)
+        sys.exit(1)
+
+
+def compare_profiles(d, root, r2, nreads):
+    """decoded .prof of the reference run vs the profiles of the e2e arm's last step -> list of mismatches"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py                      # the checker: Fetch_Profile restated (libfastk.c:1707-1803)
+    import util
+    so = os.path.join(ROOT, "oracle", "libfastk_oracle.so")
+    orc = oracle_py.load(so)
+    prof, off, _ = util.decode_prof_files(d, root, orc)
+    bad = []
+    if len(off) != nreads + 1 or not np.array_equal(off, r2.prof_off):
+        bad.append(".prof read offsets differ")
+    elif not np.array_equal(prof, r2.prof):
+        bad.append(".prof decoded counts differ")
+    return bad
 
 
 if __name__ == "__main__":

@@ -1593,32 +1593,23 @@ extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int 
   return FKGPU_OK;
 }
 
+/*  pieces: copy praw[src[i] .. src[i]+len[i]) to the output at dst[i]; offs = profile start of every read (+ total)  */
+struct ProfPieces { std::vector<long long> src, dst; std::vector<int> len; std::vector<int64_t> offs; long long run = 0; };
+
 template<int NW>
-static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)
-{ const long long npos = c->last_npos;
-  const int k = c->cfg.kmer, bc = c->cfg.bc_prefix;
-  /* pieces in tid-major order; a continuation piece (rem carry) extends the previous read */
-  std::vector<long long> src, dst; std::vector<int> len; std::vector<int64_t> offs;
-  long long run = 0;
-  for (auto &t : c->tids)
-    for (size_t i = 0; i < t.rstart.size(); i++)
-      { const int b = t.rcont[i] ? 0 : bc;
-        int pl = t.rlen[i] - b - k + 1; if (pl < 0) pl = 0;
-        if (!t.rcont[i]) offs.push_back(run);
-        src.push_back(t.rstart[i] + b); dst.push_back(run); len.push_back(pl);
-        run += pl;
-      }
-  offs.push_back(run);
-  const size_t np = src.size();
+static int profiles_run(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, const ProfPieces &pp,
+                        int64_t *nreads, const int64_t **off, const uint16_t **prof)
+{ const size_t np = pp.src.size();
+  const long long run = pp.run;
   if (c->praw.ensure((size_t) (npos + 64) * 2) || c->pout.ensure((size_t) (run + 2) * 2) || c->psrc.ensure(np*8 + 8) || c->pdst.ensure(np*8 + 8)
       || c->plen.ensure(np*4 + 8))
     return set_err(FKGPU_E_NOMEM,"out of device memory (profiles of %lld positions)",npos);
-  if (c->h_prof.ensure((size_t) (run + 2) * 2) || c->h_poff.ensure(offs.size() * 8))
+  if (c->h_prof.ensure((size_t) (run + 2) * 2) || c->h_poff.ensure(pp.offs.size() * 8))
     return set_err(FKGPU_E_NOMEM,"out of pinned host memory (profiles)");
   stage_begin(c,FKGPU_ST_PROFILE);
   ProfileParams q;
   ScanGeom g = scan_geom(c,npos,0);
-  fill_scan_params(c,q.sp,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,0,g);
+  fill_scan_params(c,q.sp,d_seq,d_val,npos,0,g);
   q.keys = c->pkeys.p; q.cnts = (const uint16_t *) c->pcnts.p; q.idx = (const u64 *) c->pidx.p; q.B = c->ptab_B;
   q.raw = (uint16_t *) c->praw.p;
   if (g.ntiles > 0)
@@ -1626,9 +1617,9 @@ static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const 
       k_profile<NW><<<(unsigned) g.ntiles,SCAN_TPB,sm,c->st>>>(q); KCHECK();
     }
   if (np > 0)
-    { CU(cudaMemcpyAsync(c->psrc.p,src.data(),np*8,cudaMemcpyHostToDevice,c->st));
-      CU(cudaMemcpyAsync(c->pdst.p,dst.data(),np*8,cudaMemcpyHostToDevice,c->st));
-      CU(cudaMemcpyAsync(c->plen.p,len.data(),np*4,cudaMemcpyHostToDevice,c->st));
+    { CU(cudaMemcpyAsync(c->psrc.p,pp.src.data(),np*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->pdst.p,pp.dst.data(),np*8,cudaMemcpyHostToDevice,c->st));
+      CU(cudaMemcpyAsync(c->plen.p,pp.len.data(),np*4,cudaMemcpyHostToDevice,c->st));
       k_gather_profile<<<c->sms * 8,256,0,c->st>>>((const uint16_t *) c->praw.p,(const long long *) c->psrc.p,(const long long *) c->pdst.p,
                                                   (const int *) c->plen.p,(long long) np,(uint16_t *) c->pout.p); KCHECK();
     }
@@ -1636,11 +1627,52 @@ static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const 
   if (run > 0) CU(cudaMemcpyAsync(c->h_prof.p,c->pout.p,(size_t) run * 2,cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
   cudaEventElapsedTime(&c->ms[FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE+1]);
-  memcpy(c->h_poff.p,offs.data(),offs.size()*8);
-  *nreads = (int64_t) offs.size() - 1;
+  memcpy(c->h_poff.p,pp.offs.data(),pp.offs.size()*8);
+  *nreads = (int64_t) pp.offs.size() - 1;
   *off = (const int64_t *) c->h_poff.p;
   *prof = (const uint16_t *) c->h_prof.p;
   return FKGPU_OK;
+}
+
+template<int NW>
+static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)
+{ const int k = c->cfg.kmer, bc = c->cfg.bc_prefix;
+  /* pieces in tid-major order; a continuation piece (rem carry) extends the previous read */
+  ProfPieces pp;
+  for (auto &t : c->tids)
+    for (size_t i = 0; i < t.rstart.size(); i++)
+      { const int b = t.rcont[i] ? 0 : bc;
+        int pl = t.rlen[i] - b - k + 1; if (pl < 0) pl = 0;
+        if (!t.rcont[i]) pp.offs.push_back(pp.run);
+        pp.src.push_back(t.rstart[i] + b); pp.dst.push_back(pp.run); pp.len.push_back(pl);
+        pp.run += pl;
+      }
+  pp.offs.push_back(pp.run);
+  return profiles_run<NW>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,c->last_npos,pp,nreads,off,prof);
+}
+
+extern "C" int fkgpu_profiles_packed(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                                     const int64_t *read_start, const int32_t *read_len, int64_t nreads_in,
+                                     int64_t *nreads, const int64_t **off, const uint16_t **prof)
+{ if (c == NULL || nreads == NULL || off == NULL || prof == NULL || nreads_in < 0 || (nreads_in > 0 && (read_start == NULL || read_len == NULL))
+      || (npos > 0 && (d_seq == NULL || d_val == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_profiles_packed: bad argument");
+  if (!c->cfg.do_profile) return set_err(FKGPU_E_STATE,"fkgpu_profiles_packed: the context was created without do_profile");
+  if (c->ptab_n <= 0 && c->last_ndist > 0) return set_err(FKGPU_E_STATE,"fkgpu_profiles_packed: call fkgpu_count_packed first");
+  CU(cudaSetDevice(c->cfg.device));
+  const int k = c->cfg.kmer, bc = c->cfg.bc_prefix;
+  ProfPieces pp;
+  pp.src.reserve((size_t) nreads_in); pp.dst.reserve((size_t) nreads_in); pp.len.reserve((size_t) nreads_in); pp.offs.reserve((size_t) nreads_in + 1);
+  for (int64_t i = 0; i < nreads_in; i++)
+    { if (read_start[i] < 0 || read_len[i] < 0 || read_start[i] + read_len[i] > npos)
+        return set_err(FKGPU_E_ARG,"fkgpu_profiles_packed: read %lld lies outside the stream",(long long) i);
+      int pl = read_len[i] - bc - k + 1; if (pl < 0) pl = 0;
+      pp.offs.push_back(pp.run);
+      pp.src.push_back(read_start[i] + bc); pp.dst.push_back(pp.run); pp.len.push_back(pl);
+      pp.run += pl;
+    }
+  pp.offs.push_back(pp.run);
+  return (c->res_nw == 1) ? profiles_run<1>(c,d_seq,d_val,npos,pp,nreads,off,prof) : profiles_run<2>(c,d_seq,d_val,npos,pp,nreads,off,prof);
 }
 
 extern "C" int fkgpu_profiles(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const uint16_t **prof)

@@ -61,6 +61,9 @@ def load_library(path=None):
     lib.fkgpu_finish.restype = C.c_int
     lib.fkgpu_profiles.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(i64)), C.POINTER(C.POINTER(C.c_uint16))]
     lib.fkgpu_profiles.restype = C.c_int
+    lib.fkgpu_profiles_packed.argtypes = [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32), i64, C.POINTER(i64),
+                                          C.POINTER(C.POINTER(i64)), C.POINTER(C.POINTER(C.c_uint16))]
+    lib.fkgpu_profiles_packed.restype = C.c_int
     lib.fkgpu_read_counts.argtypes = [vp, C.POINTER(i64)]
     lib.fkgpu_read_counts.restype = C.c_int
     lib.fkgpu_packed_words.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
@@ -115,7 +118,7 @@ def load_library(path=None):
 
 
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
-           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
+           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
            "fkgpu_super_supported", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
@@ -139,7 +142,16 @@ class FkResult:
             self.table = np.ctypeslib.as_array(r.table, shape=(r.ntable * tw,)).copy().reshape(r.ntable, tw)
         else:
             self.table = None
+        self._table_ptr = r.table if (r.ntable > 0 and bool(r.table)) else None
         self.ms_pack, self.ms_count, self.ms_total = r.ms_pack, r.ms_count, r.ms_total
+
+    def view_table(self):
+        """(ntable, kmer_bytes + 2) uint8 view of the context's pinned host copy -- no copy; valid until the next
+        finish / count / reset / close on the context that produced it."""
+        tw = self.kmer_bytes + 2
+        if self._table_ptr is None:
+            return np.zeros((0, tw), dtype=np.uint8)
+        return np.ctypeslib.as_array(self._table_ptr, shape=(self.ntable * tw,)).reshape(self.ntable, tw)
 
 
 class FastKGPU:
@@ -292,12 +304,30 @@ class FastKGPU:
         self._chk(self.lib.fkgpu_stage_times(self.h, ms, by), "fkgpu_stage_times")
         return {STAGES[i]: float(ms[i]) for i in range(NSTAGES)}
 
-    def profiles(self):
+    @staticmethod
+    def _prof_arrays(n, off, prof, copy):
+        offs = np.ctypeslib.as_array(off, shape=(n.value + 1,))
+        tot = int(offs[-1])
+        p = np.ctypeslib.as_array(prof, shape=(max(tot, 1),))[:tot]
+        return (offs.copy(), p.copy()) if copy else (offs, p)
+
+    def profiles(self, copy=True):
+        """-> (off int64 [nreads+1], prof uint16): prof[off[r]:off[r+1]] = counts of read r (tid-major read order).
+        copy=False returns views of the context's pinned memory (valid until the next call on the context)."""
         n = C.c_int64()
         off = C.POINTER(C.c_int64)()
         prof = C.POINTER(C.c_uint16)()
         self._chk(self.lib.fkgpu_profiles(self.h, C.byref(n), C.byref(off), C.byref(prof)), "fkgpu_profiles")
-        offs = np.ctypeslib.as_array(off, shape=(n.value + 1,)).copy()
-        tot = int(offs[-1])
-        p = np.ctypeslib.as_array(prof, shape=(max(tot, 1),))[:tot].copy()
-        return offs, p
+        return self._prof_arrays(n, off, prof, copy)
+
+    def profiles_packed(self, d_seq_ptr, d_val_ptr, npos, read_start, read_len, copy=True):
+        """profiles over a packed stream counted with count_packed (do_profile contexts)"""
+        rs = np.ascontiguousarray(read_start, dtype=np.int64)
+        rl = np.ascontiguousarray(read_len, dtype=np.int32)
+        n = C.c_int64()
+        off = C.POINTER(C.c_int64)()
+        prof = C.POINTER(C.c_uint16)()
+        self._chk(self.lib.fkgpu_profiles_packed(self.h, d_seq_ptr, d_val_ptr, npos, rs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 rl.ctypes.data_as(C.POINTER(C.c_int32)), len(rs), C.byref(n), C.byref(off),
+                                                 C.byref(prof)), "fkgpu_profiles_packed")
+        return self._prof_arrays(n, off, prof, copy)

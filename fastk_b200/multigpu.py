@@ -189,12 +189,26 @@ class MultiGPUCounter:
         self._opened = []
         self.peer_seq = None
 
-    def count_packed(self, d_seq, d_val, npos, fetch_table=False):
-        """d_seq / d_val: torch tensors or raw device pointers.  The super-mer path needs the buffers of alloc_reads()."""
+    def _all_agree(self, ok):
+        """collective AND of a rank-local condition: every rank takes the same branch (a rank that went into an
+        all-to-all alone would hang the job)"""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(int(flag.item()))
+
+    def count_packed(self, d_seq, d_val, npos, fetch_table=False, copy_table=True):
+        """d_seq / d_val: torch tensors or raw device pointers.  The super-mer path needs the buffers of alloc_reads().
+        The choice of the pipeline, and the fall back to the record path when the super-mer scan of ANY rank declines
+        its input, are agreed collectively."""
         sp = d_seq if isinstance(d_seq, int) else d_seq.data_ptr()
         vp = d_val if isinstance(d_val, int) else d_val.data_ptr()
-        if getattr(self, "super_ok", False) and sp == self.seq_ptr and npos == self.npos and os.environ.get("FKGPU_MG") != "records":
-            return self._count_super(sp, vp, npos, fetch_table)
+        self.copy_table = copy_table
+        mine = (getattr(self, "super_ok", False) and sp == getattr(self, "seq_ptr", None) and npos == getattr(self, "npos", -1)
+                and os.environ.get("FKGPU_MG") != "records")
+        if self._all_agree(mine):
+            out = self._count_super(sp, vp, npos, fetch_table)
+            if out is not None:
+                return out
         return self._count_records(sp, vp, npos, fetch_table)
 
     def _finish(self, out, res, hist, scalars, t0, t1):
@@ -222,7 +236,12 @@ class MultiGPUCounter:
         t0.record()
         total = self.pos_base[-1]
         tm = _Timer(self.rank == 0 and os.environ.get("FKGPU_MG_TIMING"))
-        sc = eng.super_scan(sp, vp, npos, total, self.pos_base[self.rank])
+        try:
+            sc = eng.super_scan(sp, vp, npos, total, self.pos_base[self.rank])
+        except Exception as e:                       # e.g. more super-mers than the staging buffer holds on this rank
+            sc, self.last_super_error = None, str(e)
+        if not self._all_agree(sc is not None):
+            return None                              # every rank falls back to the record path together
         scan_ms = dict(eng.stage_times())
         tm.lap("super_scan")
         nb = 1 << sc["bits"]
@@ -288,7 +307,7 @@ class MultiGPUCounter:
             recv2, rc2 = exchange_records(part, sc2)
             torch.cuda.current_stream().synchronize()
             tm.lap("entries all-to-all")
-            tres = eng.entries_sort(recv2.data_ptr(), sum(rc2), fetch_table=fetch_table)
+            tres = eng.entries_sort(recv2.data_ptr(), sum(rc2), fetch_table=fetch_table, copy_table=self.copy_table)
             tm.lap("entries_sort")
             for kname, v in eng.stage_times().items():
                 if v:
@@ -323,7 +342,7 @@ class MultiGPUCounter:
         recv, recv_counts = exchange_records(self.send, send_counts)
         torch.cuda.current_stream().synchronize()      # NCCL wrote `recv` on torch's stream; the library runs on its own
         nrecv = sum(recv_counts)
-        res = eng.count_records(recv.data_ptr(), nrecv, fetch_table=fetch_table)
+        res = eng.count_records(recv.data_ptr(), nrecv, fetch_table=fetch_table, copy_table=getattr(self, 'copy_table', True))
         out = MultiResult()
         out.path = "records"
         out.stage_ms = dict(eng.stage_times())

@@ -77,3 +77,57 @@ def write_fastq(reads, path):
     with open(path, "wb") as f:
         for i, r in enumerate(reads):
             f.write(b"@r%d\n" % i + r + b"\n+\n" + b"I" * len(r) + b"\n")
+
+
+# ---- bench-scale workloads: one generator for BOTH bench arms and the at-scale parity tests ------------------------------
+
+def workload_rows(genome_bp, nreads, read_len, sub_rate, seed, out=None):
+    """Fixed-length reads of the BASELINE.json shape -> uint8 [nreads, read_len+1], every row one ASCII read followed by
+    a 0 terminator: the concatenation of the rows is a DATA_BLOCK's `bases` (FastK.h:92).  Deterministic in its
+    arguments, so the GPU arm, the reference arm and the parity check of bench.py all see the same reads."""
+    rng = np.random.default_rng(seed)
+    G, L = int(genome_bp), int(read_len)
+    genome = rng.integers(0, 4, G, dtype=np.uint8)
+    rows = out if out is not None else np.empty((nreads, L + 1), dtype=np.uint8)
+    assert rows.shape == (nreads, L + 1) and rows.dtype == np.uint8
+    rows[:, L] = 0
+    ar = np.arange(L, dtype=np.int64)
+    chunk = max(1, (32 << 20) // L)
+    for r0 in range(0, nreads, chunk):
+        r1 = min(nreads, r0 + chunk)
+        n = r1 - r0
+        st = rng.integers(0, G - L + 1, n)
+        if L >= 1024:
+            blk = np.empty((n, L), dtype=np.uint8)
+            for i in range(n):
+                blk[i] = genome[st[i]:st[i] + L]
+        else:
+            blk = genome[st[:, None] + ar[None, :]]
+        if sub_rate > 0:
+            ns = int(rng.binomial(n * L, sub_rate))
+            pos = rng.integers(0, n * L, ns)
+            add = rng.integers(1, 4, ns, dtype=np.uint8)
+            flat = blk.reshape(-1)
+            flat[pos] = (flat[pos] + add) & 3
+        flip = rng.random(n) < 0.5
+        blk[flip] = (3 - blk[flip])[:, ::-1]
+        rows[r0:r1, :L] = _ACGT[blk]
+    return rows
+
+
+def write_rows_fasta(rows, path, first_id=0, append=False):
+    """rows of workload_rows -> single-line FASTA with fixed-width headers (one 2-D array, one write)."""
+    n, L = rows.shape[0], rows.shape[1] - 1
+    hdr = 12                                               # ">r%010d"
+    rec = np.empty((n, hdr + 1 + L + 1), dtype=np.uint8)
+    ids = np.arange(first_id, first_id + n, dtype=np.int64)
+    rec[:, 0] = ord(">")
+    rec[:, 1] = ord("r")
+    for d in range(10):
+        rec[:, 11 - d] = ord("0") + (ids // 10 ** d) % 10
+    rec[:, hdr] = ord("\n")
+    rec[:, hdr + 1:hdr + 1 + L] = rows[:, :L]
+    rec[:, hdr + 1 + L] = ord("\n")
+    with open(path, "ab" if append else "wb") as f:
+        rec.tofile(f)
+    return n * L

@@ -121,6 +121,13 @@ int  fkgpu_pack_ascii_dev(fkgpu_ctx *ctx, const char *d_ascii, int64_t npos, uin
 int  fkgpu_count_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
                         int fetch_table, fkgpu_result *res);
 
+/*  Count profiles over a packed stream counted by fkgpu_count_packed on a context with do_profile (the device-resident
+ *  form of fkgpu_profiles; count.c:817-1181): read i occupies positions [read_start[i], read_start[i] + read_len[i]) of
+ *  the stream (host arrays).  Outputs as fkgpu_profiles.                                                          */
+int  fkgpu_profiles_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                           const int64_t *read_start, const int32_t *read_len, int64_t nreads_in,
+                           int64_t *nreads, const int64_t **off, const uint16_t **prof);
+
 /*  Multi-GPU stages (one process per GPU; the exchange itself is done by the caller, e.g. NCCL
  *  all-to-all via torch.distributed -- see fastk_b200/multigpu.py):
  *   1. fkgpu_prefix_hist:   histogram of the top `bits` key bits of every valid canonical k-mer

@@ -13,6 +13,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _have_gpu():
+    try:
+        import fastk_b200
+        return fastk_b200.load_library().fkgpu_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are skipped (not failed) on a box without a CUDA device or without the built library"""
+    if any(it.get_closest_marker("gpu") for it in items) and not _have_gpu():
+        skip = pytest.mark.skip(reason="no CUDA device / libfastk_gpu.so not built")
+        for it in items:
+            if it.get_closest_marker("gpu"):
+                it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle_lib():
     """TEST INFRASTRUCTURE: builds (if needed) and loads the CPU oracle."""

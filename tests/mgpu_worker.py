@@ -1,5 +1,6 @@
-"""torchrun worker for tests/test_gpu_multi.py: N ranks count disjoint read sets with the prefix all-to-all; rank 0
-recounts the union on one GPU through fkgpu_ingest/finish and both must agree bit for bit."""
+"""torchrun worker for tests/test_gpu_multi.py: N ranks count disjoint read sets through the multi-GPU pipeline; rank 0
+counts the union with the CPU ORACLE (oracle/libfastk_oracle.so, the checker) and the global histogram, the scalars and
+the rank-ordered table must agree with it bit for bit."""
 import os
 import sys
 
@@ -9,7 +10,9 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from fastk_b200 import FastKGPU, synth, multigpu  # noqa: E402
+import oracle_py  # noqa: E402
 
 
 def reads_of(rank, k):
@@ -45,17 +48,15 @@ def main():
     ok = 1
     if rank == 0:
         table = np.concatenate([allt[r, :out.table_sizes[r]].cpu().numpy() for r in range(world)])
-        one = FastKGPU(k=k, table_cutoff=1, device=local)
+        union = []
         for r in range(world):
-            for b, o in synth.blocks(reads_of(r, k)):
-                one.ingest(b, o.astype(np.int32))
-        want = one.finish(fetch_table=True)
-        one.close()
+            union += reads_of(r, k)
+        want = oracle_py.load(os.path.join(ROOT, "oracle", "libfastk_oracle.so")).count(union, k, cutoff=1)
         try:
-            assert out.nkmers == want.nkmers and out.ndistinct == want.ndistinct and out.max_inst == want.max_inst
-            assert np.array_equal(out.hist[1:], want.hist[1:]), "global histogram differs"
-            assert out.ntable == want.ntable and np.array_equal(table, want.table), "rank-ordered table differs"
-            print(f"MGPU_OK world={world} k={k} path={out.path} kmers={out.nkmers} distinct={out.ndistinct} sizes={out.table_sizes}")
+            assert out.nkmers == want["nkmers"] and out.ndistinct == want["ndistinct"] and out.max_inst == want["max_inst"]
+            assert np.array_equal(out.hist[1:], want["hist"][1:]), "global histogram differs from the oracle"
+            assert out.ntable == len(want["table"]) and np.array_equal(table, want["table"]), "rank-ordered table differs from the oracle"
+            print(f"MGPU_OK world={world} k={k} path={out.path} oracle=libfastk_oracle kmers={out.nkmers} distinct={out.ndistinct} sizes={out.table_sizes}")
         except AssertionError as e:
             ok = 0
             print("MGPU_FAIL", e)
