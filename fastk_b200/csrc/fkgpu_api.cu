@@ -15,6 +15,7 @@
 
 #include "fastk_gpu.h"
 #include "fkgpu_kernels.cuh"
+#include "fkgpu_bucket.cuh"
 
 using namespace fk;
 
@@ -655,7 +656,8 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       cp.stage0 = Y; cp.stage1 = X; cp.stage_cnt = (const u32 *) c->scnt.p;
       cp.starts = gstart; cp.flags = NULL; cp.e_all = (const u32 *) c->eall.p; cp.out_off = (const u64 *) c->qoff.p;
       cp.out = NULL; cp.nitems = gmax; cp.cutoff = 0; cp.kbytes = c->kbytes;
-      k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cp,(K *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
+      typedef Key<(NW == 3) ? 2 : NW> PK;            /* key words only: the third word of a wide entry held the count */
+      k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cp,(PK *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
       if (nsub > 0)
         { if (c->sub_base.ensure(nsub*8) || c->sub_off.ensure(nsub*8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
           CU(cudaMemcpyAsync(c->sub_base.p,hb.data(),nsub*8,cudaMemcpyHostToDevice,c->st));
@@ -664,10 +666,10 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
           CompactParams cq = cp;
           cq.starts = (const u64 *) c->sub_s.p; cq.flags = (const u32 *) c->sub_f.p; cq.e_all = (const u32 *) c->sub_ea.p;
           cq.out_off = (const u64 *) c->sub_off.p; cq.nitems = (long long) nsub;
-          k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cq,(K *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
+          k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cq,(PK *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
           CU(cudaStreamSynchronize(c->st));       /* hb is about to go out of scope */
         }
-      k_build_index<NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const K *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
+      k_build_index<(NW == 3) ? 2 : NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const PK *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
       c->ptab_n = (long long) U; c->ptab_B = B;
     }
 
@@ -730,7 +732,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   res->ndistinct = (int64_t) hm.ndistinct;
   res->nkmers = (int64_t) ntot;
   c->last_ndist = (long long) hm.ndistinct;
-  c->res_nw = NW;
+  c->res_nw = (NW == 3) ? 2 : NW;
   return FKGPU_OK;
 }
 
@@ -908,9 +910,11 @@ static bool super_path_ok_k(int kmer)
 { static int forced = -1;
   if (forced < 0) { const char *e = getenv("FKGPU_PATH"); forced = e ? (strcmp(e,"records") == 0 ? 1 : (strcmp(e,"super") == 0 ? 2 : 0)) : 0; }
   if (forced == 1) return false;
-  return kmer >= 18 && kmer <= 56;
+  return kmer >= 18 && kmer <= FKGPU_MAX_K;
 }
 static bool super_path_ok(fkgpu_ctx *c) { return super_path_ok_k(c->cfg.kmer); }
+/*  words of a distinct entry: (key | count in the low 16 bits) fits two words up to k = 56; beyond, the count takes a third */
+static int entry_words(int kmer) { return kmer > 56 ? 3 : 2; }
 
 struct SuperCounters { u64 nrec, nkmers, nent; u32 fail, pad; };
 
@@ -981,7 +985,7 @@ static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S
  *  ranks (seqr/pbase, nranks > 1): the bucket kernel then gathers the bases from peer memory over NVLink.             */
 static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
                              const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase, const void *payload, void *wait_event,
-                             Key<2> *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
+                             void *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
 /*  entries below the table cutoff never leave the chip unless profiles need every count */
 { Misc *d_misc = (Misc *) c->misc.p;
   const int bbits = g.bbits;
@@ -1004,15 +1008,15 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     }
   stage_end(c,FKGPU_ST_SUPERPART);
 
-  /* groups of whole buckets, ~TS super-mers each */
-  static int bcvar = -1, tsv = 512;
+  /* groups of whole buckets, ~TS super-mers each (FKGPU_BC=old keeps the previous kernel for A/B runs) */
+  static int bcvar = -1, tsv = 224;
   if (bcvar < 0)
-    { const char *e = getenv("FKGPU_BC"); bcvar = e ? atoi(e) : 14;
+    { const char *e = getenv("FKGPU_BC"); bcvar = (e && strcmp(e,"old") == 0) ? 14 : 0;
       const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
     }
-  int gcv = 384;                                    /* super-mers per piece of the chosen kernel geometry */
-  switch (bcvar) { case 14: gcv = 256; break; default: gcv = 384; }
-  const u32 TS = (u32) std::min(tsv,gcv);
+  const bool wide = entry_words(g.k) == 3;
+  if (wide) bcvar = 0;
+  const u32 TS = (u32) ((bcvar == 0) ? std::min(tsv,8192) : std::min(tsv,256));
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -1034,6 +1038,23 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(g.k,km);
+    const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
+    if (bcvar == 0)
+      { /* persistent CTAs: one resident wave, groups dealt round-robin */
+#define BK_LAUNCH(KWV,PAYV,WIDEV) do { \
+          CU(cudaFuncSetAttribute(k_bucket_count2<KWV,PAYV,WIDEV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) BK_SMEM)); \
+          int occ = 0; \
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_bucket_count2<KWV,PAYV,WIDEV>,BK_TPB,BK_SMEM)); \
+          const long long grid = std::max<long long>(1,std::min<long long>(gmax,(long long) c->sms * std::max(1,occ))); \
+          k_bucket_count2<KWV,PAYV,WIDEV><<<(unsigned) grid,BK_TPB,BK_SMEM,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
+#define BK_LAUNCH_P(KWV,WIDEV) do { if (payload != NULL) BK_LAUNCH(KWV,true,WIDEV); else BK_LAUNCH(KWV,false,WIDEV); } while (0)
+        if (kw == 2) BK_LAUNCH_P(2,false);
+        else if (kw == 3) BK_LAUNCH_P(3,false);
+        else if (wide) BK_LAUNCH_P(4,true);
+        else BK_LAUNCH_P(4,false);
+      }
+    else
+      {
 #define BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,PAYV) do { \
       const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
       CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL,KWV,PAYV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
@@ -1042,9 +1063,8 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
       if (payload != NULL) BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,true); else BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,false); } while (0)
 #define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
       if (kw == 2) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,2); else if (kw == 3) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,3); else BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,4); } while (0)
-    const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
-    if (bcvar == 14) BC_LAUNCH(256,256,512,512,1024);
-    else BC_LAUNCH(512,384,768,1024,2048);
+        BC_LAUNCH(256,256,512,512,1024);
+      }
   }
   stage_end(c,FKGPU_ST_BUCKET);
   CU(cudaMemcpyAsync(hc,d_cnt,sizeof(*hc),cudaMemcpyDeviceToHost,c->st));
@@ -1058,7 +1078,8 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
 
 /*  stage C: U distinct (key | count in the low 16 bits) entries in `ent` -> key order -> table.  The record pipeline in
  *  weighted mode; `ent` is consumed (second sort buffer), `other` holds U + 4 entries.                               */
-static int entries_sort_stage(fkgpu_ctx *c, void *ent, void *other, long long U, int fetch_table, fkgpu_result *res)
+template<int EW>
+static int entries_sort_stage_t(fkgpu_ctx *c, void *ent, void *other, long long U, int fetch_table, fkgpu_result *res)
 { Misc *d_misc = (Misc *) c->misc.p;
   int q1, q2;
   choose_levels(U,&q1,&q2);
@@ -1068,22 +1089,27 @@ static int entries_sort_stage(fkgpu_ctx *c, void *ent, void *other, long long U,
   CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (n1 + 1) * 8,c->st));
   CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
   const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
-  const long long nt = (U + TP_TILE(2) - 1) / TP_TILE(2);
+  const long long nt = (U + TP_TILE(EW) - 1) / TP_TILE(EW);
   stage_begin(c,FKGPU_ST_ENTPART);
   if (nt > 0)
-    { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) ent,NULL,(u64) U,q1,(u64 *) c->hist1.p); KCHECK(); }
+    { k_tilepart<EW,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<EW> *) ent,NULL,(u64) U,q1,(u64 *) c->hist1.p); KCHECK(); }
   k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,n1); KCHECK();
   int rc = choose_p2(c,q1,&q2);
   if (rc) return rc;
   if (nt > 0)
-    { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-      k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) ent,(Key<2> *) other,(u64) U,q1,(u64 *) c->cur1.p); KCHECK();
+    { CU(cudaFuncSetAttribute(k_tilepart<EW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<EW,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<EW> *) ent,(Key<EW> *) other,(u64) U,q1,(u64 *) c->cur1.p); KCHECK();
     }
   stage_end(c,FKGPU_ST_ENTPART);
   c->weighted = 1;
-  rc = count_from_level1<2>(c,std::max<long long>(U,1),q1,q2,fetch_table,res,other,ent);
+  rc = count_from_level1<EW>(c,std::max<long long>(U,1),q1,q2,fetch_table,res,other,ent);
   c->weighted = 0;
   return rc;
+}
+
+static int entries_sort_stage(fkgpu_ctx *c, void *ent, void *other, long long U, int fetch_table, fkgpu_result *res)
+{ return entry_words(c->cfg.kmer) == 3 ? entries_sort_stage_t<3>(c,ent,other,U,fetch_table,res)
+                                       : entries_sort_stage_t<2>(c,ent,other,U,fetch_table,res);
 }
 
 /*  layout of the super-mer staging inside record buffer A (free until the final sort), for a buffer sized for nub positions */
@@ -1106,7 +1132,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   *fell_back = false;
   int rc;
   if (!prescanned)
-    { rc = prepare_common(c,nub,std::max(g.P1,1),true,2);
+    { rc = prepare_common(c,nub,std::max(g.P1,1),true,entry_words(c->cfg.kmer));
       if (rc) return rc;
       if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
     }
@@ -1132,7 +1158,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   Misc hm;
   long long gmax = 0;
-  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,NULL,NULL,want_entries ? (Key<2> *) c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
+  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,NULL,NULL,want_entries ? c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   static int verbose = -1;
   if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
@@ -1186,7 +1212,7 @@ static int stream_begin(fkgpu_ctx *c)
   const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0;
   if (scan)
     { c->sgeom = super_geom(c->cfg.kmer,cap);
-      ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,2) == 0) && !c->segs.ensure(sizeof(SuperCounters));
+      ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,entry_words(c->cfg.kmer)) == 0) && !c->segs.ensure(sizeof(SuperCounters));
     }
   if (!ok)
     { c->ascii.release(); c->seq.release(); c->val.release(); c->bufA.release(); c->bufB.release();
@@ -1445,7 +1471,7 @@ extern "C" int fkgpu_super_scan(fkgpu_ctx *c, const uint32_t *d_seq, const uint3
 { if (c == NULL || d_records == NULL || nrecords == NULL || nkmers == NULL || d_bucket_hist == NULL || d_bucket_offsets == NULL
       || hist_bits == NULL || npos < 0 || (npos > 0 && (d_seq == NULL || d_val == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_scan: bad argument");
-  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: k = %d is outside the super-mer path (18..64)",c->cfg.kmer);
   if (pos_offset + npos > npos_total || super_geom(c->cfg.kmer,npos_total).pbits > 64 - SUP_LBITS - 1)
     return set_err(FKGPU_E_ARG,"fkgpu_super_scan: positions [%lld,%lld) do not fit the declared total of %lld",(long long) pos_offset,
                    (long long) (pos_offset + npos),(long long) npos_total);
@@ -1487,7 +1513,7 @@ extern "C" int fkgpu_super_payload(fkgpu_ctx *c, const uint32_t *d_seq, int64_t 
                                    const uint64_t *d_records, int64_t nrecords, void *d_payload)
 { if (c == NULL || nrecords < 0 || (nrecords > 0 && (d_seq == NULL || d_records == NULL || d_payload == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_payload: bad argument");
-  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_payload: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_payload: k = %d is outside the super-mer path (18..64)",c->cfg.kmer);
   CU(cudaSetDevice(c->cfg.device));
   const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
   if (nrecords > 0)
@@ -1505,7 +1531,7 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
       || (d_payload == NULL && (nranks < 1 || nranks > SUP_MAXRANKS || seq_of_rank == NULL || pos_base == NULL))
       || (want_entries && (d_entries == NULL || nentries == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_count: bad argument");
-  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_count: k = %d is outside the super-mer path (18..56)",c->cfg.kmer);
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_count: k = %d is outside the super-mer path (18..64)",c->cfg.kmer);
   CU(cudaSetDevice(c->cfg.device));
   init_result(c,res);
   const SuperGeom g = super_geom(c->cfg.kmer,npos_total);
@@ -1523,10 +1549,10 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
     { k_sum_lengths<<<c->sms * 4,256,0,c->st>>>((const u64 *) d_records,(long long) nrecords,super_geom(c->cfg.kmer,npos_total).pbits,(u64 *) c->bsum.p); KCHECK(); }
   CU(cudaMemcpyAsync(&nk,c->bsum.p,8,cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
-  Key<2> *ent = NULL;
+  void *ent = NULL;
   if (want_entries)
-    { if (c->bufB.ensure((size_t) (nk + 4) * 16)) return set_err(FKGPU_E_NOMEM,"out of device memory (entries of %llu k-mers)",nk);
-      ent = (Key<2> *) c->bufB.p;
+    { if (c->bufB.ensure((size_t) (nk + 4) * 8 * entry_words(c->cfg.kmer))) return set_err(FKGPU_E_NOMEM,"out of device memory (entries of %llu k-mers)",nk);
+      ent = c->bufB.p;
     }
   const u32 *seqr[SUP_MAXRANKS]; u64 pb[SUP_MAXRANKS];
   for (int r = 0; r < SUP_MAXRANKS; r++)
@@ -1555,25 +1581,33 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
   return FKGPU_OK;
 }
 
+template<int EW>
+static int entries_partition_t(fkgpu_ctx *c, const void *d_entries, int64_t n, int bits, void *d_out, uint64_t *d_hist, uint64_t *d_offsets)
+{ const int n1 = 1 << bits;
+  if (c->cur1.ensure((size_t) (n1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (cursors)");
+  const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
+  const long long nt = (n + TP_TILE(EW) - 1) / TP_TILE(EW);
+  CU(cudaMemsetAsync(d_hist,0,(size_t) n1 * 8,c->st));
+  if (nt > 0)
+    { k_tilepart<EW,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<EW> *) d_entries,NULL,(u64) n,bits,(u64 *) d_hist); KCHECK(); }
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) c->cur1.p,n1); KCHECK();
+  if (nt > 0)
+    { CU(cudaFuncSetAttribute(k_tilepart<EW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+      k_tilepart<EW,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<EW> *) d_entries,(Key<EW> *) d_out,(u64) n,bits,(u64 *) c->cur1.p); KCHECK();
+    }
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_entry_bytes(int kmer) { return 8 * entry_words(kmer); }
+
 extern "C" int fkgpu_entries_partition(fkgpu_ctx *c, const void *d_entries, int64_t n, int bits, void *d_out,
                                        uint64_t *d_hist, uint64_t *d_offsets)
 { if (c == NULL || n < 0 || (n > 0 && (d_entries == NULL || d_out == NULL)) || d_hist == NULL || d_offsets == NULL || bits < 0 || bits > 11)
     return set_err(FKGPU_E_ARG,"fkgpu_entries_partition: bad argument");
   CU(cudaSetDevice(c->cfg.device));
-  const int n1 = 1 << bits;
-  if (c->cur1.ensure((size_t) (n1 + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (cursors)");
-  const size_t smh = (size_t) (n1 + (n1 & 1)) * 4, sms = smh + (size_t) n1 * 8;
-  const long long nt = (n + TP_TILE(2) - 1) / TP_TILE(2);
-  CU(cudaMemsetAsync(d_hist,0,(size_t) n1 * 8,c->st));
-  if (nt > 0)
-    { k_tilepart<2,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<2> *) d_entries,NULL,(u64) n,bits,(u64 *) d_hist); KCHECK(); }
-  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) d_hist,(u64 *) d_offsets,(u64 *) c->cur1.p,n1); KCHECK();
-  if (nt > 0)
-    { CU(cudaFuncSetAttribute(k_tilepart<2,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
-      k_tilepart<2,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<2> *) d_entries,(Key<2> *) d_out,(u64) n,bits,(u64 *) c->cur1.p); KCHECK();
-    }
-  CU(cudaStreamSynchronize(c->st));
-  return FKGPU_OK;
+  return entry_words(c->cfg.kmer) == 3 ? entries_partition_t<3>(c,d_entries,n,bits,d_out,d_hist,d_offsets)
+                                       : entries_partition_t<2>(c,d_entries,n,bits,d_out,d_hist,d_offsets);
 }
 
 extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int fetch_table, fkgpu_result *res)
@@ -1582,7 +1616,7 @@ extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int 
   init_result(c,res);
   int rc = prepare_small(c,1);
   if (rc) return rc;
-  if (c->bufA.ensure((size_t) (n + 4) * 16)) return set_err(FKGPU_E_NOMEM,"out of device memory (entry sort buffer)");
+  if (c->bufA.ensure((size_t) (n + 4) * 8 * entry_words(c->cfg.kmer))) return set_err(FKGPU_E_NOMEM,"out of device memory (entry sort buffer)");
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
   rc = entries_sort_stage(c,d_entries,c->bufA.p,(long long) n,fetch_table,res);
   if (rc) return rc;

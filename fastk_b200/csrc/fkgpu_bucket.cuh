@@ -1,0 +1,253 @@
+/*  fkgpu_bucket.cuh -- k_bucket_count: on-chip expansion + hash count of whole minimizer buckets (sm_100a).
+ *
+ *  Replaces, for the k-mers of one bucket group, the reference's  supermer_list_thread -> Supermer_Sort -> kmer_list_thread
+ *  -> Weighted_Kmer_Sort / hist_kmers  chain (count.c:165-313, MSDsort.c:458-489, count.c:339-542, MSDsort.c:491-544):
+ *  every instance of a canonical k-mer lives in one bucket, so a bucket group is counted completely inside one CTA.
+ *
+ *  Persistent CTAs walk the work groups (whole buckets, ~BK_T super-mers).  Per group and hash class:
+ *    load     every warp owns an equal slice of the group's super-mer records (<= 32 per piece, one per lane): the lane
+ *             gathers its super-mer's bases from the resident packed reads (or a peer's HBM / the exchanged payload) and
+ *             parks them left-aligned in the warp's own rows of shared memory -- no block barrier, only __syncwarp
+ *    expand   the warp's k-mer instances are dealt out 32 per round, ONE PER LANE: the lane finds its (super-mer, offset)
+ *             from a warp prefix sum of the lengths with one REDUX.OR + popc + shuffle, cuts both strands out of the row
+ *             (funnel shifts) and takes the smaller -- no per-thread binary search, no rolling state, no divergence at
+ *             super-mer boundaries
+ *    count    open-addressing table in shared memory: slot word = [16-bit fingerprint | key index + 1]; the distinct
+ *             keys live in SoA arrays k0[] / k1[] with their counts in cnt[]; a probe compares the fingerprint before it
+ *             touches the key, a first occurrence claims the slot with one CAS
+ *    emit     histogram contributions (CTA-private small histogram, flushed once per CTA), max_inst, and the distinct
+ *             (key | saturated count) entries with count >= the table cutoff, appended at ONE global atomic per class
+ *  A class whose distinct keys overflow the pool (or whose probes run long) is split in two residue classes of the key
+ *  hash and redone (binary tree walked without a stack).                                                             */
+#pragma once
+#include "fkgpu_kernels.cuh"
+
+namespace fk {
+
+#define BK_TPB    256
+#define BK_WARPS  (BK_TPB/32)
+#define BK_GC     (BK_WARPS*32)      /* super-mers per piece: one per lane                                   */
+#define BK_DC     1024               /* distinct keys a class may hold                                       */
+#define BK_TS     2048               /* slots (load <= 0.5)                                                   */
+#define BK_ROW    8                  /* 32-bit words of a super-mer's base string (<= 64 + k - 1 <= 127 bases) */
+#define BK_PROBE  96                 /* probe steps after which a class is split rather than ground through   */
+#define BK_MAXR   4096               /* most residue classes a group is split into                            */
+
+#define BK_SMEM   ((size_t) BK_DC*8*2 + (size_t) BK_DC*4 + (size_t) BK_TS*4 + (size_t) BK_GC*BK_ROW*4)
+
+template<int KW, bool PAY, bool WIDE>
+__global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 klast)
+{ static_assert(KW >= 2 && KW <= 4 && (!WIDE || KW == 4) && BK_DC < 65535 && BK_TS >= 2*BK_DC,"bucket kernel geometry");
+  typedef Key<WIDE ? 3 : 2> Entry;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  u64 *k0    = (u64 *) s_raw;                           /* [BK_DC] key bits 127..64                    */
+  u64 *k1    = k0 + BK_DC;                              /* [BK_DC] key bits 63..0 (unused when KW == 2) */
+  u32 *cnt   = (u32 *) (k1 + BK_DC);                    /* [BK_DC] instances of key i                   */
+  u32 *slot  = cnt + BK_DC;                             /* [BK_TS] 0 = empty, else (fp << 16) | (i + 1) */
+  u32 *sbase = slot + BK_TS;                            /* [BK_GC][BK_ROW] base strings, row = warp*32 + lane */
+  __shared__ u32 s_hist[SC_SMALLHIST], s_nkeys, s_ovf, s_wsum[BK_WARPS], s_woff[BK_WARPS];
+  __shared__ u64 s_ebase;
+
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u64 pmask = (1ull << p.pbits) - 1ull;
+  Entry *ent = (Entry *) p.ent;
+  u64 ndist = 0;                                        /* thread 0: distinct keys seen by this CTA     */
+
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BK_TPB) s_hist[i] = 0;
+  for (u32 i = threadIdx.x; i < BK_DC; i += BK_TPB) cnt[i] = 0;
+
+  for (long long g = blockIdx.x; g < p.nitems; g += gridDim.x)
+    { const u64 r0 = p.starts[g], r1 = p.ends[g];
+      if (r1 <= r0) continue;
+      u32 R = 1, rd = 0;                                /* current hash class: keys with ((h >> 20) & (R-1)) == rd */
+      for (;;)
+        { /* ---- clear ---- */
+          { uint4 *s4 = (uint4 *) slot;
+            const uint4 z = make_uint4(0,0,0,0);
+#pragma unroll
+            for (u32 i = 0; i < BK_TS/4/BK_TPB; i++) s4[threadIdx.x + i*BK_TPB] = z;
+          }
+          if (threadIdx.x == 0) { s_nkeys = 0; s_ovf = 0; }
+          __syncthreads();
+
+          /* ---- load + expand + count: warps are independent ---- */
+          u32 spare = 0xffffffffu;                      /* a key index this thread allocated and has not used yet */
+          for (u64 q0 = r0; q0 < r1; q0 += BK_GC)
+            { if (*(volatile u32 *) &s_ovf) break;
+              const u32 ns  = (u32) ((r1 - q0 < (u64) BK_GC) ? (r1 - q0) : (u64) BK_GC);
+              const u32 per = (ns + BK_WARPS - 1) / BK_WARPS;           /* <= 32 super-mers for each warp */
+              const u32 w0  = warp * per;
+              const u32 nw_ = (w0 < ns) ? ((ns - w0 < per) ? (ns - w0) : per) : 0u;
+              u32 *rows = sbase + (warp*32)*BK_ROW;
+              u32 l = 0;
+              if (lane < nw_)
+                { const u64 sm = p.recs[q0 + w0 + lane];
+                  l = (u32) ((sm >> p.pbits) & 63u) + 1u;
+                  u64 ps = sm & pmask;
+                  uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
+                  if (PAY)
+                    { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
+                  else
+                    { const u32 *sq = p.seq;
+                      if (p.nranks > 1)
+                        { int r = 0;                    /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
+#pragma unroll 1
+                          for (int q = 1; q < p.nranks; q++)
+                            if (ps >= p.pbase[q]) r = q;
+                          ps -= p.pbase[r]; sq = p.seqr[r];
+                        }
+                      const u32 *gp = sq + (ps >> 4);
+                      const int sh = 2*(int) (ps & 15ull);
+                      const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
+                      u32 x[9];
+#pragma unroll
+                      for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
+                      d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
+                                         __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
+                      d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
+                                         __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
+                    }
+                }
+              /* warp prefix of the lengths: instance x of the warp belongs to the super-mer i with pre[i] <= x < pre[i] + l[i] */
+              u32 incl = l;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1)
+                { const u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+                  if ((int) lane >= o) incl += y;
+                }
+              const u32 T   = __shfl_sync(0xffffffffu,incl,31);
+              const u32 pre = incl - l;
+              __syncwarp();
+              u32 before = 0;                           /* super-mers that start before the window */
+              for (u32 g0 = 0; g0 < T; g0 += 32)
+                { const u32 rel = pre - g0;
+                  const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
+                  const u32 si  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;     /* my super-mer (lane that loaded it) */
+                  before += __popc(m);
+                  const u32 ps_ = __shfl_sync(0xffffffffu,pre,si & 31u);
+                  if (g0 + lane < T)
+                    { const u32 j = g0 + lane - ps_;
+                      u32 F[KW], G[KW];
+                      supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
+                      const Key<2> key = strands_canon<KW>(F,G);
+                      const u32 h = bucket_hash<KW>(key);
+                      if (((h >> 20) & (R-1)) == rd)
+                        { const u32 fp = h & 0xffff0000u;
+                          u32 x = h & (BK_TS-1);
+                          for (u32 step = 0; ; step++)
+                            { if (step >= BK_PROBE) { s_ovf = 1; break; }
+                              u32 v = ((volatile u32 *) slot)[x];
+                              if (v == 0u)
+                                { if (spare == 0xffffffffu)
+                                    { spare = atomicAdd(&s_nkeys,1u);
+                                      if (spare >= BK_DC) { s_ovf = 1; spare = 0xffffffffu; break; }
+                                    }
+                                  k0[spare] = key.w[0];
+                                  if (KW > 2) k1[spare] = key.w[1];
+                                  __threadfence_block();
+                                  const u32 old = atomicCAS(&slot[x],0u,fp | (spare + 1u));
+                                  if (old == 0u) { atomicAdd(&cnt[spare],1u); spare = 0xffffffffu; break; }
+                                  v = old;
+                                }
+                              if ((v & 0xffff0000u) == fp)
+                                { const u32 ki = (v & 0xffffu) - 1u;
+                                  bool eq = (((volatile u64 *) k0)[ki] == key.w[0]);
+                                  if (KW > 2) eq = eq && (((volatile u64 *) k1)[ki] == key.w[1]);
+                                  if (eq) { atomicAdd(&cnt[ki],1u); break; }
+                                }
+                              x = (x+1) & (BK_TS-1);
+                            }
+                        }
+                    }
+                }
+              __syncwarp();                             /* every lane is done with the rows before the next piece overwrites them */
+            }
+          __syncthreads();
+          const u32 nk = (s_nkeys < (u32) BK_DC) ? s_nkeys : (u32) BK_DC;
+          if (s_ovf)
+            { /* split the class: forget what was counted, descend to the left child (2R, rd) */
+              for (u32 i = threadIdx.x; i < nk; i += BK_TPB) cnt[i] = 0;
+              if (R >= BK_MAXR)
+                { if (threadIdx.x == 0) atomicAdd(p.g_fail,1u);
+                  __syncthreads();
+                  break;
+                }
+              if (threadIdx.x == 0) atomicAdd(p.g_fail + 1,1u);          /* statistics: classes split after an overflow */
+              R <<= 1;
+              __syncthreads();
+              continue;
+            }
+
+          /* ---- emit this class: histogram, max_inst, distinct entries ---- */
+          u32 cv[BK_DC/BK_TPB];
+          u32 mine = 0;                                 /* (# real keys << 16) | # emitted entries; both <= BK_DC/BK_TPB per thread */
+#pragma unroll
+          for (u32 u = 0; u < BK_DC/BK_TPB; u++)
+            { const u32 i = u*BK_TPB + threadIdx.x;
+              u32 c = 0;
+              if (i < nk) { c = cnt[i]; cnt[i] = 0; }
+              cv[u] = c;
+              if (c != 0u)
+                { const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
+                  if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
+                  else atomicAdd(p.g_hist + cs,1ull);
+                  if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
+                  mine += 0x10000u + ((ent != NULL && cs >= p.ent_min) ? 1u : 0u);
+                }
+            }
+          u32 wtot = mine;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xffffffffu,wtot,o);
+          if (lane == 0) s_wsum[warp] = wtot;
+          __syncthreads();
+          if (threadIdx.x == 0)
+            { u32 run = 0, real = 0;
+#pragma unroll
+              for (int w = 0; w < BK_WARPS; w++)
+                { const u32 x = s_wsum[w];
+                  s_woff[w] = run; run += x & 0xffffu; real += x >> 16;
+                }
+              ndist += real;
+              s_ebase = run ? atomicAdd(p.ent_counter,(u64) run) : 0ull;
+            }
+          __syncthreads();
+          if (ent != NULL && (wtot & 0xffffu))
+            { u64 at = s_ebase + s_woff[warp];
+#pragma unroll
+              for (u32 u = 0; u < BK_DC/BK_TPB; u++)
+                { const u32 c  = cv[u];
+                  const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
+                  const bool em = (c != 0u) && (cs >= p.ent_min);
+                  const u32 b = __ballot_sync(0xffffffffu,em);
+                  if (em)
+                    { const u64 o = at + __popc(b & ((1u << lane) - 1u));
+                      if (o < p.ent_cap)
+                        { const u32 i = u*BK_TPB + threadIdx.x;
+                          Entry e;
+                          e.w[0] = k0[i];
+                          if (WIDE) { e.w[1] = k1[i]; e.w[WIDE ? 2 : 1] = (u64) cs; }
+                          else e.w[1] = ((KW > 2) ? k1[i] : 0ull) | (u64) cs;
+                          ent[o] = e;
+                        }
+                    }
+                  at += __popc(b);
+                }
+            }
+          /* ---- next class: right sibling of the nearest ancestor-or-self that is a left child ---- */
+          while (R > 1 && rd >= (R >> 1)) { rd -= (R >> 1); R >>= 1; }
+          if (R == 1) break;
+          rd += (R >> 1);
+          __syncthreads();                              /* entries were read out of k0 / k1: the next class may overwrite them */
+        }
+      __syncthreads();
+    }
+
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BK_TPB)
+    { const u32 c = s_hist[i];
+      if (c) atomicAdd(p.g_hist + i,(u64) c);
+    }
+  if (threadIdx.x == 0 && ndist) atomicAdd(p.g_ndistinct,ndist);
+}
+
+}  // namespace fk

@@ -764,8 +764,8 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   u64     *srt   = (u64 *) (s_raw + p.srt_off);
 
   /* TMA bulk load of the item (16-byte granules) */
-  const u64 a0 = (NW == 1) ? (r0 & ~1ull) : r0;
-  const u64 a1 = (NW == 1) ? ((r1 + 1) & ~1ull) : r1;
+  const u64 a0 = (NW & 1) ? (r0 & ~1ull) : r0;
+  const u64 a1 = (NW & 1) ? ((r1 + 1) & ~1ull) : r1;
   const u32 shift = (u32) (r0 - a0);
   const u32 bytes = (u32) ((a1 - a0) * sizeof(Key<NW>));
   if (threadIdx.x == 0)
@@ -1327,7 +1327,7 @@ struct BucketParams
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
-    Key<2>    *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL)  */
+    void      *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL): Key<2> (key | count), or Key<3> (key, count) when k > 56 */
     u32        ent_min;                                  /* only entries with (saturated) count >= ent_min are emitted */
     u32       *g_fail;                                   /* set if a group could not be counted */
   };
@@ -1610,7 +1610,7 @@ __global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParam
               if (at < p.ent_cap)
                 { Key<2> e = pool[i];
                   e.w[1] |= (u64) cs;
-                  p.ent[at] = e;
+                  ((Key<2> *) p.ent)[at] = e;
                 }
             }
         }
@@ -1667,7 +1667,7 @@ __global__ void __launch_bounds__(256) k_sum_lengths(const u64 *recs, long long 
  *  turned into an indexed lookup.  Result: one u16 per read position (0 where no legal k-mer starts).  */
 
 template<int NW>
-__global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<NW> *keys, uint16_t *cnts)
+__global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<(NW == 3) ? 2 : NW> *keys, uint16_t *cnts)
 { const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
   for (long long g = (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < p.nitems; g += nwarps)
@@ -1678,7 +1678,11 @@ __global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<NW> *
       const u32 *cnt = p.stage_cnt + p.starts[g];
       const u64 o = p.out_off[g];
       for (u32 q = lane; q < D; q += 32)
-        { keys[o+q] = stage[q];
+        { const Key<NW> sk = stage[q];
+          Key<(NW == 3) ? 2 : NW> ok;
+#pragma unroll
+          for (int m = 0; m < ((NW == 3) ? 2 : NW); m++) ok.w[m] = sk.w[m];
+          keys[o+q] = ok;
           cnts[o+q] = (uint16_t) cnt[q];
         }
     }

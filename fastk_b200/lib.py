@@ -91,6 +91,8 @@ def load_library(path=None):
     u8p, pp = C.POINTER(C.c_uint8), C.POINTER(vp)
     lib.fkgpu_super_supported.argtypes = [C.c_int]
     lib.fkgpu_super_supported.restype = C.c_int
+    lib.fkgpu_entry_bytes.argtypes = [C.c_int]
+    lib.fkgpu_entry_bytes.restype = C.c_int
     lib.fkgpu_super_bucket_bits.argtypes = [C.c_int, i64]
     lib.fkgpu_super_bucket_bits.restype = C.c_int
     lib.fkgpu_reads_alloc.argtypes = [vp, i64, pp, pp]
@@ -121,7 +123,7 @@ EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "
            "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
-           "fkgpu_super_supported", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
+           "fkgpu_super_supported", "fkgpu_entry_bytes", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
            "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_payload", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort"]
 
 

@@ -1,6 +1,6 @@
 """Multi-GPU k-mer counting: one process per GPU.
 
-Super-mer path (k in 18..56, the default; `MultiGPUCounter._count_super`):
+Super-mer path (k in 18..64, the default; `MultiGPUCounter._count_super`):
   1. every rank scans ITS reads into 8-byte super-mer records [minimizer bucket | # k-mers | GLOBAL position]
      partitioned by bucket                                                          (fkgpu_super_scan, CUDA)
   2. all-reduce(sum) of the 2^11-bin bucket histogram; contiguous bucket ranges per rank by the cumulative-threshold
@@ -297,7 +297,7 @@ class MultiGPUCounter:
             nb2 = 1 << PREFIX_BITS
             e_hist = torch.zeros(nb2, dtype=torch.int64, device=dev)
             e_offs = torch.zeros(nb2 + 1, dtype=torch.int64, device=dev)
-            part = torch.empty((nent + 8, 2), dtype=torch.int64, device=dev)
+            part = torch.empty((nent + 8, eng.lib.fkgpu_entry_bytes(eng.k) // 8), dtype=torch.int64, device=dev)
             eng.entries_partition(ent_ptr, nent, PREFIX_BITS, part.data_ptr(), e_hist.data_ptr(), e_offs.data_ptr())
             g2 = e_hist.clone()
             dist.all_reduce(g2)

@@ -146,7 +146,7 @@ int  fkgpu_scatter_prefix(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t 
                           uint64_t *d_offsets);
 int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int fetch_table, fkgpu_result *res);
 
-/*  Multi-GPU stages of the super-mer path (k in 18..56; fastk_b200/multigpu.py drives them, one process per GPU).
+/*  Multi-GPU stages of the super-mer path (k in 18..64; fastk_b200/multigpu.py drives them, one process per GPU).
  *  A super-mer record is 8 bytes, [minimizer bucket : <= 22][# k-mers - 1 : 6][GLOBAL position of its first base : 36],
  *  where the global position space is the concatenation of every rank's packed read stream (rank r starts at
  *  pos_base[r]).  Ranks own contiguous bucket ranges; ONE all-to-all moves the 8-byte records (not the k-mers), and the
@@ -164,11 +164,12 @@ int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int 
  *                           fkgpu_super_count the bases are instead gathered from peer HBM inside the counting kernel
  *                           (measured: fine at 2 GPUs, collapses at 4 -- small random NVLink reads; FKGPU_MG=peer keeps it)
  *   fkgpu_super_count       received records (consumed; room for nrecords + 8) -> histogram / scalars in res and, if
- *                           want_entries, the distinct (16-byte key | count in the low 16 bits) entries on the device
+ *                           want_entries, the distinct entries (fkgpu_entry_bytes(k) each: 16-byte key | count in the low 16 bits, or 24 bytes key, count) on the device
  *   fkgpu_entries_partition entries -> d_out ordered by the top `bits` key bits; d_hist [2^bits], d_offsets [2^bits+1]
  *   fkgpu_entries_sort      distinct entries (consumed; room for n + 4) -> key order -> table in res               */
 #define FKGPU_IPC_HANDLE_BYTES 64
 int  fkgpu_super_supported(int kmer);
+int  fkgpu_entry_bytes(int kmer);            /* bytes of a distinct entry: 16 (key | count) up to k = 56, 24 (key, count) beyond */
 int  fkgpu_super_bucket_bits(int kmer, int64_t npos_total);
 int  fkgpu_reads_alloc(fkgpu_ctx *ctx, int64_t npos, uint32_t **d_seq, uint32_t **d_val);
 int  fkgpu_ipc_export(fkgpu_ctx *ctx, const void *d_ptr, uint8_t *handle /*[FKGPU_IPC_HANDLE_BYTES]*/);
@@ -204,7 +205,7 @@ int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double 
 #define FKGPU_ST_SORTCOUNT 5
 #define FKGPU_ST_COMPACT   6
 #define FKGPU_ST_PROFILE   7
-/* super-mer path (k in 18..56): stages 5/6 then only order the distinct entries */
+/* super-mer path (k in 18..64): stages 5/6 then only order the distinct entries */
 #define FKGPU_ST_SUPERSCAN 8     /* reads -> super-mer records                       */
 #define FKGPU_ST_SUPERPART 9     /* bucket partition of the super-mer records        */
 #define FKGPU_ST_BUCKET    10    /* on-chip expansion + hash count per bucket group  */

@@ -18,7 +18,7 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("k,path,env", [(40, "super-mer", {}), (21, "super-mer", {"FKGPU_MG": "payload"}), (40, "super-mer", {"FKGPU_MG": "peer"}),
-                                        (40, "records", {"FKGPU_MG": "records"}), (63, "records", {})])
+                                        (40, "records", {"FKGPU_MG": "records"}), (63, "super-mer", {}), (63, "records", {"FKGPU_MG": "records"})])
 def test_multi_gpu_equals_oracle(k, path, env):
     n = _ngpu()
     if n < 2:
@@ -31,7 +31,8 @@ def test_multi_gpu_equals_oracle(k, path, env):
 
 
 @pytest.mark.parametrize("k,path,env", [(40, "super-mer", {"FKGPU_MG": "payload"}), (50, "super-mer", {"FKGPU_MG": "peer"}),
-                                        (21, "super-mer", {"FKGPU_MG": "payload"}), (40, "records", {"FKGPU_MG": "records"})])
+                                        (21, "super-mer", {"FKGPU_MG": "payload"}), (40, "records", {"FKGPU_MG": "records"}),
+                                        (63, "super-mer", {"FKGPU_MG": "payload"}), (57, "super-mer", {"FKGPU_MG": "peer"})])
 def test_multi_gpu_stages_world1(k, path, env):
     """The same staged pipeline (scan -> exchange -> count -> entry exchange -> sort) with a world of ONE rank: runs on a
     single-GPU box, so every stage entry point of the multi-GPU path is parity-checked there too."""

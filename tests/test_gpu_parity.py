@@ -32,7 +32,7 @@ def check(oracle_lib, reads, k, cutoff=1, bc=0, nthreads=1, **kw):
     return got
 
 
-@pytest.mark.parametrize("k", [40, 21, 63, 32, 33, 64, 7])
+@pytest.mark.parametrize("k", [40, 21, 63, 32, 33, 64, 7, 17, 18, 48, 49, 56, 57])
 def test_config1_1k_reads(oracle_lib, k):
     genome = synth.random_genome(20_000, 11)
     reads = synth.sample_reads(genome, 1000, 150, 0.005, 12)
