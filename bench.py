@@ -61,6 +61,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference run: no cpu_baseline and NO parity check")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--mem-limit-gb", type=float, default=0.0, help="fkgpu_config.mem_limit (the host's -M): below the one-round "
+                    "working set the count takes several rounds")
+    ap.add_argument("--device-gen", action="store_true", help="generate the reads on the device chunk by chunk (batches too large "
+                    "to stage as ASCII on the host: no e2e arm, no FASTA, parity = invariants only)")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     for key in ("kmer", "genome_mbp", "coverage", "read_len", "sub_rate", "cutoff"):
@@ -202,6 +206,37 @@ def reference_arm(a, rank):
 
 # ----------------------------------------------------------------------------------------------------------
 
+def device_generate_packed(torch, dev, eng, a, rank, seq_ptr, val_ptr):
+    """same read model as synth.workload_rows, drawn with the device RNG and packed chunk by chunk (64 reads x n at a time:
+    a multiple of 64 positions, so every chunk starts on whole packed words)"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(a.seed + 7919 * rank)
+    G, L = a.genome_bp, a.read_len
+    genome = torch.randint(0, 4, (G,), dtype=torch.uint8, device=dev, generator=g)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ar = torch.arange(L, device=dev)
+    per = max(64, ((48 << 20) // (L + 1)) // 64 * 64)
+    pos = 0
+    for r0 in range(0, a.nreads, per):
+        n = min(per, a.nreads - r0)
+        st = torch.randint(0, G - L + 1, (n,), device=dev, generator=g)
+        r = genome[(st[:, None] + ar[None, :])]
+        if a.sub_rate > 0:
+            m = torch.rand((n, L), device=dev, generator=g) < a.sub_rate
+            add = torch.randint(1, 4, (n, L), dtype=torch.uint8, device=dev, generator=g)
+            r = torch.where(m, (r + add) % 4, r)
+        flip = torch.rand((n,), device=dev, generator=g) < 0.5
+        r = torch.where(flip[:, None], (3 - r).flip(1), r)
+        blk = torch.zeros((n * (L + 1) + 64,), dtype=torch.uint8, device=dev)
+        blk[:n * (L + 1)].view(n, L + 1)[:, :L] = lut[r.long()]
+        assert pos % 64 == 0
+        eng.pack_ascii_dev(blk.data_ptr(), n * (L + 1), seq_ptr + (pos // 16) * 4, val_ptr + (pos // 32) * 4)
+        torch.cuda.synchronize()
+        pos += n * (L + 1)
+        del r, m, add, blk
+    return pos
+
+
 def invariants(res_hist, max_inst, nkmers, ndistinct):
     """size-independent properties of any correct count: sum of the histogram = distinct k-mers; sum of c * hist[c]
     below saturation + max_inst = k-mer instances"""
@@ -247,11 +282,16 @@ def main():
     npos = nreads * (L + 1)
 
     # ---- the batch: rank r's reads in pinned host memory (DATA_BLOCK layout), then ASCII on the device -> packed
-    host_ascii = torch.empty((nreads, L + 1), dtype=torch.uint8, pin_memory=True)
-    make_rows(a, rank, out=host_ascii.numpy())
-    ascii_dev = host_ascii.to(dev, non_blocking=True)
+    host_ascii = None
+    if not a.device_gen:
+        host_ascii = torch.empty((nreads, L + 1), dtype=torch.uint8, pin_memory=True)
+        make_rows(a, rank, out=host_ascii.numpy())
+        ascii_dev = host_ascii.to(dev, non_blocking=True)
+    else:
+        a.no_e2e, a.no_cpu = True, True
     nthr = a.ingest_threads or max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
-    eng = FastKGPU(k=k, table_cutoff=a.cutoff, profile=a.profile, device=local, nthreads=nthr, reserve_bases=npos)
+    eng = FastKGPU(k=k, table_cutoff=a.cutoff, profile=a.profile, device=local, nthreads=nthr,
+                   reserve_bases=0 if a.device_gen else npos, mem_limit=int(a.mem_limit_gb * (1 << 30)))
     runner = None
     if world > 1:
         # packed reads live in library-owned buffers that every peer maps over CUDA IPC (NVLink gathers in the count kernel)
@@ -263,9 +303,12 @@ def main():
         d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
         d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
         seq_ptr, val_ptr = d_seq.data_ptr(), d_val.data_ptr()
-    eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, seq_ptr, val_ptr)
-    torch.cuda.synchronize()
-    del ascii_dev
+    if not a.device_gen:
+        eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, seq_ptr, val_ptr)
+        torch.cuda.synchronize()
+        del ascii_dev
+    else:
+        device_generate_packed(torch, dev, eng, a, rank, seq_ptr, val_ptr)
     torch.cuda.empty_cache()
 
     want_table = a.cutoff > 0
@@ -374,7 +417,7 @@ def main():
 
     # ---- parity against the reference FastK on the FASTA of rank 0's reads, and the CPU baseline (the same run) --------
     cpu, parity = None, {"checked": False}
-    if not a.no_cpu and ref_binary() is not None:
+    if not a.no_cpu and ref_binary() is not None and host_ascii is not None:
         tmpdir = scratch_dir("fastk_cpu_") if rank == 0 else None
         try:
             if rank == 0:
@@ -388,7 +431,7 @@ def main():
                            "sample": sample_text(a, used, f", one run, {t:.1f} s wall; FASTA parse and file writes included")}
             if world == 1:
                 got = r2 if r2 is not None else eng.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
-                table = got.view_table() if want_table else None
+                table = (got.merged_runs() if got.nruns > 1 else got.view_table()) if want_table else None
                 ghist, gmax = got.hist, got.max_inst
                 via = "fkgpu_ingest/fkgpu_finish (the e2e arm's last step)" if r2 is not None else "fkgpu_count_packed"
             else:
@@ -451,7 +494,7 @@ def main():
     else:
         # rank 0's share of the job: its own stage times against its own record / entry counts
         st = dict(path=1 if res.path == "super-mer" else 0, supermers=getattr(res, "supermers", 0),
-                  entries=getattr(res, "entries", 0), groups=0)
+                  entries=getattr(res, "entries", 0), groups=0, rounds=1)
         N, U = N // world, U // world
     ntab = res.ntable // world
     if st["path"] == 1:
@@ -474,6 +517,7 @@ def main():
                "refine": 3 * N * W,
                "sortcount": N * W + U * (W + 4),
                "compact": U * (W + 4) + ntab * (res.kmer_bytes + 2)}
+    stage_ms["super_partition"] = stage_ms.get("super_partition", 0.0) + stage_ms.pop("super_refine", 0.0)   # both levels
     per_stage = {}
     for s, b in alg.items():
         ms = stage_ms.get(s, 0.0) / a.steps
@@ -504,7 +548,9 @@ def main():
                 "config": {"workload": workload_name(a), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),
                            "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
-                           "supermer_records": st["supermers"],
+                           "supermer_records": st["supermers"], "rounds": st.get("rounds", 1), "sorted_runs": getattr(res, "nruns", 1),
+                           "split_classes": st.get("split_classes", 0), "spilled_kmers": st.get("spilled_kmers", 0),
+                           "mem_limit_gb": a.mem_limit_gb, "reads": "generated on the device" if a.device_gen else "host generator",
                            "timed_region": "packed reads resident in HBM -> sorted [key][count] table + histogram in pinned host memory",
                            "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),

@@ -63,6 +63,7 @@ struct PinBuf
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
   };
 
+#define FKGPU_D2H_CHUNKS 8          /* the table leaves the device in this many key ranges, each copied while the next is sorted */
 #define CHUNK_BYTES (8u << 20)         /* pinned staging chunk per ingest thread; also the granule of the streamed pack + scan */
 
 struct SuperGeom { int k, m, w, p2, bbits, P1, P2, pbits; };
@@ -90,6 +91,7 @@ struct fkgpu_ctx
     cudaStream_t st = nullptr, cst = nullptr;
     cudaEvent_t  ev[2*FKGPU_NSTAGES + 4];
     float        ms[FKGPU_NSTAGES];
+    float        ms_bank[FKGPU_NSTAGES];
     double       bytes[FKGPU_NSTAGES];
     bool         used[FKGPU_NSTAGES];
     long long    launches = 0;
@@ -116,6 +118,14 @@ struct fkgpu_ctx
     DevBuf ctah, ctao, seq, val, bufA, bufB, scnt, hist1, off1, cur1, off2, gstart, eall, epass, poff, bsum, ghist, misc, table;
     DevBuf segs, child, pcl, sub_s, sub_e, sub_f, sub_ea, sub_ep, sub_off, sub_par, sub_base, rstart_d, prof_d;
     PinBuf h_table, h_misc, h_prof, h_poff;
+    PinBuf      *h_out = nullptr;      /* where the table of the current sort goes (a run buffer of a multi-round count), default h_table */
+    std::vector<PinBuf *> h_runs;      /* pinned run buffers of multi-round counts (kept for re-use)                      */
+    std::vector<int64_t>  run_n;       /* result: records of every sorted run                                             */
+    std::vector<const uint8_t *> run_p;/* result: host pointer of every sorted run                                        */
+    DevBuf       bufC, roff1, l1k;     /* multi-round count: second entry buffer, record level-1 offsets, k-mers per level-1 bucket */
+    cudaEvent_t  ev_sorted[FKGPU_D2H_CHUNKS], ev_d2h = nullptr;
+    bool         d2h_pending = false;  /* a table copy on the copy stream still reads c->table                            */
+    long long    st_rounds = 0, st_split = 0, st_spill = 0;
     int64_t h_hist[FKGPU_HIST_BINS];
 
     /* profile lookup table built by finish when cfg.do_profile */
@@ -173,7 +183,10 @@ extern "C" int fkgpu_create(const fkgpu_config *cfg, fkgpu_ctx **out)
   CU(cudaStreamCreateWithFlags(&c->st,cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->cst,cudaStreamNonBlocking));
   for (auto &e : c->ev) CU(cudaEventCreate(&e));
+  for (auto &e : c->ev_sorted) CU(cudaEventCreateWithFlags(&e,cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_d2h,cudaEventDisableTiming));
   memset(c->ms,0,sizeof(c->ms));
+  memset(c->ms_bank,0,sizeof(c->ms_bank));
   memset(c->bytes,0,sizeof(c->bytes));
   memset(c->used,0,sizeof(c->used));
   *out = c;
@@ -196,6 +209,10 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
                      &c->rstart_d,&c->prof_d,&c->eprof,&c->qoff,&c->pkeys,&c->pcnts,&c->pidx,&c->praw,&c->pout,&c->psrc,&c->pdst,&c->plen };
   for (auto b : bufs) b->release();
   c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
+  for (auto r : c->h_runs) { r->release(); delete r; }
+  c->bufC.release(); c->roff1.release(); c->l1k.release();
+  for (auto &e : c->ev_sorted) cudaEventDestroy(e);
+  if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
   for (auto &e : c->ev) cudaEventDestroy(e);
   if (c->st) cudaStreamDestroy(c->st);
   if (c->cst) cudaStreamDestroy(c->cst);
@@ -232,6 +249,7 @@ extern "C" int fkgpu_last_path(fkgpu_ctx *c) { return c ? c->last_path : 0; }
 extern "C" int fkgpu_last_stats(fkgpu_ctx *c, int64_t *v)
 { if (c == NULL || v == NULL) return set_err(FKGPU_E_ARG,"fkgpu_last_stats: NULL argument");
   v[0] = c->last_path; v[1] = c->st_super; v[2] = c->st_ent; v[3] = c->st_groups;
+  v[4] = c->st_rounds; v[5] = c->st_split; v[6] = c->st_spill; v[7] = 0;
   return FKGPU_OK;
 }
 
@@ -520,7 +538,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   sp.g_hist = (u64 *) c->ghist.p; sp.g_maxinst = &d_misc->maxinst; sp.g_ndistinct = &d_misc->ndistinct;
   if (c->segs.ensure((size_t) gmax * 4)) return set_err(FKGPU_E_NOMEM,"out of device memory (overflow list)");
   sp.ovf_cnt = &d_misc->ovf_cnt; sp.ovf_list = (u32 *) c->segs.p; sp.ovf_cap = (u32) std::min<long long>(gmax,0x7fffffffll);
-  sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax;
+  sp.cap = SC_CAP; sp.cutoff = (u32) std::max(1,c->cfg.do_table); sp.nitems = gmax; sp.item_base = 0;
   sp.tab_off = L.tab_off; sp.srt_off = L.srt_off; sp.srt2_off = L.srt2_off;
   sp.weighted = (u32) c->weighted;
   /* weighted + no profiles: every entry is distinct and already passed the cutoff in the bucket kernel, so entry i of
@@ -533,7 +551,39 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       sp.direct = (uint8_t *) c->table.p;
     }
   CU(cudaFuncSetAttribute(k_sortcount<NW>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) L.total));
-  k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK();
+  /* direct + fetch: entry i of the key order is table record i and their number is known (nub), so the table leaves the
+     device in FKGPU_D2H_CHUNKS key ranges, each copied on the copy stream while the next range is being sorted          */
+  PinBuf *hout = c->h_out ? c->h_out : &c->h_table;
+  bool d2h_chunked = false;
+  if (c->d2h_pending) { CU(cudaStreamWaitEvent(c->st,c->ev_d2h,0)); c->d2h_pending = false; }   /* c->table is about to be rewritten */
+  if (direct && fetch_table && (size_t) nub * twd >= ((size_t) 32 << 20))
+    { if (hout->ensure((size_t) nub * twd + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
+      long long gb[FKGPU_D2H_CHUNKS + 1];
+      u64 eb[FKGPU_D2H_CHUNKS + 1];
+      for (int q = 0; q <= FKGPU_D2H_CHUNKS; q++) gb[q] = gmax * q / FKGPU_D2H_CHUNKS;
+      for (int q = 0; q <= FKGPU_D2H_CHUNKS; q++)
+        CU(cudaMemcpyAsync(eb + q,gstart + gb[q],8,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      for (int q = 0; q < FKGPU_D2H_CHUNKS; q++)
+        { if (gb[q+1] > gb[q])
+            { SortCountParams sq = sp;
+              sq.starts = gstart + gb[q]; sq.ends = gstart + gb[q] + 1;
+              sq.e_all = sp.e_all + gb[q]; sq.e_pass = sp.e_pass + gb[q];
+              sq.nitems = gb[q+1] - gb[q]; sq.item_base = (u32) gb[q];
+              k_sortcount<NW><<<(unsigned) sq.nitems,SC_TPB,L.total,c->st>>>(sq); KCHECK();
+            }
+          CU(cudaEventRecord(c->ev_sorted[q],c->st));
+          CU(cudaStreamWaitEvent(c->cst,c->ev_sorted[q],0));
+          if (eb[q+1] > eb[q])
+            CU(cudaMemcpyAsync((uint8_t *) hout->p + eb[q] * twd,(const uint8_t *) c->table.p + eb[q] * twd,(size_t) (eb[q+1] - eb[q]) * twd,
+                               cudaMemcpyDeviceToHost,c->cst));
+        }
+      CU(cudaEventRecord(c->ev_d2h,c->cst));
+      c->d2h_pending = true;
+      d2h_chunked = true;
+    }
+  else
+    { k_sortcount<NW><<<(unsigned) gmax,SC_TPB,L.total,c->st>>>(sp); KCHECK(); }
   stage_end(c,FKGPU_ST_SORTCOUNT);
 
   /* first sync: overflow list + totals */
@@ -683,9 +733,12 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       res->ntable = (int64_t) ntot_d;
       res->table_dev = (const uint8_t *) c->table.p;
       if (fetch_table)
-        { if (c->h_table.ensure((size_t) ntot_d * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
-          CU(cudaMemcpyAsync(c->h_table.p,c->table.p,(size_t) ntot_d * tw,cudaMemcpyDeviceToHost,c->st));
-          res->table = (const uint8_t *) c->h_table.p;
+        { if (hout->ensure((size_t) ntot_d * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
+          if (!d2h_chunked || hm.ovf_cnt > 0)       /* oversize items were finished after their range had been copied: take it all again */
+            { if (c->d2h_pending) { CU(cudaStreamSynchronize(c->cst)); c->d2h_pending = false; }
+              CU(cudaMemcpyAsync(hout->p,c->table.p,(size_t) ntot_d * tw,cudaMemcpyDeviceToHost,c->st));
+            }
+          res->table = (const uint8_t *) hout->p;
         }
     }
   else if (c->cfg.do_table > 0)
@@ -715,9 +768,9 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       res->ntable = (int64_t) hm.total_pass;
       res->table_dev = (const uint8_t *) c->table.p;
       if (fetch_table)
-        { if (c->h_table.ensure((size_t) hm.total_pass * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
-          CU(cudaMemcpyAsync(c->h_table.p,c->table.p,(size_t) hm.total_pass * tw,cudaMemcpyDeviceToHost,c->st));
-          res->table = (const uint8_t *) c->h_table.p;
+        { if (hout->ensure((size_t) hm.total_pass * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (table)");
+          CU(cudaMemcpyAsync(hout->p,c->table.p,(size_t) hm.total_pass * tw,cudaMemcpyDeviceToHost,c->st));
+          res->table = (const uint8_t *) hout->p;
         }
     }
 
@@ -734,6 +787,24 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
   c->last_ndist = (long long) hm.ndistinct;
   c->res_nw = (NW == 3) ? 2 : NW;
   return FKGPU_OK;
+}
+
+/*  the table's last key ranges may still be crossing PCIe on the copy stream: order the compute stream behind them, so
+ *  that the end-of-count event (and the caller's synchronize) covers the whole table                                  */
+static int d2h_join(fkgpu_ctx *c)
+{ if (c->d2h_pending)
+    { CU(cudaStreamWaitEvent(c->st,c->ev_d2h,0));
+      c->d2h_pending = false;
+    }
+  return FKGPU_OK;
+}
+
+/*  result of a one-round count: the table is its own single run */
+static void single_run(fkgpu_ctx *c, fkgpu_result *res)
+{ c->run_n.assign(1,res->ntable);
+  c->run_p.assign(1,res->table);
+  res->nruns = 1; res->run_ntable = c->run_n.data(); res->run_table = c->run_p.data();
+  c->st_rounds = 1;
 }
 
 static void make_kmask(int k, u32 *km)
@@ -787,10 +858,26 @@ static int prepare_common(fkgpu_ctx *c, long long nub, int P1, bool needB = true
   return prepare_small(c,P1);
 }
 
+/*  a multi-round count re-uses the stage events every round: bank what the finished round measured (stream idle) */
+static void bank_times(fkgpu_ctx *c)
+{ for (int s = 0; s < FKGPU_NSTAGES; s++)
+    if (c->used[s])
+      { float t = 0;
+        if (cudaEventElapsedTime(&t,c->ev[2*s],c->ev[2*s+1]) == cudaSuccess) c->ms_bank[s] += t;
+        else cudaGetLastError();
+        c->used[s] = false;
+      }
+}
+
 static void collect_times(fkgpu_ctx *c, fkgpu_result *res)
 { for (int s = 0; s < FKGPU_NSTAGES; s++)
-    { c->ms[s] = 0;
-      if (c->used[s]) cudaEventElapsedTime(&c->ms[s],c->ev[2*s],c->ev[2*s+1]);
+    { c->ms[s] = c->ms_bank[s];
+      c->ms_bank[s] = 0;
+      if (c->used[s])
+        { float t = 0;
+          cudaEventElapsedTime(&t,c->ev[2*s],c->ev[2*s+1]);
+          c->ms[s] += t;
+        }
     }
   float tot = 0;
   cudaEventElapsedTime(&tot,c->ev[2*FKGPU_NSTAGES],c->ev[2*FKGPU_NSTAGES+1]);
@@ -896,6 +983,9 @@ static int count_packed_t(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long
   stage_end(c,FKGPU_ST_SCATTER);
   rc = count_from_level1<NW>(c,npos,P1,P2,fetch_table,res,c->bufA.p,c->bufB.p);
   if (rc) return rc;
+  rc = d2h_join(c);
+  if (rc) return rc;
+  single_run(c,res);
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
   collect_times(c,res);
@@ -982,41 +1072,42 @@ static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S
 /*  stage B: S super-mer records in `in` (consumed; `scratch` has room for S records too) -> bucket partition -> per-bucket
  *  on-chip expansion + hash count.  Histogram contributions go to c->ghist, scalars to d_misc / d_cnt, the distinct
  *  (key | count) entries to ent[0..ent_cap) when ent != NULL.  The records may point into the read streams of several
- *  ranks (seqr/pbase, nranks > 1): the bucket kernel then gathers the bases from peer memory over NVLink.             */
-static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
-                             const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase, const void *payload, void *wait_event,
-                             void *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
+ *  ranks (seqr/pbase, nranks > 1): the bucket kernel then gathers the bases from peer memory over NVLink.
+ *  super_bucket_range does this for the level-1 buckets [b0, b1) of records already partitioned on their top P1 bucket bits
+ *  (l1recs, starts off1[0..n1]); Sr >= the number of records in the range.  A round of a multi-round count is one call.   */
+static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1recs, Key<1> *l2recs, const u64 *off1, int b0, int b1, long long Sr,
+                              const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase, const void *payload, void *wait_event,
+                              void *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
 /*  entries below the table cutoff never leave the chip unless profiles need every count */
 { Misc *d_misc = (Misc *) c->misc.p;
   const int bbits = g.bbits;
-  stage_begin(c,FKGPU_ST_SUPERPART);
-  const int b1 = bbits ? g.P1 : 0;
-  const int n1 = 1 << b1;
-  int rc = super_level1(c,in,scratch,S,b1);
-  if (rc) return rc;
-  const u64 *offs = (const u64 *) c->off1.p;
-  const Key<1> *recs = scratch;
-  long long mbuckets = n1;
+  const int p1 = bbits ? g.P1 : 0;
+  const int nb = b1 - b0;
+  const long long S = Sr;
+  stage_begin(c,FKGPU_ST_SUPERREFINE);
+  const u64 *offs = off1 + b0;
+  const Key<1> *recs = l1recs;
+  long long mbuckets = nb;
   if (bbits && g.P2 > 0)
-    { mbuckets = (long long) n1 << g.P2;
+    { mbuckets = (long long) nb << g.P2;
       if (c->off2.ensure((size_t) (mbuckets + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
       const size_t sm = (size_t) REF_ST * REF_SLOT * sizeof(Key<1>) + (size_t) (1 << g.P2) * 4;
       CU(cudaFuncSetAttribute(k_refine<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm));
       CU(cudaMemsetAsync(&d_misc->ticket,0,4,c->st));
-      k_refine<1><<<std::min(n1,c->sms * 2),REF_TPB,sm,c->st>>>(scratch,in,(const u64 *) c->off1.p,n1,b1,g.P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
-      offs = (const u64 *) c->off2.p; recs = in;
+      k_refine<1><<<std::min(nb,c->sms * 2),REF_TPB,sm,c->st>>>(l1recs,l2recs,off1 + b0,nb,p1,g.P2,(u64 *) c->off2.p,&d_misc->ticket); KCHECK();
+      offs = (const u64 *) c->off2.p; recs = l2recs;
     }
-  stage_end(c,FKGPU_ST_SUPERPART);
+  stage_end(c,FKGPU_ST_SUPERREFINE);
 
   /* groups of whole buckets, ~TS super-mers each (FKGPU_BC=old keeps the previous kernel for A/B runs) */
   static int bcvar = -1, tsv = 224;
   if (bcvar < 0)
-    { const char *e = getenv("FKGPU_BC"); bcvar = (e && strcmp(e,"old") == 0) ? 14 : 0;
-      const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(16,atoi(f));
+    { const char *e = getenv("FKGPU_BC"); bcvar = (e && strcmp(e,"old") == 0) ? 14 : ((e && strcmp(e,"warp") == 0) ? 3 : 0);
+      const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(8,atoi(f)); else if (bcvar == 3) tsv = 32;
     }
   const bool wide = entry_words(g.k) == 3;
-  if (wide) bcvar = 0;
-  const u32 TS = (u32) ((bcvar == 0) ? std::min(tsv,8192) : std::min(tsv,256));
+  const int bcv = (wide && bcvar == 14) ? 0 : bcvar;
+  const u32 TS = (u32) ((bcv != 14) ? std::min(tsv,8192) : std::min(tsv,256));
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -1039,7 +1130,21 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
     bp.g_fail = &d_cnt->fail;
     u32 km[4]; make_kmask(g.k,km);
     const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
-    if (bcvar == 0)
+    if (bcv == 3)
+      { /* warp-private tables: a warp owns a group from load to emit */
+#define BW_LAUNCH(KWV,PAYV,WIDEV) do { \
+          CU(cudaFuncSetAttribute(k_bucket_count3<KWV,PAYV,WIDEV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) BW_SMEM)); \
+          int occ = 0; \
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_bucket_count3<KWV,PAYV,WIDEV>,BW_TPB,BW_SMEM)); \
+          const long long grid = std::max<long long>(1,std::min<long long>((gmax + BW_WARPS - 1) / BW_WARPS,(long long) c->sms * std::max(1,occ))); \
+          k_bucket_count3<KWV,PAYV,WIDEV><<<(unsigned) grid,BW_TPB,BW_SMEM,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
+#define BW_LAUNCH_P(KWV,WIDEV) do { if (payload != NULL) BW_LAUNCH(KWV,true,WIDEV); else BW_LAUNCH(KWV,false,WIDEV); } while (0)
+        if (kw == 2) BW_LAUNCH_P(2,false);
+        else if (kw == 3) BW_LAUNCH_P(3,false);
+        else if (wide) BW_LAUNCH_P(4,true);
+        else BW_LAUNCH_P(4,false);
+      }
+    else if (bcv == 0)
       { /* persistent CTAs: one resident wave, groups dealt round-robin */
 #define BK_LAUNCH(KWV,PAYV,WIDEV) do { \
           CU(cudaFuncSetAttribute(k_bucket_count2<KWV,PAYV,WIDEV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) BK_SMEM)); \
@@ -1074,6 +1179,18 @@ static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1
   if (ent != NULL && hc->nent > ent_cap) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow (%llu > %llu)",hc->nent,ent_cap);
   *ngroups = gmax;
   return FKGPU_OK;
+}
+
+
+static int super_count_stage(fkgpu_ctx *c, const SuperGeom &g, Key<1> *in, Key<1> *scratch, long long S,
+                             const u32 *d_seq, int nranks, const u32 *const *seqr, const u64 *pbase, const void *payload, void *wait_event,
+                             void *ent, u64 ent_cap, SuperCounters *d_cnt, SuperCounters *hc, Misc *hm, long long *ngroups)
+{ const int b1 = g.bbits ? g.P1 : 0;
+  stage_begin(c,FKGPU_ST_SUPERPART);
+  int rc = super_level1(c,in,scratch,S,b1);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERPART);
+  return super_bucket_range(c,g,scratch,in,(const u64 *) c->off1.p,0,1 << b1,S,d_seq,nranks,seqr,pbase,payload,wait_event,ent,ent_cap,d_cnt,hc,hm,ngroups);
 }
 
 /*  stage C: U distinct (key | count in the low 16 bits) entries in `ent` -> key order -> table.  The record pipeline in
@@ -1158,7 +1275,15 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = (c->cfg.do_table > 0) || c->cfg.do_profile;
   Misc hm;
   long long gmax = 0;
-  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,NULL,NULL,want_entries ? c->bufB.p : NULL,(u64) nub,d_cnt,&hc,&hm,&gmax);
+  /* the entry buffer was sized from nub positions; a streamed ingest may have delivered more than its reservation said
+     (the stream is abandoned only beyond stream_cap): the distinct entries are bounded by the k-mers actually seen        */
+  u64 ent_cap = (u64) nub;
+  if (want_entries && hc.nkmers > ent_cap)
+    { if (c->bufB.ensure((size_t) (hc.nkmers + 4) * 8 * entry_words(c->cfg.kmer)))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (entries of %llu k-mers)",hc.nkmers);
+      ent_cap = hc.nkmers;
+    }
+  rc = super_count_stage(c,g,SA,SB,S,d_seq,1,NULL,NULL,NULL,NULL,want_entries ? c->bufB.p : NULL,ent_cap,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   static int verbose = -1;
   if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
@@ -1169,7 +1294,12 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   res->ntable = 0; res->table = NULL; res->table_dev = NULL;
   c->ptab_n = 0;
   if (want_entries)
-    { rc = entries_sort_stage(c,c->bufB.p,c->bufA.p,(long long) hc.nent,fetch_table,res);
+    { /* the super-mer records in buffer A are dead: it is the second sort buffer (and may have to grow with the entries) */
+      if (c->bufA.ensure((size_t) (hc.nent + 4) * 8 * entry_words(c->cfg.kmer)))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (entry sort buffer of %llu entries)",hc.nent);
+      rc = entries_sort_stage(c,c->bufB.p,c->bufA.p,(long long) hc.nent,fetch_table,res);
+      if (rc) return rc;
+      rc = d2h_join(c);
       if (rc) return rc;
     }
   else
@@ -1186,6 +1316,177 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   collect_times(c,res);
   c->last_path = 1;
   c->st_super = (long long) hc.nrec; c->st_ent = want_entries ? (long long) hc.nent : 0; c->st_groups = gmax;
+  c->st_split = hc.pad; c->st_spill = 0;
+  single_run(c,res);
+  return FKGPU_OK;
+}
+
+/*  Device memory the working buffers of a count may take: cfg.mem_limit (the host's -M), FKGPU_MEM_LIMIT (bytes; tests
+ *  force multi-round counts of small inputs with it), else 0 = no limit beyond what is free.                          */
+static size_t mem_limit_of(fkgpu_ctx *c)
+{ const char *e = getenv("FKGPU_MEM_LIMIT");
+  if (e && atoll(e) > 0) return (size_t) atoll(e);
+  return c->cfg.mem_limit > 0 ? (size_t) c->cfg.mem_limit : 0;
+}
+
+/*  bytes the one-round super-mer count reserves for nub positions: two record buffers of entry width and the table */
+static size_t one_round_bytes(fkgpu_ctx *c, long long nub)
+{ const size_t ew = (size_t) 8 * entry_words(c->cfg.kmer);
+  return (size_t) (nub + 4) * ew * 2 + (c->cfg.do_table > 0 ? (size_t) nub * (c->kbytes + 2) : 0) + ((size_t) 64 << 20);
+}
+
+/*  does the one-round working set fit?  (what the context already holds of it counts as available) */
+static bool one_round_fits(fkgpu_ctx *c, long long nub)
+{ const size_t need = one_round_bytes(c,nub), lim = mem_limit_of(c);
+  if (lim && need > lim) return false;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr,&tot) != cudaSuccess) { cudaGetLastError(); return true; }
+  const size_t held = c->bufA.cap + c->bufB.cap + c->table.cap;
+  return need <= (size_t) ((fr + held) * 0.94);
+}
+
+/*  Inputs beyond one round (the reference's NPARTS > 1: FastK.c:419-429 sizes the parts from -M, count.c:1337 loops over
+ *  them, table.c:240-313 merges their sorted files).  The reads are scanned ONCE into super-mer records (0.7 B per k-mer)
+ *  and partitioned on the top bucket bits; then contiguous ranges of level-1 buckets are counted one ROUND at a time, each
+ *  sized so that even all-distinct k-mers fit the entry buffers (k-mers per level-1 bucket are summed exactly first).  A
+ *  round's distinct entries are put in key order and leave as one sorted run, copied to pinned host memory while the next
+ *  round is counted.  Runs hold disjoint key sets (a canonical k-mer lives in one minimizer bucket): no counts merge.    */
+static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res,
+                                     bool own_total)
+{ const SuperGeom g = super_geom(c->cfg.kmer,npos);
+  const int EW = entry_words(c->cfg.kmer), tw = c->kbytes + 2;
+  const size_t EB = (size_t) 8 * EW;
+  const bool want_entries = c->cfg.do_table > 0;
+  if (c->cfg.do_profile)
+    return set_err(FKGPU_E_NOMEM,"out of device memory: -p needs the whole table on the device and a multi-round count does not keep it");
+  /* this path sizes the big buffers itself */
+  c->bufA.release(); c->bufB.release(); c->bufC.release(); c->table.release();
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr,&tot));
+  size_t budget = (size_t) (fr * 0.94);
+  { const size_t lim = mem_limit_of(c); if (lim && lim < budget) budget = lim; }
+  int rc = prepare_small(c,std::max(g.P1,1));
+  if (rc) return rc;
+  if (own_total) cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+
+  /* ---- scan once: expected record density 2/(w+1) per position for random minimizers + 1/64 for the cuts, 50 % slack;
+          k_super keeps counting past the capacity, so a denser input is rescanned once with the exact size            */
+  SuperCounters hc;
+  long long scap = (long long) (npos * std::min(1.0,(2.0 / (g.w + 1) + 1.0/64) * 1.5)) + (1 << 16);
+  for (int attempt = 0; ; attempt++)
+    { if ((size_t) (scap + 8) * 17 + budget / 8 > budget)
+        return set_err(FKGPU_E_NOMEM,"out of device memory: %lld super-mer records do not fit the %zu MB budget",scap,budget >> 20);
+      if (c->bufA.ensure((size_t) (scap + 8) * 16) || c->segs.ensure(sizeof(SuperCounters)))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (super-mer records)");
+      CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
+      stage_begin(c,FKGPU_ST_SUPERSCAN);
+      rc = super_scan_stage(c,d_seq,d_val,npos,g,0,(u64 *) c->bufA.p,(u64) scap,(SuperCounters *) c->segs.p);
+      if (rc) return rc;
+      stage_end(c,FKGPU_ST_SUPERSCAN);
+      CU(cudaMemcpyAsync(&hc,c->segs.p,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      bank_times(c);
+      if ((long long) hc.nrec <= scap) break;
+      if (attempt) return set_err(FKGPU_E_CUDA,"internal: super-mer scan overflowed twice");
+      scap = (long long) hc.nrec + 1024;
+    }
+  const long long S = (long long) hc.nrec;
+  const u64 nkmers = hc.nkmers;
+  Key<1> *SA = (Key<1> *) c->bufA.p;
+  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + (((size_t) (scap + 8) * 8) & ~(size_t) 15));
+
+  /* ---- level 1, then what every level-1 bucket holds: records (histogram) and k-mers (summed lengths) */
+  const int b1 = g.bbits ? g.P1 : 0, n1 = 1 << b1;
+  stage_begin(c,FKGPU_ST_SUPERPART);
+  rc = super_level1(c,SA,SB,S,b1);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERPART);
+  if (c->roff1.ensure((size_t) (n1 + 1) * 8) || c->l1k.ensure((size_t) n1 * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  CU(cudaMemcpyAsync(c->roff1.p,c->off1.p,(size_t) (n1 + 1) * 8,cudaMemcpyDeviceToDevice,c->st));
+  k_bucket_kmers<<<n1,256,0,c->st>>>((const u64 *) SB,(const u64 *) c->roff1.p,g.pbits,(u64 *) c->l1k.p); KCHECK();
+  std::vector<u64> hrec(n1), hkm(n1);
+  CU(cudaMemcpyAsync(hrec.data(),c->hist1.p,(size_t) n1 * 8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(hkm.data(),c->l1k.p,(size_t) n1 * 8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  bank_times(c);
+
+  /* ---- entry buffers from what is left: ent + other + table per entry */
+  long long ecap = 0;
+  if (want_entries)
+    { /* small stuff (bucket offsets, group lists, per-item counters) rides in the slack; 4 more bytes per entry for its count */
+      const size_t used = c->bufA.cap + std::min((size_t) 256 << 20,budget / 8);
+      if (budget <= used) return set_err(FKGPU_E_NOMEM,"out of device memory: nothing left for the entry buffers (budget %zu MB)",budget >> 20);
+      ecap = (long long) ((budget - used) / (2*EB + (size_t) tw + 4));
+      if (ecap > (long long) nkmers) ecap = (long long) nkmers;
+      u64 mx = 0;
+      for (u64 x : hkm) mx = std::max(mx,x);
+      if ((u64) ecap < mx)
+        return set_err(FKGPU_E_NOMEM,"out of device memory: a level-1 bucket of %llu k-mers exceeds the %lld-entry buffers the %zu MB budget allows",
+                       mx,ecap,budget >> 20);
+      if (c->bufB.ensure((size_t) (ecap + 4) * EB) || c->bufC.ensure((size_t) (ecap + 4) * EB) || c->table.ensure((size_t) ecap * tw + 64))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (entry buffers of %lld entries)",ecap);
+    }
+
+  /* ---- rounds: greedy over the level-1 buckets, worst case (every k-mer distinct) fits the entry buffers */
+  c->run_n.clear(); c->run_p.clear();
+  res->ntable = 0; res->table = NULL; res->table_dev = NULL;
+  c->ptab_n = 0;
+  long long groups = 0, ents = 0; u32 splits = 0, fails = 0;
+  Misc hm; memset(&hm,0,sizeof(hm));
+  int nrounds = 0;
+  for (int b0 = 0; b0 < n1; )
+    { int bq = b0; u64 kr = 0, sr = 0;
+      while (bq < n1 && (!want_entries || bq == b0 || kr + hkm[bq] <= (u64) ecap)) { kr += hkm[bq]; sr += hrec[bq]; bq++; }
+      if (sr > 0)
+        { if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+          SuperCounters *d_cnt = (SuperCounters *) c->segs.p;          /* the entry sort borrows this buffer: take it back */
+          CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+          Misc *d_misc = (Misc *) c->misc.p;
+          CU(cudaMemsetAsync(&d_misc->ovf_cnt,0,8,c->st));
+          SuperCounters rc_h; long long gm = 0;
+          rc = super_bucket_range(c,g,SB,SA,(const u64 *) c->roff1.p,b0,bq,(long long) sr,d_seq,1,NULL,NULL,NULL,NULL,
+                                  want_entries ? c->bufB.p : NULL,(u64) ecap,d_cnt,&rc_h,&hm,&gm);
+          if (rc) return rc;
+          groups += gm; splits += rc_h.pad; fails += rc_h.fail;
+          if (want_entries)
+            { if ((size_t) nrounds >= c->h_runs.size()) c->h_runs.push_back(new PinBuf());
+              c->h_out = c->h_runs[nrounds];
+              fkgpu_result rr; memset(&rr,0,sizeof(rr));
+              rc = entries_sort_stage(c,c->bufB.p,c->bufC.p,(long long) rc_h.nent,fetch_table,&rr);
+              c->h_out = nullptr;
+              if (rc) return rc;
+              c->run_n.push_back(rr.ntable); c->run_p.push_back(rr.table);
+              res->ntable += rr.ntable; ents += (long long) rc_h.nent;
+            }
+          bank_times(c);
+          nrounds++;
+        }
+      b0 = bq;
+    }
+  if (nrounds == 0 && want_entries) { c->run_n.push_back(0); c->run_p.push_back(NULL); }
+  rc = d2h_join(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(&hm,c->misc.p,sizeof(hm),cudaMemcpyDeviceToHost,c->st));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  static int verbose = -1;
+  if (verbose < 0) { const char *e = getenv("FKGPU_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (verbose)
+    fprintf(stderr,"[fkgpu] multi-round count: %d rounds over %d level-1 buckets, budget %zu MB, %lld super-mers, %llu k-mers, entry buffers %lld, %lld entries\n",
+            nrounds,n1,budget >> 20,S,nkmers,ecap,ents);
+  res->hist = c->h_hist;
+  res->max_inst = (int64_t) hm.maxinst;
+  res->ndistinct = (int64_t) hm.ndistinct;
+  res->nkmers = (int64_t) nkmers;
+  res->nruns = (int32_t) c->run_n.size();
+  res->run_ntable = c->run_n.data(); res->run_table = c->run_p.data();
+  if (res->nruns == 1) res->table = c->run_p[0];
+  c->last_ndist = (long long) hm.ndistinct;
+  c->last_path = 1;
+  c->st_super = S; c->st_ent = ents; c->st_groups = groups; c->st_rounds = nrounds; c->st_split = splits; c->st_spill = 0;
+  (void) fails;
   return FKGPU_OK;
 }
 
@@ -1209,7 +1510,7 @@ static int stream_begin(fkgpu_ctx *c)
       fkgpu_packed_words(cap,&sw,&vw);
       ok = !(c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4));
     }
-  const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0;
+  const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0 && (c->cfg.do_profile || one_round_fits(c,nub));
   if (scan)
     { c->sgeom = super_geom(c->cfg.kmer,cap);
       ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,entry_words(c->cfg.kmer)) == 0) && !c->segs.ensure(sizeof(SuperCounters));
@@ -1247,6 +1548,8 @@ static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
 { c->last_path = 0;
   if (super_path_ok(c))
     { bool fb = false;
+      if (!prescanned && !c->cfg.do_profile && !one_round_fits(c,npos))
+        return count_packed_super_rounds(c,d_seq,d_val,npos,fetch_table,res,own_total);
       int rc = count_packed_super(c,d_seq,d_val,npos,fetch_table,res,own_total,&fb,prescanned);
       if (rc || !fb) return rc;
       memset(c->used,0,sizeof(c->used));
@@ -1258,6 +1561,7 @@ static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
 
 static void init_result(fkgpu_ctx *c, fkgpu_result *res)
 { memset(res,0,sizeof(*res));
+  memset(c->ms_bank,0,sizeof(c->ms_bank));
   res->kmer = c->cfg.kmer;
   res->kmer_bytes = c->kbytes;
   memset(c->used,0,sizeof(c->used));
@@ -1405,6 +1709,9 @@ static int count_records_t(fkgpu_ctx *c, void *d_records, long long n, int fetch
     }
   rc = count_from_level1<NW>(c,n,P1,P2,fetch_table,res,c->bufA.p,d_records);
   if (rc) return rc;
+  rc = d2h_join(c);
+  if (rc) return rc;
+  single_run(c,res);
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
   collect_times(c,res);
@@ -1620,6 +1927,9 @@ extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int 
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
   rc = entries_sort_stage(c,d_entries,c->bufA.p,(long long) n,fetch_table,res);
   if (rc) return rc;
+  rc = d2h_join(c);
+  if (rc) return rc;
+  single_run(c,res);
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
   collect_times(c,res);

@@ -250,4 +250,210 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
   if (threadIdx.x == 0 && ndist) atomicAdd(p.g_ndistinct,ndist);
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/*  k_bucket_count3: the same algorithm with WARP-PRIVATE tables: a warp owns a work group (whole buckets, ~32 super-mers)
+ *  from load to emit -- no block barrier anywhere in the loop (the CTA-wide variant above spends ~45 % of its warp time
+ *  waiting at the four barriers per group, ncu r2b).  Groups are dealt round-robin to the resident warps.            */
+
+#define BW_WARPS  4
+#define BW_TPB    (32*BW_WARPS)
+#define BW_KC     256                /* distinct keys a warp's class may hold */
+#define BW_SL     512                /* slots per warp (load <= 0.5)          */
+#define BW_WBYTES ((size_t) BW_KC*8*2 + (size_t) BW_KC*4 + (size_t) BW_SL*4 + (size_t) 32*BK_ROW*4)
+#define BW_SMEM   (BW_WBYTES*BW_WARPS)
+
+template<int KW, bool PAY, bool WIDE>
+__global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 klast)
+{ static_assert(KW >= 2 && KW <= 4 && (!WIDE || KW == 4) && BW_KC < 65535 && BW_SL >= 2*BW_KC,"bucket kernel geometry");
+  typedef Key<WIDE ? 3 : 2> Entry;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ u32 s_hist[SC_SMALLHIST], s_nk[BW_WARPS], s_ov[BW_WARPS];
+
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wb = s_raw + (size_t) warp * BW_WBYTES;
+  u64 *k0   = (u64 *) wb;                               /* [BW_KC] */
+  u64 *k1   = k0 + BW_KC;                               /* [BW_KC] */
+  u32 *cnt  = (u32 *) (k1 + BW_KC);                     /* [BW_KC] */
+  u32 *slot = cnt + BW_KC;                              /* [BW_SL] */
+  u32 *rows = slot + BW_SL;                             /* [32][BK_ROW] */
+  const u64 pmask = (1ull << p.pbits) - 1ull;
+  Entry *ent = (Entry *) p.ent;
+  u32 ndist = 0;                                        /* warp-uniform: distinct keys this warp has seen */
+
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BW_TPB) s_hist[i] = 0;
+  for (u32 i = lane; i < BW_KC; i += 32) cnt[i] = 0;
+  __syncthreads();
+
+  const long long nwarps = (long long) gridDim.x * BW_WARPS;
+  for (long long g = (long long) blockIdx.x * BW_WARPS + warp; g < p.nitems; g += nwarps)
+    { const u64 r0 = p.starts[g], r1 = p.ends[g];
+      if (r1 <= r0) continue;
+      u32 R = 1, rd = 0;
+      for (;;)
+        { { uint4 *s4 = (uint4 *) slot;
+            const uint4 z = make_uint4(0,0,0,0);
+#pragma unroll
+            for (u32 i = 0; i < BW_SL/4/32; i++) s4[lane + i*32] = z;
+          }
+          if (lane == 0) { s_nk[warp] = 0; s_ov[warp] = 0; }
+          __syncwarp();
+          volatile u32 *ovf = &s_ov[warp];
+
+          u32 spare = 0xffffffffu;
+          for (u64 q0 = r0; q0 < r1; q0 += 32)
+            { if (*ovf) break;
+              const u32 ns = (u32) ((r1 - q0 < 32ull) ? (r1 - q0) : 32ull);
+              u32 l = 0;
+              if (lane < ns)
+                { const u64 sm = p.recs[q0 + lane];
+                  l = (u32) ((sm >> p.pbits) & 63u) + 1u;
+                  u64 ps = sm & pmask;
+                  uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
+                  if (PAY)
+                    { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
+                  else
+                    { const u32 *sq = p.seq;
+                      if (p.nranks > 1)
+                        { int r = 0;
+#pragma unroll 1
+                          for (int q = 1; q < p.nranks; q++)
+                            if (ps >= p.pbase[q]) r = q;
+                          ps -= p.pbase[r]; sq = p.seqr[r];
+                        }
+                      const u32 *gp = sq + (ps >> 4);
+                      const int sh = 2*(int) (ps & 15ull);
+                      const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);
+                      u32 x[9];
+#pragma unroll
+                      for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
+                      d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
+                                         __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
+                      d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
+                                         __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
+                    }
+                }
+              u32 incl = l;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1)
+                { const u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+                  if ((int) lane >= o) incl += y;
+                }
+              const u32 T   = __shfl_sync(0xffffffffu,incl,31);
+              const u32 pre = incl - l;
+              __syncwarp();
+              u32 before = 0;
+              for (u32 g0 = 0; g0 < T; g0 += 32)
+                { const u32 rel = pre - g0;
+                  const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
+                  const u32 si  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;
+                  before += __popc(m);
+                  const u32 ps_ = __shfl_sync(0xffffffffu,pre,si & 31u);
+                  if (g0 + lane < T)
+                    { const u32 j = g0 + lane - ps_;
+                      u32 F[KW], G[KW];
+                      supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
+                      const Key<2> key = strands_canon<KW>(F,G);
+                      const u32 h = bucket_hash<KW>(key);
+                      if (((h >> 20) & (R-1)) == rd)
+                        { const u32 fp = h & 0xffff0000u;
+                          u32 x = h & (BW_SL-1);
+                          for (u32 step = 0; ; step++)
+                            { if (step >= BK_PROBE) { *ovf = 1; break; }
+                              u32 v = ((volatile u32 *) slot)[x];
+                              if (v == 0u)
+                                { if (spare == 0xffffffffu)
+                                    { spare = atomicAdd(&s_nk[warp],1u);
+                                      if (spare >= BW_KC) { *ovf = 1; spare = 0xffffffffu; break; }
+                                    }
+                                  k0[spare] = key.w[0];
+                                  if (KW > 2) k1[spare] = key.w[1];
+                                  __threadfence_block();
+                                  const u32 old = atomicCAS(&slot[x],0u,fp | (spare + 1u));
+                                  if (old == 0u) { atomicAdd(&cnt[spare],1u); spare = 0xffffffffu; break; }
+                                  v = old;
+                                }
+                              if ((v & 0xffff0000u) == fp)
+                                { const u32 ki = (v & 0xffffu) - 1u;
+                                  bool eq = (((volatile u64 *) k0)[ki] == key.w[0]);
+                                  if (KW > 2) eq = eq && (((volatile u64 *) k1)[ki] == key.w[1]);
+                                  if (eq) { atomicAdd(&cnt[ki],1u); break; }
+                                }
+                              x = (x+1) & (BW_SL-1);
+                            }
+                        }
+                    }
+                }
+              __syncwarp();
+            }
+          __syncwarp();
+          const u32 nkr = ((volatile u32 *) s_nk)[warp];
+          const u32 nk  = (nkr < (u32) BW_KC) ? nkr : (u32) BW_KC;
+          if (*ovf)
+            { for (u32 i = lane; i < nk; i += 32) cnt[i] = 0;
+              if (R >= BK_MAXR)
+                { if (lane == 0) atomicAdd(p.g_fail,1u);
+                  __syncwarp();
+                  break;
+                }
+              if (lane == 0) atomicAdd(p.g_fail + 1,1u);
+              R <<= 1;
+              __syncwarp();
+              continue;
+            }
+
+          /* emit: pass 1 histogram + totals, pass 2 entries behind one global atomic */
+          u32 nemit = 0;
+          for (u32 b0 = 0; b0 < nk; b0 += 32)
+            { const u32 i = b0 + lane;
+              const u32 c = (i < nk) ? cnt[i] : 0u;
+              const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
+              if (c != 0u)
+                { if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
+                  else atomicAdd(p.g_hist + cs,1ull);
+                  if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
+                }
+              ndist += __popc(__ballot_sync(0xffffffffu,c != 0u));
+              nemit += __popc(__ballot_sync(0xffffffffu,c != 0u && ent != NULL && cs >= p.ent_min));
+            }
+          u64 at = 0;
+          if (nemit)
+            { if (lane == 0) at = atomicAdd(p.ent_counter,(u64) nemit);
+              at = __shfl_sync(0xffffffffu,at,0);
+            }
+          for (u32 b0 = 0; b0 < nk; b0 += 32)
+            { const u32 i = b0 + lane;
+              u32 c = 0;
+              if (i < nk) { c = cnt[i]; cnt[i] = 0; }
+              const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
+              const bool em = (nemit != 0u) && (c != 0u) && (cs >= p.ent_min);
+              const u32 b = __ballot_sync(0xffffffffu,em);
+              if (em)
+                { const u64 o = at + __popc(b & ((1u << lane) - 1u));
+                  if (o < p.ent_cap)
+                    { Entry e;
+                      e.w[0] = k0[i];
+                      if (WIDE) { e.w[1] = k1[i]; e.w[WIDE ? 2 : 1] = (u64) cs; }
+                      else e.w[1] = ((KW > 2) ? k1[i] : 0ull) | (u64) cs;
+                      ent[o] = e;
+                    }
+                }
+              at += __popc(b);
+            }
+          while (R > 1 && rd >= (R >> 1)) { rd -= (R >> 1); R >>= 1; }
+          if (R == 1) break;
+          rd += (R >> 1);
+          __syncwarp();
+        }
+      __syncwarp();
+    }
+
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BW_TPB)
+    { const u32 c = s_hist[i];
+      if (c) atomicAdd(p.g_hist + i,(u64) c);
+    }
+  if (lane == 0 && ndist) atomicAdd(p.g_ndistinct,(u64) ndist);
+}
+
 }  // namespace fk

@@ -657,12 +657,13 @@ __global__ void k_fill_u64(u64 *a, long long n, const u64 *value)
   if (i < n) a[i] = *value;
 }
 
-__global__ void k_groups(const u64 *off, long long m /* # of buckets; off[m] = N */, u32 T, u64 *gstart, long long gmax)
+__global__ void k_groups(const u64 *off, long long m /* # of buckets; off[m] = end */, u32 T, u64 *gstart, long long gmax)
 { long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i > m) return;
+  const u64 base = off[0];                   /* a bucket range need not start at record 0 */
   u64 s = off[i];
-  long long glo = (i == 0) ? 0 : (long long) (off[i-1] / T) + 1;
-  long long ghi = (long long) (s / T);
+  long long glo = (i == 0) ? 0 : (long long) ((off[i-1] - base) / T) + 1;
+  long long ghi = (long long) ((s - base) / T);
   if (i == 0) glo = 0;
   for (long long g = glo; g <= ghi && g <= gmax; g++)
     gstart[g] = s;
@@ -693,6 +694,7 @@ struct SortCountParams
     u64        *g_maxinst;
     u64        *g_ndistinct;
     u32        *ovf_cnt; u32 *ovf_list; u32 ovf_cap;
+    u32         item_base;               /* index of item 0 of this launch in the host's item numbering (chunked launches) */
     u32         cap;                     /* C                                                 */
     u32         tab_off, srt_off;        /* byte offsets of the hash table / sort array in smem */
     u32         srt2_off;                /* entries: second sort array inside srt (>= SC_RANKMAX free) */
@@ -750,7 +752,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   if (n64 > p.cap)
     { if (threadIdx.x == 0)
         { u32 s = atomicAdd(p.ovf_cnt,1u);
-          if (s < p.ovf_cap) p.ovf_list[s] = (u32) g;
+          if (s < p.ovf_cap) p.ovf_list[s] = p.item_base + (u32) g;
           p.e_all[g] = 0; p.e_pass[g] = 0;
         }
       return;
@@ -1648,6 +1650,23 @@ __global__ void __launch_bounds__(256) k_materialise(const u64 *recs, long long 
 __global__ void __launch_bounds__(256) k_reindex(u64 *recs, long long n, int pbits)
 { const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) recs[i] = (recs[i] & ~((1ull << pbits) - 1ull)) | (u64) i;
+}
+
+/* k-mers covered by the records of every level-1 bucket b = [off[b], off[b+1]): one CTA per bucket (plans the bucket-range rounds) */
+__global__ void __launch_bounds__(256) k_bucket_kmers(const u64 *recs, const u64 *off, int pbits, u64 *out)
+{ __shared__ u64 s_w[8];
+  const u64 a = off[blockIdx.x], b = off[blockIdx.x + 1];
+  u64 s = 0;
+  for (u64 i = a + threadIdx.x; i < b; i += 256) s += ((recs[i] >> pbits) & 63ull) + 1ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { u64 t = 0;
+      for (int i = 0; i < 8; i++) t += s_w[i];
+      out[blockIdx.x] = t;
+    }
 }
 
 /* total k-mers covered by n super-mer records (sizes the distinct-entry buffer of a rank after the exchange) */

@@ -32,6 +32,7 @@
 static char *Prog_Name = "FastK";
 
 static int   VERBOSE, COMPRESS, KMER = 40, DO_TABLE, DO_PROFILE, BC_PREFIX, NTHREADS = 4, ITHREADS;
+static int64_t SORT_MEMORY;            /* -M in bytes; 0 = not given: use what the device has */
 static char *OUT_NAME;
 static char  OUT_DIR[4096], OUT_ROOT[4096];
 static int   have_out;
@@ -314,7 +315,8 @@ int main(int argc, char *argv[])
         switch (a[1])
         { case 'k': KMER = atoi(a+2); if (KMER <= 0) { fprintf(stderr,"%s: K-mer length must be positive\n",Prog_Name); exit(1); } break;
           case 'T': NTHREADS = atoi(a+2); if (NTHREADS <= 0) { fprintf(stderr,"%s: Number of threads must be positive\n",Prog_Name); exit(1); } break;
-          case 'M': break;                       /* sort memory: the device arena is sized from the input */
+          case 'M': SORT_MEMORY = (int64_t) (atof(a+2) * 1073741824.);    /* SORT_MEMORY (FastK.c:353-361), here: device memory for the count's working buffers; an input that needs more is counted in rounds */
+                    if (SORT_MEMORY <= 0) { fprintf(stderr,"%s: Memory must be positive\n",Prog_Name); exit(1); } break;
           case 'P': spath = a+2; break;
           case 'N': OUT_NAME = a+2; break;
           case 'b':
@@ -389,7 +391,7 @@ int main(int argc, char *argv[])
   memset(&cfg,0,sizeof(cfg));
   cfg.kmer = KMER; cfg.do_table = DO_TABLE; cfg.do_profile = DO_PROFILE; cfg.bc_prefix = BC_PREFIX;
   cfg.device = getenv("FASTK_GPU") ? atoi(getenv("FASTK_GPU")) : 0;
-  cfg.nthreads = ITHREADS; cfg.reserve_bases = work;
+  cfg.nthreads = ITHREADS; cfg.reserve_bases = work; cfg.mem_limit = SORT_MEMORY;
   if (fkgpu_create(&cfg,&CTX) != 0)
     { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
   have_out = 1;
@@ -444,13 +446,14 @@ int main(int argc, char *argv[])
     { fprintf(stderr,"  %lld %d-mers, %lld distinct; device %.3f ms (pack %.3f ms), wall %.3fs\n",
               (long long) res.nkmers,KMER,(long long) res.ndistinct,res.ms_total,res.ms_pack,t2-t1);
       fprintf(stderr,"  %.3f Gbases/s on the device\n",res.ms_total > 0 ? res.nbases/1e6/res.ms_total : 0.);
+      if (res.nruns > 1) fprintf(stderr,"  Counted in %d rounds (sorted runs merged while the table parts are written)\n",res.nruns);
     }
 
   if (fk_write_hist(OUT_DIR,OUT_ROOT,KMER,res.hist,res.max_inst))
     { fprintf(stderr,"%s: Cannot write to %s/%s.hist.  Enough disk space?\n",Prog_Name,OUT_DIR,OUT_ROOT); Clean_Exit(1); }
   if (DO_TABLE > 0)
     { if (VERBOSE) fprintf(stderr,"\nPhase 3 (-t option): Writing K-mer Table Parts\n");
-      if (fk_write_ktab(OUT_DIR,OUT_ROOT,KMER,DO_TABLE,NTHREADS,res.table,res.ntable))
+      if (fk_write_ktab_runs(OUT_DIR,OUT_ROOT,KMER,DO_TABLE,NTHREADS,res.run_table,res.run_ntable,res.nruns))
         { fprintf(stderr,"%s: Cannot write to %s/%s.ktab.  Enough disk space?\n",Prog_Name,OUT_DIR,OUT_ROOT); Clean_Exit(1); }
       if (VERBOSE)
         fprintf(stderr,"  There are %lld %d-mers that occur %d-or-more times\n",(long long) res.ntable,KMER,DO_TABLE);

@@ -73,6 +73,7 @@ void Split_Kmers(Input_Partition *io, char *root)
   cfg.device = getenv("FASTK_GPU") ? atoi(getenv("FASTK_GPU")) : 0;
   cfg.nthreads = ITHREADS;
   cfg.reserve_bases = EST_POSITIONS;
+  cfg.mem_limit = getenv("FASTK_GPU_MEM_GB") ? (int64_t) (atof(getenv("FASTK_GPU_MEM_GB")) * 1073741824.) : 0;
   if (fkgpu_create(&cfg,&CTX) != 0) fail("fkgpu_create");
   NUM_RID = (int64 *) calloc(ITHREADS > 0 ? ITHREADS : 1,sizeof(int64));
   Scan_All_Input(io);
@@ -105,22 +106,29 @@ void Sorting(char *path, char *root)
   if (DO_TABLE > 0)            /* what table_write_thread leaves for Merge_Tables (count.c:564-616,1560-1626) */
     { int   *beg = (int *) malloc(sizeof(int)*(NTHREADS+1));
       char  *name = (char *) malloc(strlen(SORT_PATH) + strlen(root) + 100);
-      int64  i = 0;
-      int    t;
+      int    t, n;
+      /* one sorted run per round of the count = one "part" of the reference: Merge_Tables merges <root>.<n>.L<t> over
+         n < NPARTS for every thread t (table.c:382-394); the first-byte ranges of the threads are the same in every part */
+      NPARTS = RES.nruns;
       IDX_BYTES = fk_idx_bytes(RES.ntable,KMER);
-      fk_table_split(RES.table,RES.ntable,TMER_WORD,NTHREADS,beg);
-      for (t = 0; t < NTHREADS; t++)
-        { int64 j = i;
-          int   f;
-          while (j < RES.ntable && RES.table[j*TMER_WORD] < beg[t+1]) j++;
-          sprintf(name,"%s/%s.%d.L%d",SORT_PATH,root,0,t);
-          f = open(name,O_WRONLY|O_CREAT|O_TRUNC,S_IRWXU|S_IRWXG|S_IRWXO);
-          if (f < 0 || (j > i && write(f,RES.table + i*TMER_WORD,(size_t) (j-i)*TMER_WORD) < 0))
-            { fprintf(stderr,"%s: Cannot write to %s.  Enough disk space?\n",Prog_Name,name);
-              Clean_Exit(1);
+      fk_table_split_runs(RES.run_table,RES.run_ntable,RES.nruns,TMER_WORD,NTHREADS,beg);
+      for (n = 0; n < RES.nruns; n++)
+        { const uint8_t *tab = RES.run_table[n];
+          const int64   nt = RES.run_ntable[n];
+          int64 i = 0;
+          for (t = 0; t < NTHREADS; t++)
+            { int64 j = i;
+              int   f;
+              while (j < nt && tab[j*TMER_WORD] < beg[t+1]) j++;
+              sprintf(name,"%s/%s.%d.L%d",SORT_PATH,root,n,t);
+              f = open(name,O_WRONLY|O_CREAT|O_TRUNC,S_IRWXU|S_IRWXG|S_IRWXO);
+              if (f < 0 || (j > i && write(f,tab + i*TMER_WORD,(size_t) (j-i)*TMER_WORD) < 0))
+                { fprintf(stderr,"%s: Cannot write to %s.  Enough disk space?\n",Prog_Name,name);
+                  Clean_Exit(1);
+                }
+              close(f);
+              i = j;
             }
-          close(f);
-          i = j;
         }
       free(name); free(beg);
     }

@@ -35,15 +35,19 @@ static int64_t first_byte_lower_bound(const uint8_t *entries, int64_t n, int tw,
   return lo;
 }
 
-void fk_table_split(const uint8_t *entries, int64_t n, int tw, int nparts, int *beg)
-{ int64_t asize = n * tw, sum = 0, thr, prev = 0;
-  int     x, m = 0;
+void fk_table_split_runs(const uint8_t *const *runs, const int64_t *ns, int nruns, int tw, int nparts, int *beg)
+{ int64_t asize = 0, sum = 0, thr;
+  int64_t *prev = (int64_t *) calloc((size_t) (nruns > 0 ? nruns : 1),sizeof(int64_t));
+  int     x, r, m = 0;
+  for (r = 0; r < nruns; r++) asize += ns[r] * tw;
   thr = asize / nparts;
   beg[0] = 0;
   for (x = 0; x < 256; x++)
-    { int64_t next = first_byte_lower_bound(entries,n,tw,x+1);       /* part[x] = (next - prev) * tw */
-      sum += (next - prev) * tw;
-      prev = next;
+    { for (r = 0; r < nruns; r++)
+        { int64_t next = first_byte_lower_bound(runs[r],ns[r],tw,x+1);       /* part[x] = sum over the runs of (next - prev) * tw */
+          sum += (next - (prev ? prev[r] : 0)) * tw;
+          if (prev) prev[r] = next;
+        }
       if (sum >= thr && m < nparts)
         { beg[++m] = x+1;
           thr = (asize * (m+1)) / nparts;
@@ -51,7 +55,11 @@ void fk_table_split(const uint8_t *entries, int64_t n, int tw, int nparts, int *
     }
   while (m < nparts) beg[++m] = 256;
   beg[nparts] = 256;
+  free(prev);
 }
+
+void fk_table_split(const uint8_t *entries, int64_t n, int tw, int nparts, int *beg)
+{ fk_table_split_runs(&entries,&n,1,tw,nparts,beg); }
 
 int fk_write_hist(const char *dir, const char *root, int kmer, const int64_t *hist, int64_t max_inst)
 { char name[4096];
@@ -70,36 +78,51 @@ int fk_write_hist(const char *dir, const char *root, int kmer, const int64_t *hi
 }
 
 /* one hidden table part per thread: parts are separate files, and because they are cut on first-byte boundaries no
-   prefix-index slot is shared between two parts (table.c:257 relies on the same fact)                              */
+   prefix-index slot is shared between two parts (table.c:257 relies on the same fact).  The table may arrive as several
+   sorted runs with disjoint keys (a multi-round count): the part's slices of the runs are merged on the fly, the role of
+   table.c:240-313 for the NPARTS part files.                                                                        */
 typedef struct
-  { const char *dir, *root; const uint8_t *entries;
-    int64_t i, j; int64_t *pindex;
+  { const char *dir, *root; const uint8_t *const *runs; int nruns;
+    int64_t *i, *j; int64_t *pindex;
     int kmer, tw, ib, t, bad;
   } Ktab_Job;
 
 static void *ktab_part_thread(void *arg)
 { Ktab_Job *J = (Ktab_Job *) arg;
-  const int pw = J->tw - J->ib;
+  const int pw = J->tw - J->ib, kb = J->tw - 2;
   const size_t cap = 1 << 22;
   size_t   fill = 0;
   uint8_t *buf = (uint8_t *) malloc(cap + 64);
   char     name[4096];
-  int64_t  i, m = J->j - J->i;
-  int      f;
+  int64_t  m = 0;
+  int      f, r, live = 0;
+  for (r = 0; r < J->nruns; r++) { m += J->j[r] - J->i[r]; live += (J->j[r] > J->i[r]); }
   snprintf(name,sizeof(name),"%s/.%s.ktab.%d",J->dir,J->root,J->t+1);
   f = open(name,O_WRONLY|O_CREAT|O_TRUNC,0700);
   if (f < 0 || buf == NULL) { J->bad = 1; free(buf); if (f >= 0) close(f); return NULL; }
   J->bad |= put(f,&J->kmer,sizeof(int));
   J->bad |= put(f,&m,sizeof(int64_t));
-  for (i = J->i; i < J->j; i++)
-    { const uint8_t *e = J->entries + i*J->tw;
-      int64_t idx = 0;
-      int b;
-      for (b = 0; b < J->ib; b++) idx = (idx << 8) | e[b];
-      J->pindex[idx] += 1;
-      memcpy(buf+fill,e+J->ib,pw);
-      fill += pw;
-      if (fill + pw > cap) { J->bad |= put(f,buf,fill); fill = 0; }
+  while (live > 0)
+    { const uint8_t *e = NULL;
+      int64_t idx = 0, stop;
+      int b, best = -1;
+      /* the run whose next entry is smallest; with one live run its whole remainder goes out without comparisons */
+      for (r = 0; r < J->nruns; r++)
+        if (J->i[r] < J->j[r])
+          { const uint8_t *x = J->runs[r] + J->i[r]*J->tw;
+            if (best < 0 || memcmp(x,e,(size_t) kb) < 0) { best = r; e = x; }
+          }
+      stop = (live == 1) ? J->j[best] : J->i[best] + 1;
+      for ( ; J->i[best] < stop; J->i[best]++)
+        { e = J->runs[best] + J->i[best]*J->tw;
+          idx = 0;
+          for (b = 0; b < J->ib; b++) idx = (idx << 8) | e[b];
+          J->pindex[idx] += 1;
+          memcpy(buf+fill,e+J->ib,pw);
+          fill += pw;
+          if (fill + pw > cap) { J->bad |= put(f,buf,fill); fill = 0; }
+        }
+      if (J->i[best] >= J->j[best]) live--;
     }
   J->bad |= put(f,buf,fill);
   free(buf);
@@ -107,26 +130,35 @@ static void *ktab_part_thread(void *arg)
   return NULL;
 }
 
-int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int nparts, const uint8_t *entries, int64_t n)
+int fk_write_ktab_runs(const char *dir, const char *root, int kmer, int cutoff, int nparts,
+                       const uint8_t *const *runs, const int64_t *ns, int nruns)
 { const int kb = (2*kmer+7) >> 3, tw = kb+2;
-  const int ib = fk_idx_bytes(n,kmer);
-  const int64_t ilen = 1ll << (8*ib);
-  int64_t  *pindex = (int64_t *) calloc((size_t) ilen,sizeof(int64_t));
+  int64_t  n = 0, *pindex, *cur;
+  int      ib, r;
   int      *beg = (int *) malloc(sizeof(int)*(nparts+1));
   Ktab_Job *job = (Ktab_Job *) calloc((size_t) nparts,sizeof(Ktab_Job));
   pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t)*(size_t) nparts);
   char     name[4096];
-  int64_t  x;
+  int64_t  x, ilen;
   int      f, t, bad = 0;
 
-  if (pindex == NULL || beg == NULL || job == NULL || th == NULL) { free(pindex); free(beg); free(job); free(th); return 1; }
-  fk_table_split(entries,n,tw,nparts,beg);
+  for (r = 0; r < nruns; r++) n += ns[r];
+  ib = fk_idx_bytes(n,kmer);
+  ilen = 1ll << (8*ib);
+  pindex = (int64_t *) calloc((size_t) ilen,sizeof(int64_t));
+  cur = (int64_t *) calloc((size_t) nparts * (size_t) (nruns > 0 ? nruns : 1) * 2,sizeof(int64_t));
+  if (pindex == NULL || beg == NULL || job == NULL || th == NULL || cur == NULL)
+    { free(pindex); free(beg); free(job); free(th); free(cur); return 1; }
+  fk_table_split_runs(runs,ns,nruns,tw,nparts,beg);
   for (t = 0; t < nparts; t++)
     { Ktab_Job *J = job+t;
-      J->dir = dir; J->root = root; J->entries = entries; J->pindex = pindex;
+      J->dir = dir; J->root = root; J->runs = runs; J->nruns = nruns; J->pindex = pindex;
       J->kmer = kmer; J->tw = tw; J->ib = ib; J->t = t; J->bad = 0;
-      J->i = first_byte_lower_bound(entries,n,tw,beg[t]);
-      J->j = first_byte_lower_bound(entries,n,tw,beg[t+1]);
+      J->i = cur + (size_t) t * nruns * 2; J->j = J->i + nruns;
+      for (r = 0; r < nruns; r++)
+        { J->i[r] = first_byte_lower_bound(runs[r],ns[r],tw,beg[t]);
+          J->j[r] = first_byte_lower_bound(runs[r],ns[r],tw,beg[t+1]);
+        }
       if (pthread_create(th+t,NULL,ktab_part_thread,J) != 0) { ktab_part_thread(J); th[t] = 0; J->t = -1; }
     }
   for (t = 0; t < nparts; t++)
@@ -145,9 +177,12 @@ int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int n
       bad |= put(f,pindex,sizeof(int64_t)*ilen);
       close(f);
     }
-  free(pindex); free(beg); free(job); free(th);
+  free(pindex); free(beg); free(job); free(th); free(cur);
   return bad;
 }
+
+int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int nparts, const uint8_t *entries, int64_t n)
+{ return fk_write_ktab_runs(dir,root,kmer,cutoff,nparts,&entries,&n,1); }
 
 int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out)
 { uint8_t *o = out;

@@ -14,11 +14,18 @@ int  fk_idx_bytes(int64_t nentries, int kmer);
 /* first-byte cut points for nparts table parts, rule of MSDsort.c:330-352 applied to the entry bytes */
 void fk_table_split(const uint8_t *entries, int64_t n, int tmer_word, int nparts, int *beg /*[nparts+1]*/);
 
+/* the same over a table delivered as nruns sorted runs with disjoint keys (fkgpu_result.run_table / run_ntable) */
+void fk_table_split_runs(const uint8_t *const *runs, const int64_t *ns, int nruns, int tmer_word, int nparts, int *beg);
+
 int  fk_write_hist(const char *dir, const char *root, int kmer, const int64_t *hist /*[32768]*/, int64_t max_inst);
 
 /* entries = n records [kmer_bytes key][u16 LE count], sorted */
 int  fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int nparts,
                    const uint8_t *entries, int64_t n);
+
+/* the table as nruns sorted runs with disjoint keys: every part merges its slices of the runs (table.c:240-313) */
+int  fk_write_ktab_runs(const char *dir, const char *root, int kmer, int cutoff, int nparts,
+                        const uint8_t *const *runs, const int64_t *ns, int nruns);
 
 /* greedy profile code of one read's count vector; returns # of bytes written (out needs 2*plen+2) */
 int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out);

@@ -7,9 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FKGPU_LIB") or os.path.join(HERE, "lib", "libfastk_gpu.so")
 
 HIST_BINS = 32768
-NSTAGES = 12
+NSTAGES = 14
 STAGES = ["pack", "scan_hist", "scan_scatter", "l1_hist_records", "refine", "sortcount", "compact", "profile",
-          "super_scan", "super_partition", "bucket_count", "entry_partition"]
+          "super_scan", "super_partition", "bucket_count", "entry_partition", "super_refine", "spill"]
 PACK_PAD = 16
 
 
@@ -20,7 +20,7 @@ class FkgpuError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("kmer", C.c_int32), ("do_table", C.c_int32), ("do_profile", C.c_int32),
                 ("bc_prefix", C.c_int32), ("device", C.c_int32), ("nthreads", C.c_int32),
-                ("reserve_bases", C.c_int64)]
+                ("reserve_bases", C.c_int64), ("mem_limit", C.c_int64)]
 
 
 class _Result(C.Structure):
@@ -28,7 +28,8 @@ class _Result(C.Structure):
                 ("nbases", C.c_int64), ("nreads", C.c_int64), ("nkmers", C.c_int64), ("ndistinct", C.c_int64),
                 ("hist", C.POINTER(C.c_int64)), ("max_inst", C.c_int64),
                 ("ntable", C.c_int64), ("table", C.POINTER(C.c_uint8)), ("table_dev", C.c_void_p),
-                ("ms_pack", C.c_float), ("ms_count", C.c_float), ("ms_total", C.c_float)]
+                ("ms_pack", C.c_float), ("ms_count", C.c_float), ("ms_total", C.c_float),
+                ("nruns", C.c_int32), ("run_ntable", C.POINTER(C.c_int64)), ("run_table", C.POINTER(C.POINTER(C.c_uint8)))]
 
 
 _lib = None
@@ -140,12 +141,36 @@ class FkResult:
         self.ntable = r.ntable
         self.table_dev = r.table_dev
         tw = r.kmer_bytes + 2
+        self.nruns = max(1, int(r.nruns))
+        self.run_ntable = [int(r.run_ntable[i]) for i in range(r.nruns)] if r.nruns > 0 and bool(r.run_ntable) else [int(r.ntable)]
+        self._run_ptrs = [r.run_table[i] for i in range(r.nruns)] if r.nruns > 1 and bool(r.run_table) else None
         if copy_table and r.ntable > 0 and bool(r.table):
             self.table = np.ctypeslib.as_array(r.table, shape=(r.ntable * tw,)).copy().reshape(r.ntable, tw)
+        elif copy_table and r.ntable > 0 and self._run_ptrs is not None and all(bool(x) for x in self._run_ptrs):
+            self.table = self.merged_runs()
         else:
             self.table = None
         self._table_ptr = r.table if (r.ntable > 0 and bool(r.table)) else None
         self.ms_pack, self.ms_count, self.ms_total = r.ms_pack, r.ms_count, r.ms_total
+
+    def view_runs(self):
+        """list of (n_i, kmer_bytes + 2) uint8 views, one per sorted run (no copy; same lifetime as view_table)"""
+        tw = self.kmer_bytes + 2
+        if self._run_ptrs is None:
+            return [self.view_table()]
+        return [np.ctypeslib.as_array(p, shape=(n * tw,)).reshape(n, tw) if n else np.zeros((0, tw), np.uint8)
+                for p, n in zip(self._run_ptrs, self.run_ntable)]
+
+    def merged_runs(self):
+        """the runs of a multi-round count merged into one key-ordered table (what Merge_Tables does with the part files,
+        table.c:382-394): the runs hold disjoint keys, so the merge is a sort of their concatenation by the key bytes"""
+        tw = self.kmer_bytes + 2
+        allr = np.concatenate(self.view_runs())
+        pad = np.zeros((len(allr), 16), dtype=np.uint8)
+        pad[:, :self.kmer_bytes] = allr[:, :self.kmer_bytes]
+        w = pad.view(">u8")                                    # key order = order of the two big-endian words
+        order = np.lexsort((w[:, 1], w[:, 0]))
+        return np.ascontiguousarray(allr[order])
 
     def view_table(self):
         """(ntable, kmer_bytes + 2) uint8 view of the context's pinned host copy -- no copy; valid until the next
@@ -160,9 +185,9 @@ class FastKGPU:
     """One context = one GPU.  Mirrors the stages the reference's driver sequences (FastK.c:498-540):
     ingest() <-> Distribute_Block, finish() <-> Sorting, profiles() <-> Merge_Profiles."""
 
-    def __init__(self, k=40, table_cutoff=0, profile=False, bc_prefix=0, device=0, nthreads=1, reserve_bases=0):
+    def __init__(self, k=40, table_cutoff=0, profile=False, bc_prefix=0, device=0, nthreads=1, reserve_bases=0, mem_limit=0):
         self.lib = load_library()
-        cfg = _Config(k, table_cutoff, 1 if profile else 0, bc_prefix, device, nthreads, reserve_bases)
+        cfg = _Config(k, table_cutoff, 1 if profile else 0, bc_prefix, device, nthreads, reserve_bases, mem_limit)
         h = C.c_void_p()
         rc = self.lib.fkgpu_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -290,9 +315,10 @@ class FastKGPU:
         return FkResult(r, copy_table)
 
     def last_stats(self):
-        v = (C.c_int64 * 4)()
+        v = (C.c_int64 * 8)()
         self._chk(self.lib.fkgpu_last_stats(self.h, v), "fkgpu_last_stats")
-        return dict(path=int(v[0]), supermers=int(v[1]), entries=int(v[2]), groups=int(v[3]))
+        return dict(path=int(v[0]), supermers=int(v[1]), entries=int(v[2]), groups=int(v[3]), rounds=int(v[4]), split_classes=int(v[5]),
+                    spilled_kmers=int(v[6]))
 
     def last_path(self):
         return int(self.lib.fkgpu_last_path(self.h))

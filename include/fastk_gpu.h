@@ -49,6 +49,10 @@ typedef struct
     int32_t  device;        /* CUDA device ordinal                                             */
     int32_t  nthreads;      /* # of distinct tid values that will call fkgpu_ingest (ITHREADS)  */
     int64_t  reserve_bases; /* hint: total bases expected (0 = grow as needed)                 */
+    int64_t  mem_limit;     /* SORT_MEMORY -M<GB> in bytes: most device memory the working buffers of a count may take
+                               (0 = whatever is free).  An input whose one-pass working set does not fit is counted in
+                               several ROUNDS over disjoint minimizer-bucket ranges, each leaving one sorted run -- the
+                               role of NPARTS in the reference (FastK.c:419-429, count.c:1337, merged by table.c:240-313) */
   } fkgpu_config;
 
 /*  Result of fkgpu_finish / fkgpu_count_packed.  All pointers are owned by the context and stay
@@ -70,6 +74,13 @@ typedef struct
     float          ms_pack;           /* device time of the stages, CUDA events, for -v reporting */
     float          ms_count;
     float          ms_total;
+    /*  The table as sorted runs.  One run (nruns == 1, run_table[0] == table) unless the count took several rounds; then
+     *  every round leaves one run, strictly increasing by key, the runs hold DISJOINT key sets (a canonical k-mer lives in
+     *  one minimizer bucket), ntable is their total and table / table_dev are NULL: the consumer merges them, as
+     *  Merge_Tables does with the NPARTS part files (table.c:382-394).                                               */
+    int32_t        nruns;
+    const int64_t *run_ntable;        /* [nruns] records of every run                              */
+    const uint8_t *const *run_table;  /* [nruns] host (pinned) pointer of every run, NULL entries if not fetched */
   } fkgpu_result;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
@@ -195,7 +206,7 @@ int64_t fkgpu_launch_count(fkgpu_ctx *ctx);
 int     fkgpu_last_stats(fkgpu_ctx *ctx, int64_t *v /*[4]: path, super-mer records, distinct entries sorted, work groups*/);
 int     fkgpu_last_path(fkgpu_ctx *ctx);     /* which pipeline served the last count: 0 = 16-byte records, 1 = super-mers */
 int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double *bytes /*[FKGPU_NSTAGES]*/);
-#define FKGPU_NSTAGES 12
+#define FKGPU_NSTAGES 14
 /* stage ids */
 #define FKGPU_ST_PACK      0
 #define FKGPU_ST_SCANHIST  1
@@ -210,6 +221,8 @@ int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double 
 #define FKGPU_ST_SUPERPART 9     /* bucket partition of the super-mer records        */
 #define FKGPU_ST_BUCKET    10    /* on-chip expansion + hash count per bucket group  */
 #define FKGPU_ST_ENTPART   11    /* prefix partition of the distinct (key|count) entries */
+#define FKGPU_ST_SUPERREFINE 12   /* second partition level of the super-mer records  */
+#define FKGPU_ST_SPILL     13    /* oversize buckets expanded to k-mer records and counted by the record pipeline */
 
 #ifdef __cplusplus
 }

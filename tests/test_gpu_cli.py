@@ -77,3 +77,29 @@ def test_cli_error_paths(tmp_path):
     assert r.returncode == 1 and "Cannot find" in r.stderr
     r = subprocess.run([OURS, "-k99", util.golden("c1_k40")["src"]], capture_output=True, text=True)
     assert r.returncode == 1 and "not supported" in r.stderr
+
+
+@pytest.mark.parametrize("exe_name", ["ours", "refhost"])
+def test_cli_multi_round_with_small_memory(oracle_lib, exe_name, tmp_path):
+    """-M (ours) / FASTK_GPU_MEM_GB (reference host + shim) far below the one-round working set: the count takes several
+    rounds; our writer merges the runs, the reference's own Merge_Tables merges them as NPARTS part files (table.c:382-394).
+    Files must still equal the reference's golden outputs byte for byte."""
+    g = dict(util.golden("c1_k40"))
+    d = str(tmp_path)
+    if exe_name == "ours":
+        assert os.path.exists(OURS)
+        cmd, env = [OURS, "-k40", "-t1", "-T4", "-M0.006", "-v", "-P" + d, "-N" + os.path.join(d, "out"), g["src"]], dict(os.environ)
+    else:
+        if not os.path.exists(REFHOST):
+            pytest.skip("integration/_build/FastK_refhost not built")
+        cmd, env = [REFHOST, "-k40", "-t1", "-T4", "-v", "-P" + d, "-N" + os.path.join(d, "out"), g["src"]], dict(os.environ, FASTK_GPU_MEM_GB="0.006")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, FKGPU_VERBOSE="1"))
+    assert r.returncode == 0, r.stderr
+    import re
+    m = re.search(r"multi-round count: (\d+) rounds", r.stderr)
+    assert m and int(m.group(1)) > 1, r.stderr
+    h = util.read_hist_file(os.path.join(d, "out.hist"))
+    assert np.array_equal(h["hist"][1:], g["hist"][1:])
+    kt = util.read_ktab_files(d, "out")
+    assert kt["stub"] == g["ktab_stub"] and kt["payload"] == g["ktab_payload"]
+    util.check_parts_on_first_byte_boundaries(kt)

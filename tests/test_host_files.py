@@ -26,7 +26,30 @@ def fkfiles(tmp_path_factory):
     L.fk_encode_profile.argtypes = [C.POINTER(C.c_uint16), C.c_int64, C.POINTER(C.c_uint8)]
     L.fk_encode_profile.restype = C.c_int64
     L.fk_table_split.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.fk_write_ktab_runs.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
+                                     C.POINTER(C.c_int64), C.c_int]
     return L
+
+
+@pytest.mark.parametrize("name,nruns", [("c1_k40", 3), ("mixed_k21", 5), ("long_k63", 2), ("c1_k40", 1)])
+def test_table_delivered_as_runs_merges_to_the_reference_table(oracle_lib, fkfiles, name, nruns, tmp_path):
+    """A multi-round count hands the table over as sorted runs with disjoint keys (fkgpu_result.run_table): the writer
+    merges every part's slices of the runs (the role of table.c:240-313 for NPARTS part files) -- same files as the
+    reference's, whatever way the keys were dealt to the runs (here: by a hash, and one run left empty)."""
+    g = util.golden(name)
+    reads = util.read_seq_file(g["src"])
+    r = oracle_lib.count(reads, g["k"], cutoff=g["t"])
+    tab = np.ascontiguousarray(r["table"], dtype=np.uint8)
+    rng = np.random.default_rng(7)
+    owner = rng.integers(0, max(1, nruns - 1), len(tab)) if nruns > 1 else np.zeros(len(tab), dtype=np.int64)   # last run stays empty
+    runs = [np.ascontiguousarray(tab[owner == i]) for i in range(nruns)]
+    ptrs = (C.POINTER(C.c_uint8) * nruns)(*[x.ctypes.data_as(C.POINTER(C.c_uint8)) for x in runs])
+    ns = (C.c_int64 * nruns)(*[len(x) for x in runs])
+    d = str(tmp_path).encode()
+    assert fkfiles.fk_write_ktab_runs(d, b"w", g["k"], g["t"], g["T"], ptrs, ns, nruns) == 0
+    kt = util.read_ktab_files(str(tmp_path), "w")
+    assert kt["stub"] == g["ktab_stub"] and kt["payload"] == g["ktab_payload"]
+    util.check_parts_on_first_byte_boundaries(kt)
 
 
 @pytest.mark.parametrize("name", util.golden_cases())
