@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cutoff", type=int, default=None, help="-t<cutoff>")
     ap.add_argument("--ingest-threads", type=int, default=0, help="e2e arm: ingest threads (0 = host cores, at most 16)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-order", default="rr", choices=["rr", "contig"], help="e2e arm: how DATA_BLOCKs are dealt to the ingest threads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference run: no cpu_baseline and NO parity check")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--mem-limit-gb", type=float, default=0.0, help="fkgpu_config.mem_limit (the host's -M): below the one-round "
@@ -230,6 +231,7 @@ def device_generate_packed(torch, dev, eng, a, rank, seq_ptr, val_ptr):
         blk = torch.zeros((n * (L + 1) + 64,), dtype=torch.uint8, device=dev)
         blk[:n * (L + 1)].view(n, L + 1)[:, :L] = lut[r.long()]
         assert pos % 64 == 0
+        torch.cuda.synchronize()             # torch's stream wrote blk; the library packs on its own stream
         eng.pack_ascii_dev(blk.data_ptr(), n * (L + 1), seq_ptr + (pos // 16) * 4, val_ptr + (pos // 32) * 4)
         torch.cuda.synchronize()
         pos += n * (L + 1)
@@ -303,6 +305,7 @@ def main():
         d_seq = torch.zeros(sw, dtype=torch.int32, device=dev)
         d_val = torch.zeros(vw, dtype=torch.int32, device=dev)
         seq_ptr, val_ptr = d_seq.data_ptr(), d_val.data_ptr()
+    torch.cuda.synchronize()                 # the library packs on its own stream: the ASCII must have landed
     if not a.device_gen:
         eng.pack_ascii_dev(ascii_dev.data_ptr(), npos, seq_ptr, val_ptr)
         torch.cuda.synchronize()
@@ -362,9 +365,13 @@ def main():
         blocks = [(r0, min(nreads, r0 + rows_per_block)) for r0 in range(0, nreads, rows_per_block)]
 
         def worker(tid):
-            # tid-major read order, contiguous block ranges per thread (io.c hands each thread a contiguous file range)
-            b0, b1 = len(blocks) * tid // nthr, len(blocks) * (tid + 1) // nthr
-            for bi in range(b0, b1):
+            # -p: tid-major read order must be file order, so every thread takes a contiguous range of blocks (io.c hands
+            # each thread a contiguous file range); otherwise the blocks are dealt round-robin
+            if a.profile or a.e2e_order == "contig":
+                mine = range(len(blocks) * tid // nthr, len(blocks) * (tid + 1) // nthr)
+            else:
+                mine = range(tid, len(blocks), nthr)
+            for bi in mine:
                 r0, r1 = blocks[bi]
                 eng.ingest_ptr(base_ptr + r0 * (L + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
 

@@ -122,10 +122,11 @@ struct fkgpu_ctx
     std::vector<PinBuf *> h_runs;      /* pinned run buffers of multi-round counts (kept for re-use)                      */
     std::vector<int64_t>  run_n;       /* result: records of every sorted run                                             */
     std::vector<const uint8_t *> run_p;/* result: host pointer of every sorted run                                        */
+    DevBuf       spillA, spillB, spill_list;   /* oversize bucket groups: their k-mers as records, the list of the groups */
     DevBuf       bufC, roff1, l1k;     /* multi-round count: second entry buffer, record level-1 offsets, k-mers per level-1 bucket */
     cudaEvent_t  ev_sorted[FKGPU_D2H_CHUNKS], ev_d2h = nullptr;
     bool         d2h_pending = false;  /* a table copy on the copy stream still reads c->table                            */
-    long long    st_rounds = 0, st_split = 0, st_spill = 0;
+    long long    st_rounds = 0, st_split = 0, st_spill = 0, st_spill_acc = 0;
     int64_t h_hist[FKGPU_HIST_BINS];
 
     /* profile lookup table built by finish when cfg.do_profile */
@@ -210,7 +211,7 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
   for (auto b : bufs) b->release();
   c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
   for (auto r : c->h_runs) { r->release(); delete r; }
-  c->bufC.release(); c->roff1.release(); c->l1k.release();
+  c->bufC.release(); c->roff1.release(); c->l1k.release(); c->spillA.release(); c->spillB.release(); c->spill_list.release();
   for (auto &e : c->ev_sorted) cudaEventDestroy(e);
   if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -840,6 +841,9 @@ static int choose_p2(fkgpu_ctx *c, int P1, int *P2)
   return FKGPU_OK;
 }
 
+static int prepare_small(fkgpu_ctx *c, int P1);
+template<int NW> static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fetch_table, fkgpu_result *res, void *bufX, void *bufY);
+
 static int prepare_small(fkgpu_ctx *c, int P1)
 { const int nb1 = 1 << P1;
   if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8)
@@ -1006,7 +1010,7 @@ static bool super_path_ok(fkgpu_ctx *c) { return super_path_ok_k(c->cfg.kmer); }
 /*  words of a distinct entry: (key | count in the low 16 bits) fits two words up to k = 56; beyond, the count takes a third */
 static int entry_words(int kmer) { return kmer > 56 ? 3 : 2; }
 
-struct SuperCounters { u64 nrec, nkmers, nent; u32 fail, pad; };
+struct SuperCounters { u64 nrec, nkmers, nent, spill_kmers, spill_cursor; u32 fail, pad, nspill, pad2; };
 
 /*  npos_total = positions over ALL ranks' read streams (multi-GPU: every rank must derive the same bucket-id width) */
 static SuperGeom super_geom(int k, long long npos_total)
@@ -1069,6 +1073,60 @@ static int super_level1(fkgpu_ctx *c, const Key<1> *in, Key<1> *out, long long S
   return FKGPU_OK;
 }
 
+/*  Oversize bucket groups (listed by the bucket kernel in bp.spill_list): their nk k-mers are expanded to canonical records
+ *  and counted by the record pipeline (tile partition -> MSD refine -> in-smem count, with its own refinement of skewed
+ *  pieces and the saturating path for uniform ones) -- the histogram and the scalars accumulate in the same device
+ *  counters, and the distinct k-mers at or above the cutoff rejoin the entries at ent[*nent ..) for the key-order sort.  */
+template<int NW>
+static int spill_count_t(fkgpu_ctx *c, const BucketParams &bp, const u32 *km, int kw, bool pay, u32 nspill, u64 nk,
+                         void *ent, u64 ent_cap, SuperCounters *d_cnt, u64 *nent)
+{ Misc *d_misc = (Misc *) c->misc.p;
+  if (c->spillA.ensure((size_t) (nk + 4) * 8 * NW) || c->spillB.ensure((size_t) (nk + 4) * 8 * NW))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (%llu k-mers of oversize buckets)",nk);
+  stage_begin(c,FKGPU_ST_SPILL);
+  CU(cudaMemsetAsync(&d_cnt->spill_cursor,0,8,c->st));
+#define SPILL_LAUNCH(KWV,PAYV) do { \
+    k_spill_expand<NW,KWV,PAYV><<<nspill,256,0,c->st>>>(bp,km[KWV-1],(Key<NW> *) c->spillA.p,nk,&d_cnt->spill_cursor); KCHECK(); } while (0)
+#define SPILL_LAUNCH_P(KWV) do { if (pay) SPILL_LAUNCH(KWV,true); else SPILL_LAUNCH(KWV,false); } while (0)
+  if (kw == 2) SPILL_LAUNCH_P(2); else if (kw == 3) SPILL_LAUNCH_P(3); else SPILL_LAUNCH_P(4);
+  int P1, P2;
+  choose_levels((long long) nk,&P1,&P2);
+  const int nb1 = 1 << P1;
+  if (c->hist1.ensure((size_t) (nb1 + 1) * 8) || c->off1.ensure((size_t) (nb1 + 1) * 8) || c->cur1.ensure((size_t) (nb1 + 1) * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory");
+  CU(cudaMemsetAsync(c->hist1.p,0,(size_t) (nb1 + 1) * 8,c->st));
+  CU(cudaMemsetAsync(&d_misc->total_pass,0,16,c->st));                 /* total_pass, ovf_cnt, ticket: per-sort scratch */
+  const size_t smh = (size_t) (nb1 + (nb1 & 1)) * 4, sms = smh + (size_t) nb1 * 8;
+  const long long nt = ((long long) nk + TP_TILE(NW) - 1) / TP_TILE(NW);
+  k_tilepart<NW,false><<<(unsigned) nt,TP_TPB,smh,c->st>>>((const Key<NW> *) c->spillA.p,NULL,nk,P1,(u64 *) c->hist1.p); KCHECK();
+  k_scan_small<<<1,1024,0,c->st>>>((const u64 *) c->hist1.p,(u64 *) c->off1.p,(u64 *) c->cur1.p,nb1); KCHECK();
+  int rc = choose_p2(c,P1,&P2);
+  if (rc) return rc;
+  CU(cudaFuncSetAttribute(k_tilepart<NW,true>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sms));
+  k_tilepart<NW,true><<<(unsigned) nt,TP_TPB,sms,c->st>>>((const Key<NW> *) c->spillA.p,(Key<NW> *) c->spillB.p,nk,P1,(u64 *) c->cur1.p); KCHECK();
+  /* the record pipeline reads its options from the context: no profile table here, table cutoff = what the entries need */
+  const fkgpu_config saved = c->cfg;
+  const int wsaved = c->weighted;
+  c->cfg.do_profile = 0; c->cfg.do_table = (ent != NULL) ? (int) bp.ent_min : 0; c->weighted = 0;
+  fkgpu_result tmp; memset(&tmp,0,sizeof(tmp));
+  rc = count_from_level1<NW>(c,(long long) nk,P1,P2,0,&tmp,c->spillB.p,c->spillA.p);
+  c->cfg = saved; c->weighted = wsaved;
+  if (rc) return rc;
+  if (ent != NULL && tmp.ntable > 0)
+    { if (*nent + (u64) tmp.ntable > ent_cap)
+        return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow after the oversize buckets (%llu + %lld > %llu)",*nent,(long long) tmp.ntable,ent_cap);
+      const unsigned gr = (unsigned) ((tmp.ntable + 255) / 256);
+      if (entry_words(c->cfg.kmer) == 3)
+        k_table_to_entries<3><<<gr,256,0,c->st>>>((const uint8_t *) c->table.p,(u64) tmp.ntable,c->kbytes,(Key<3> *) ent,*nent,ent_cap);
+      else
+        k_table_to_entries<2><<<gr,256,0,c->st>>>((const uint8_t *) c->table.p,(u64) tmp.ntable,c->kbytes,(Key<2> *) ent,*nent,ent_cap);
+      KCHECK();
+      *nent += (u64) tmp.ntable;
+    }
+  stage_end(c,FKGPU_ST_SPILL);
+  return FKGPU_OK;
+}
+
 /*  stage B: S super-mer records in `in` (consumed; `scratch` has room for S records too) -> bucket partition -> per-bucket
  *  on-chip expansion + hash count.  Histogram contributions go to c->ghist, scalars to d_misc / d_cnt, the distinct
  *  (key | count) entries to ent[0..ent_cap) when ent != NULL.  The records may point into the read streams of several
@@ -1116,8 +1174,15 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
 
   /* the payload may still be in flight (its all-to-all overlaps the partition above): order the counting kernel behind it */
   if (wait_event != NULL) CU(cudaStreamWaitEvent(c->st,(cudaEvent_t) wait_event,0));
+  static int bigv = -1;
+  if (bigv < 0) { const char *e = getenv("FKGPU_BIG"); bigv = e ? std::max(1,atoi(e)) : 0; }
+  const u32 spill_cap = (u32) std::min<long long>(gmax,1 << 20);
+  if (c->spill_list.ensure((size_t) spill_cap * 4)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  BucketParams bp;
+  u32 km[4]; make_kmask(g.k,km);
+  const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
   stage_begin(c,FKGPU_ST_BUCKET);
-  { BucketParams bp;
+  {
     bp.recs = (const u64 *) recs; bp.seq = d_seq; bp.starts = gstart; bp.ends = gstart + 1; bp.nitems = gmax; bp.k = g.k;
     bp.nranks = nranks; bp.pbits = g.pbits; bp.payload = (const uint4 *) payload;
     for (int r = 0; r < SUP_MAXRANKS; r++)
@@ -1128,8 +1193,9 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
     bp.ent = ent; bp.ent_cap = ent_cap; bp.ent_counter = &d_cnt->nent;
     bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
-    u32 km[4]; make_kmask(g.k,km);
-    const int kw = (2*g.k + 31) / 32;            /* 32-bit words of a key: 2 (k <= 32), 3 (k <= 48), 4 */
+    /* groups beyond this many super-mers leave the chip (FKGPU_BIG overrides; the old kernel streams everything) */
+    bp.big = (bcv == 14) ? 0xffffffffu : (u32) (bigv > 0 ? bigv : (bcv == 3 ? 256 : 2048));
+    bp.spill_cnt = &d_cnt->nspill; bp.spill_list = (u32 *) c->spill_list.p; bp.spill_cap = spill_cap; bp.spill_kmers = &d_cnt->spill_kmers;
     if (bcv == 3)
       { /* warp-private tables: a warp owns a group from load to emit */
 #define BW_LAUNCH(KWV,PAYV,WIDEV) do { \
@@ -1177,6 +1243,18 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
   CU(cudaStreamSynchronize(c->st));
   if (hc->fail) return set_err(FKGPU_E_CUDA,"internal: %u bucket groups could not be counted on chip",hc->fail);
   if (ent != NULL && hc->nent > ent_cap) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow (%llu > %llu)",hc->nent,ent_cap);
+  if (hc->nspill > 0)
+    { if (hc->nspill > spill_cap) return set_err(FKGPU_E_CUDA,"internal: %u oversize bucket groups exceed the list of %u",hc->nspill,spill_cap);
+      const u32 nsp = hc->nspill; const u64 nkm = hc->spill_kmers;
+      u64 ne = hc->nent;
+      int rc = (g.k <= 32) ? spill_count_t<1>(c,bp,km,kw,payload != NULL,nsp,nkm,ent,ent_cap,d_cnt,&ne)
+                           : spill_count_t<2>(c,bp,km,kw,payload != NULL,nsp,nkm,ent,ent_cap,d_cnt,&ne);
+      if (rc) return rc;
+      hc->nent = ne;
+      CU(cudaMemcpyAsync(hm,d_misc,sizeof(*hm),cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      c->st_spill_acc += (long long) nkm;
+    }
   *ngroups = gmax;
   return FKGPU_OK;
 }
@@ -1316,7 +1394,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   collect_times(c,res);
   c->last_path = 1;
   c->st_super = (long long) hc.nrec; c->st_ent = want_entries ? (long long) hc.nent : 0; c->st_groups = gmax;
-  c->st_split = hc.pad; c->st_spill = 0;
+  c->st_split = hc.pad; c->st_spill = c->st_spill_acc;
   single_run(c,res);
   return FKGPU_OK;
 }
@@ -1485,7 +1563,7 @@ static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *
   if (res->nruns == 1) res->table = c->run_p[0];
   c->last_ndist = (long long) hm.ndistinct;
   c->last_path = 1;
-  c->st_super = S; c->st_ent = ents; c->st_groups = groups; c->st_rounds = nrounds; c->st_split = splits; c->st_spill = 0;
+  c->st_super = S; c->st_ent = ents; c->st_groups = groups; c->st_rounds = nrounds; c->st_split = splits; c->st_spill = c->st_spill_acc;
   (void) fails;
   return FKGPU_OK;
 }
@@ -1562,6 +1640,7 @@ static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
 static void init_result(fkgpu_ctx *c, fkgpu_result *res)
 { memset(res,0,sizeof(*res));
   memset(c->ms_bank,0,sizeof(c->ms_bank));
+  c->st_spill_acc = 0;
   res->kmer = c->cfg.kmer;
   res->kmer_bytes = c->kbytes;
   memset(c->used,0,sizeof(c->used));

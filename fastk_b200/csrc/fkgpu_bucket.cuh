@@ -35,6 +35,19 @@ namespace fk {
 
 #define BK_SMEM   ((size_t) BK_DC*8*2 + (size_t) BK_DC*4 + (size_t) BK_TS*4 + (size_t) BK_GC*BK_ROW*4)
 
+/*  one warp lists an oversize group for the record pipeline and adds up the k-mers its super-mers cover */
+__device__ __forceinline__ void spill_group(const BucketParams &p, long long g, u64 r0, u64 r1, u32 lane)
+{ u64 s = 0;
+  for (u64 i = r0 + lane; i < r1; i += 32) s += ((p.recs[i] >> p.pbits) & 63ull) + 1ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
+  if (lane == 0)
+    { const u32 at = atomicAdd(p.spill_cnt,1u);
+      if (at < p.spill_cap) p.spill_list[at] = (u32) g;
+      atomicAdd(p.spill_kmers,s);
+    }
+}
+
 template<int KW, bool PAY, bool WIDE>
 __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 klast)
 { static_assert(KW >= 2 && KW <= 4 && (!WIDE || KW == 4) && BK_DC < 65535 && BK_TS >= 2*BK_DC,"bucket kernel geometry");
@@ -59,6 +72,10 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
   for (long long g = blockIdx.x; g < p.nitems; g += gridDim.x)
     { const u64 r0 = p.starts[g], r1 = p.ends[g];
       if (r1 <= r0) continue;
+      if (r1 - r0 > (u64) p.big)
+        { if (warp == 0) spill_group(p,g,r0,r1,lane);
+          continue;
+        }
       u32 R = 1, rd = 0;                                /* current hash class: keys with ((h >> 20) & (R-1)) == rd */
       for (;;)
         { /* ---- clear ---- */
@@ -289,6 +306,7 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
   for (long long g = (long long) blockIdx.x * BW_WARPS + warp; g < p.nitems; g += nwarps)
     { const u64 r0 = p.starts[g], r1 = p.ends[g];
       if (r1 <= r0) continue;
+      if (r1 - r0 > (u64) p.big) { spill_group(p,g,r0,r1,lane); continue; }
       u32 R = 1, rd = 0;
       for (;;)
         { { uint4 *s4 = (uint4 *) slot;
@@ -454,6 +472,104 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
       if (c) atomicAdd(p.g_hist + i,(u64) c);
     }
   if (lane == 0 && ndist) atomicAdd(p.g_ndistinct,(u64) ndist);
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/*  Spilled groups: every k-mer of the listed groups is written out as a canonical Key<NW> record (the unit of the record
+ *  pipeline: count.c:339-542 restated per instance, as k_scan does from the reads).  One CTA per listed group, its warps
+ *  take 32 super-mers at a time; a warp reserves room for its batch with one global atomic.                            */
+template<int NW, int KW, bool PAY>
+__global__ void __launch_bounds__(256) k_spill_expand(BucketParams p, u32 klast, Key<NW> *out, u64 out_cap, u64 *cursor)
+{ __shared__ __align__(16) u32 s_rows[8][32*BK_ROW];
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u64 pmask = (1ull << p.pbits) - 1ull;
+  u32 *rows = s_rows[warp];
+  const long long g = p.spill_list[blockIdx.x];
+  const u64 r0 = p.starts[g], r1 = p.ends[g];
+  for (u64 q0 = r0 + 32ull*warp; q0 < r1; q0 += 32ull*8)
+    { const u32 ns = (u32) ((r1 - q0 < 32ull) ? (r1 - q0) : 32ull);
+      u32 l = 0;
+      if (lane < ns)
+        { const u64 sm = p.recs[q0 + lane];
+          l = (u32) ((sm >> p.pbits) & 63u) + 1u;
+          u64 ps = sm & pmask;
+          uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
+          if (PAY)
+            { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
+          else
+            { const u32 *sq = p.seq;
+              if (p.nranks > 1)
+                { int r = 0;
+#pragma unroll 1
+                  for (int q = 1; q < p.nranks; q++)
+                    if (ps >= p.pbase[q]) r = q;
+                  ps -= p.pbase[r]; sq = p.seqr[r];
+                }
+              const u32 *gp = sq + (ps >> 4);
+              const int sh = 2*(int) (ps & 15ull);
+              const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);
+              u32 x[9];
+#pragma unroll
+              for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
+              d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
+                                 __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
+              d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
+                                 __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
+            }
+        }
+      u32 incl = l;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        { const u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+          if ((int) lane >= o) incl += y;
+        }
+      const u32 T   = __shfl_sync(0xffffffffu,incl,31);
+      const u32 pre = incl - l;
+      u64 base = 0;
+      if (lane == 0) base = atomicAdd(cursor,(u64) T);
+      base = __shfl_sync(0xffffffffu,base,0);
+      __syncwarp();
+      u32 before = 0;
+      for (u32 g0 = 0; g0 < T; g0 += 32)
+        { const u32 rel = pre - g0;
+          const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
+          const u32 si  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;
+          before += __popc(m);
+          const u32 ps_ = __shfl_sync(0xffffffffu,pre,si & 31u);
+          if (g0 + lane < T)
+            { const u32 j = g0 + lane - ps_;
+              u32 F[KW], G[KW];
+              supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
+              const Key<2> key = strands_canon<KW>(F,G);
+              const u64 o = base + g0 + lane;
+              if (o < out_cap)
+                { Key<NW> rec;
+                  rec.w[0] = key.w[0];
+                  if (NW > 1) rec.w[NW > 1 ? 1 : 0] = key.w[1];
+                  out[o] = rec;
+                }
+            }
+        }
+      __syncwarp();
+    }
+}
+
+/*  table records [kbytes key][u16 LE count] (what the record pipeline leaves) -> distinct entries appended at ent[at0 ..):
+ *  the spilled k-mers rejoin the entries of the on-chip count before the key-order sort.                               */
+template<int EW>
+__global__ void __launch_bounds__(256) k_table_to_entries(const uint8_t *tab, u64 n, int kbytes, Key<EW> *ent, u64 at0, u64 ent_cap)
+{ const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || at0 + i >= ent_cap) return;
+  const uint8_t *e = tab + i * (u64) (kbytes + 2);
+  u64 w[2] = { 0ull, 0ull };
+  for (int b = 0; b < kbytes; b++) w[b >> 3] |= (u64) e[b] << (56 - 8*(b & 7));
+  const u64 c = (u64) e[kbytes] | ((u64) e[kbytes+1] << 8);
+  Key<EW> r;
+  r.w[0] = w[0];
+  if (EW == 3) { r.w[1] = w[1]; r.w[EW == 3 ? 2 : 1] = c; }
+  else r.w[1] = w[1] | c;
+  ent[at0 + i] = r;
 }
 
 }  // namespace fk

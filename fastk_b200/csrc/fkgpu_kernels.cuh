@@ -1332,6 +1332,11 @@ struct BucketParams
     void      *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL): Key<2> (key | count), or Key<3> (key, count) when k > 56 */
     u32        ent_min;                                  /* only entries with (saturated) count >= ent_min are emitted */
     u32       *g_fail;                                   /* set if a group could not be counted */
+    /* groups of more than `big` super-mers (a giant bucket: a high-copy repeat, a low-complexity run) are not counted on chip:
+       one CTA / warp would grind through them alone.  They are listed here and counted by the record pipeline instead.     */
+    u32        big;
+    u32       *spill_cnt; u32 *spill_list; u32 spill_cap;
+    u64       *spill_kmers;                              /* k-mers covered by the listed groups */
   };
 
 /*  Strand arithmetic on KW = ceil(2k/32) 32-bit words (most significant first; the 2k key bits left aligned, the

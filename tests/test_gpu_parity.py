@@ -133,6 +133,49 @@ def test_forced_bucket_geometry(bbits):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_everything_spills_to_the_record_pipeline():
+    """FKGPU_BIG=48: every bucket group of more than 48 super-mers is handed to the record pipeline (the path giant buckets
+    take: high-copy repeats, low-complexity runs), the rest is counted on chip, and both meet again in the entries.  Re-runs
+    parity tests in a fresh process (the override is read once): counts, saturation, profiles, streamed ingest."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, FKGPU_BIG="48")
+    me = os.path.join(here, "test_gpu_parity.py")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", me + "::test_medium_30x", me + "::test_long_reads_hifi_like",
+                        me + "::test_saturation_known_answer", me + "::test_profiles_match_oracle", me + "::test_edge_cases",
+                        me + "::test_multi_round_count_leaves_disjoint_sorted_runs"],
+                       capture_output=True, text=True, timeout=1500, env=env, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_repeat_family_and_low_complexity_reads(oracle_lib):
+    """A 400 bp repeat unit in 60 000 reads (its k-mers saturate: count > 32767), poly-A and dinucleotide reads, on a random
+    background: the repeat's minimizer buckets hold tens of thousands of super-mers each -- far beyond what one CTA
+    should grind through -- and leave the chip for the record pipeline; nothing errors out, everything matches the oracle."""
+    rng = np.random.default_rng(19)
+    unit = bytes(b"ACGT"[x] for x in rng.integers(0, 4, 400))
+    flank = lambda: bytes(b"ACGT"[x] for x in rng.integers(0, 4, 30))           # noqa: E731
+    reads = [flank() + unit + flank() for _ in range(60_000)]
+    reads += [b"A" * 150] * 3000 + [b"AC" * 75] * 2000 + [b"T" * 200] * 500
+    reads += synth.sample_reads(synth.random_genome(100_000, 5), 10_000, 150, 0.003, 6)
+    g = FastKGPU(k=40, table_cutoff=1, nthreads=2)
+    try:
+        want = oracle_lib.count(reads, 40, cutoff=1)
+        for i, (bases, boff) in enumerate(synth.blocks(reads)):
+            g.ingest(bases, boff.astype(np.int32), tid=i % 2)
+        got = g.finish(fetch_table=True)
+        st = g.last_stats()
+        assert st["path"] == 1 and st["spilled_kmers"] > 0, st
+        assert got.nkmers == want["nkmers"] and got.ndistinct == want["ndistinct"] and got.max_inst == want["max_inst"]
+        assert np.array_equal(got.hist[1:], want["hist"][1:])
+        assert np.array_equal(got.table, want["table"])
+        assert got.hist[32767] > 300
+    finally:
+        g.close()
+
+
 def test_long_reads_hifi_like(oracle_lib):
     genome = synth.random_genome(300_000, 31)
     reads = synth.sample_reads(genome, 400, 15_000, 0.001, 32)
