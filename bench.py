@@ -556,7 +556,7 @@ def main():
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),
                            "record_bytes": W, "pipeline": "super-mer" if st["path"] == 1 else "records",
                            "supermer_records": st["supermers"], "rounds": st.get("rounds", 1), "sorted_runs": getattr(res, "nruns", 1),
-                           "split_classes": st.get("split_classes", 0), "spilled_kmers": st.get("spilled_kmers", 0),
+                           "split_classes": st.get("split_classes", 0), "spilled_kmers": st.get("spilled_kmers", 0), "supermers_expanded": st.get("supermers_expanded", 0),
                            "mem_limit_gb": a.mem_limit_gb, "reads": "generated on the device" if a.device_gen else "host generator",
                            "timed_region": "packed reads resident in HBM -> sorted [key][count] table + histogram in pinned host memory",
                            "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"

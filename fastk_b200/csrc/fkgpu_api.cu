@@ -126,7 +126,7 @@ struct fkgpu_ctx
     DevBuf       bufC, roff1, l1k;     /* multi-round count: second entry buffer, record level-1 offsets, k-mers per level-1 bucket */
     cudaEvent_t  ev_sorted[FKGPU_D2H_CHUNKS], ev_d2h = nullptr;
     bool         d2h_pending = false;  /* a table copy on the copy stream still reads c->table                            */
-    long long    st_rounds = 0, st_split = 0, st_spill = 0, st_spill_acc = 0;
+    long long    st_rounds = 0, st_split = 0, st_spill = 0, st_spill_acc = 0, st_expanded = 0, st_exp_acc = 0;
     int64_t h_hist[FKGPU_HIST_BINS];
 
     /* profile lookup table built by finish when cfg.do_profile */
@@ -250,7 +250,7 @@ extern "C" int fkgpu_last_path(fkgpu_ctx *c) { return c ? c->last_path : 0; }
 extern "C" int fkgpu_last_stats(fkgpu_ctx *c, int64_t *v)
 { if (c == NULL || v == NULL) return set_err(FKGPU_E_ARG,"fkgpu_last_stats: NULL argument");
   v[0] = c->last_path; v[1] = c->st_super; v[2] = c->st_ent; v[3] = c->st_groups;
-  v[4] = c->st_rounds; v[5] = c->st_split; v[6] = c->st_spill; v[7] = 0;
+  v[4] = c->st_rounds; v[5] = c->st_split; v[6] = c->st_spill; v[7] = c->st_expanded;
   return FKGPU_OK;
 }
 
@@ -509,6 +509,9 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
 
   K *X = (K *) bufX, *Y = (K *) bufY;
   const u64 *offs = (const u64 *) c->off1.p;
+  /* per-sort scratch scalars (total_pass, ovf_cnt, ticket): a count may run this stage more than once (oversize buckets
+     through the record pipeline, then the entries; one sort per round)                                                  */
+  CU(cudaMemsetAsync(&d_misc->total_pass,0,16,c->st));
 
   if (P2 > 0)
     { if (c->off2.ensure((size_t) (m + 1) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (off2)");
@@ -1010,7 +1013,7 @@ static bool super_path_ok(fkgpu_ctx *c) { return super_path_ok_k(c->cfg.kmer); }
 /*  words of a distinct entry: (key | count in the low 16 bits) fits two words up to k = 56; beyond, the count takes a third */
 static int entry_words(int kmer) { return kmer > 56 ? 3 : 2; }
 
-struct SuperCounters { u64 nrec, nkmers, nent, spill_kmers, spill_cursor; u32 fail, pad, nspill, pad2; };
+struct SuperCounters { u64 nrec, nkmers, nent, spill_kmers, spill_cursor, sm_seen, sm_expanded; u32 fail, pad, nspill, pad2; };
 
 /*  npos_total = positions over ALL ranks' read streams (multi-GPU: every rank must derive the same bucket-id width) */
 static SuperGeom super_geom(int k, long long npos_total)
@@ -1019,15 +1022,15 @@ static SuperGeom super_geom(int k, long long npos_total)
   g.p2 = 1; while (2*g.p2 <= g.w) g.p2 <<= 1;
   const long long sest = std::max<long long>(1,npos_total / 10);        /* expected # of super-mers */
   int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
-  /* record = [bucket : bbits][# k-mers - 1 : 6][global position : pbits].  The bucket count grows with the input (22 bits up
+  /* record = [bucket : bbits][# k-mers - 1 : 6][strand : 1][global position : pbits].  The bucket count grows with the input (22 bits up
      to 4 G positions, one more per doubling) so that buckets keep ~40 super-mers however many GPUs feed them.            */
   g.pbits = std::max(SUP_PBITS_MIN,ilog2_ceil((unsigned long long) npos_total + 1));
   int bcap = 22 + std::max(0,g.pbits - 32);
-  bcap = std::min(bcap,std::min(SUP_BBITS,64 - SUP_LBITS - g.pbits));
+  bcap = std::min(bcap,std::min(SUP_BBITS,64 - SUP_LBITS - 1 - g.pbits));
   if (bbits > bcap) bbits = bcap;
   { static int forced = -2;                 /* FKGPU_BBITS: force the bucket-id width (tests exercise the 8-GPU geometry on one GPU) */
     if (forced == -2) { const char *e = getenv("FKGPU_BBITS"); forced = e ? atoi(e) : -1; }
-    if (forced >= 0) bbits = std::min(forced,std::min(SUP_BBITS,64 - SUP_LBITS - g.pbits));
+    if (forced >= 0) bbits = std::min(forced,std::min(SUP_BBITS,64 - SUP_LBITS - 1 - g.pbits));
   }
   static int sp1 = -1, sbb = -1;
   if (sp1 < 0) { const char *e = getenv("FKGPU_SP1"); sp1 = e ? atoi(e) : 11; const char *f = getenv("FKGPU_SBB"); sbb = f ? atoi(f) : 0; }
@@ -1157,15 +1160,15 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
     }
   stage_end(c,FKGPU_ST_SUPERREFINE);
 
-  /* groups of whole buckets, ~TS super-mers each (FKGPU_BC=old keeps the previous kernel for A/B runs) */
+  /* groups of whole buckets, ~TS super-mers each */
   static int bcvar = -1, tsv = 224;
   if (bcvar < 0)
-    { const char *e = getenv("FKGPU_BC"); bcvar = (e && strcmp(e,"old") == 0) ? 14 : ((e && strcmp(e,"warp") == 0) ? 3 : 0);
+    { const char *e = getenv("FKGPU_BC"); bcvar = (e && strcmp(e,"cta") == 0) ? 0 : 3;      /* FKGPU_BC=cta: the CTA-wide kernel without dedupe (A/B runs) */
       const char *f = getenv("FKGPU_TS"); if (f) tsv = std::max(8,atoi(f)); else if (bcvar == 3) tsv = 32;
     }
   const bool wide = entry_words(g.k) == 3;
-  const int bcv = (wide && bcvar == 14) ? 0 : bcvar;
-  const u32 TS = (u32) ((bcv != 14) ? std::min(tsv,8192) : std::min(tsv,256));
+  const int bcv = bcvar;
+  const u32 TS = (u32) std::min(tsv,8192);
   const long long gmax = S / TS + 2;
   if (c->gstart.ensure((size_t) (gmax + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (groups)");
   u64 *gstart = (u64 *) c->gstart.p;
@@ -1194,7 +1197,8 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
     bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
     /* groups beyond this many super-mers leave the chip (FKGPU_BIG overrides; the old kernel streams everything) */
-    bp.big = (bcv == 14) ? 0xffffffffu : (u32) (bigv > 0 ? bigv : (bcv == 3 ? 256 : 2048));
+    bp.big = (u32) (bigv > 0 ? bigv : (bcv == 3 ? 256 : 2048));
+    bp.g_stat = &d_cnt->sm_seen;
     bp.spill_cnt = &d_cnt->nspill; bp.spill_list = (u32 *) c->spill_list.p; bp.spill_cap = spill_cap; bp.spill_kmers = &d_cnt->spill_kmers;
     if (bcv == 3)
       { /* warp-private tables: a warp owns a group from load to emit */
@@ -1224,23 +1228,12 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
         else if (wide) BK_LAUNCH_P(4,true);
         else BK_LAUNCH_P(4,false);
       }
-    else
-      {
-#define BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,PAYV) do { \
-      const size_t sm = (size_t) (DC)*16 + (size_t) (CH)*16 + (size_t) (TSL)*4 + (size_t) (DC)*4 + (size_t) (GC)*8*4 + (size_t) ((GC)+2)*4 + (size_t) (GC)*4*4 + (size_t) (CH)*2 + 64; \
-      CU(cudaFuncSetAttribute(k_bucket_count<TPB,GC,CH,DC,TSL,KWV,PAYV>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) sm)); \
-      k_bucket_count<TPB,GC,CH,DC,TSL,KWV,PAYV><<<(unsigned) gmax,TPB,sm,c->st>>>(bp,km[KWV-1]); KCHECK(); } while (0)
-#define BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,KWV) do { \
-      if (payload != NULL) BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,true); else BC_LAUNCH_KP(TPB,GC,CH,DC,TSL,KWV,false); } while (0)
-#define BC_LAUNCH(TPB,GC,CH,DC,TSL) do { \
-      if (kw == 2) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,2); else if (kw == 3) BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,3); else BC_LAUNCH_KW(TPB,GC,CH,DC,TSL,4); } while (0)
-        BC_LAUNCH(256,256,512,512,1024);
-      }
   }
   stage_end(c,FKGPU_ST_BUCKET);
   CU(cudaMemcpyAsync(hc,d_cnt,sizeof(*hc),cudaMemcpyDeviceToHost,c->st));
   CU(cudaMemcpyAsync(hm,d_misc,sizeof(*hm),cudaMemcpyDeviceToHost,c->st));
   CU(cudaStreamSynchronize(c->st));
+  c->st_exp_acc += (long long) hc->sm_expanded;
   if (hc->fail) return set_err(FKGPU_E_CUDA,"internal: %u bucket groups could not be counted on chip",hc->fail);
   if (ent != NULL && hc->nent > ent_cap) return set_err(FKGPU_E_CUDA,"internal: distinct-entry buffer overflow (%llu > %llu)",hc->nent,ent_cap);
   if (hc->nspill > 0)
@@ -1394,7 +1387,7 @@ static int count_packed_super(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   collect_times(c,res);
   c->last_path = 1;
   c->st_super = (long long) hc.nrec; c->st_ent = want_entries ? (long long) hc.nent : 0; c->st_groups = gmax;
-  c->st_split = hc.pad; c->st_spill = c->st_spill_acc;
+  c->st_split = hc.pad; c->st_spill = c->st_spill_acc; c->st_expanded = c->st_exp_acc;
   single_run(c,res);
   return FKGPU_OK;
 }
@@ -1563,7 +1556,7 @@ static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *
   if (res->nruns == 1) res->table = c->run_p[0];
   c->last_ndist = (long long) hm.ndistinct;
   c->last_path = 1;
-  c->st_super = S; c->st_ent = ents; c->st_groups = groups; c->st_rounds = nrounds; c->st_split = splits; c->st_spill = c->st_spill_acc;
+  c->st_super = S; c->st_ent = ents; c->st_groups = groups; c->st_rounds = nrounds; c->st_split = splits; c->st_spill = c->st_spill_acc; c->st_expanded = c->st_exp_acc;
   (void) fails;
   return FKGPU_OK;
 }
@@ -1640,7 +1633,7 @@ static int count_packed_any(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, lo
 static void init_result(fkgpu_ctx *c, fkgpu_result *res)
 { memset(res,0,sizeof(*res));
   memset(c->ms_bank,0,sizeof(c->ms_bank));
-  c->st_spill_acc = 0;
+  c->st_spill_acc = 0; c->st_exp_acc = 0;
   res->kmer = c->cfg.kmer;
   res->kmer_bytes = c->kbytes;
   memset(c->used,0,sizeof(c->used));
@@ -1858,7 +1851,7 @@ extern "C" int fkgpu_super_scan(fkgpu_ctx *c, const uint32_t *d_seq, const uint3
       || hist_bits == NULL || npos < 0 || (npos > 0 && (d_seq == NULL || d_val == NULL)))
     return set_err(FKGPU_E_ARG,"fkgpu_super_scan: bad argument");
   if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_super_scan: k = %d is outside the super-mer path (18..64)",c->cfg.kmer);
-  if (pos_offset + npos > npos_total || super_geom(c->cfg.kmer,npos_total).pbits > 64 - SUP_LBITS - 1)
+  if (pos_offset + npos > npos_total || super_geom(c->cfg.kmer,npos_total).pbits > 64 - SUP_LBITS - 2)
     return set_err(FKGPU_E_ARG,"fkgpu_super_scan: positions [%lld,%lld) do not fit the declared total of %lld",(long long) pos_offset,
                    (long long) (pos_offset + npos),(long long) npos_total);
   CU(cudaSetDevice(c->cfg.device));

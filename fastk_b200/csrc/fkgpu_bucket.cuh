@@ -35,10 +35,60 @@ namespace fk {
 
 #define BK_SMEM   ((size_t) BK_DC*8*2 + (size_t) BK_DC*4 + (size_t) BK_TS*4 + (size_t) BK_GC*BK_ROW*4)
 
+/*  Super-mer record -> its base string (l + k - 1 bases, 2 bits each) left aligned in d[0..8).  With `orient` the bits beyond
+ *  the string are cleared and the string is reverse-complemented when the record says its minimizer is canonical on the
+ *  reverse strand: copies of one genomic locus, read from either strand, then give the SAME string (and the same length), which
+ *  is what lets the bucket kernel count duplicate super-mers once.  `row` (the lane's own 8 words of shared memory) is scratch. */
+template<bool PAY>
+__device__ __forceinline__ void load_supermer(const BucketParams &p, u64 sm, u64 pmask, u32 l, bool orient, u32 *d, u32 *row)
+{ u64 ps = sm & pmask;
+  if (PAY)
+    { const uint4 a = __ldg(p.payload + 2*ps), b = __ldg(p.payload + 2*ps + 1);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    }
+  else
+    { const u32 *sq = p.seq;
+      if (p.nranks > 1)
+        { int r = 0;                    /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
+#pragma unroll 1
+          for (int q = 1; q < p.nranks; q++)
+            if (ps >= p.pbase[q]) r = q;
+          ps -= p.pbase[r]; sq = p.seqr[r];
+        }
+      const u32 *gp = sq + (ps >> 4);
+      const int sh = 2*(int) (ps & 15ull);
+      const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
+      u32 x[9];
+#pragma unroll
+      for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
+#pragma unroll
+      for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
+    }
+  if (orient)
+    { const u32 nb = l + (u32) p.k - 1u;
+      const u32 wq = nb >> 4, wb = 2u*(nb & 15u);
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+        d[t] = ((u32) t < wq) ? d[t] : (((u32) t == wq && wb) ? (d[t] & (0xffffffffu << (32u - wb))) : 0u);
+      if (sm_strand(sm,p.pbits))
+        { /* reverse complement of the 128-base slot, then drop the 128 - nb pad bases that lead it */
+#pragma unroll
+          for (int t = 0; t < 8; t++) row[t] = rc32(d[7-t]);
+          const u32 sh2 = 2u*(128u - nb), ws = sh2 >> 5, bs = sh2 & 31u;
+#pragma unroll
+          for (int t = 0; t < 8; t++)
+            { const u32 a = ((u32) t + ws < 8u) ? row[t + ws] : 0u;
+              const u32 b = ((u32) t + ws + 1u < 8u) ? row[t + ws + 1] : 0u;
+              d[t] = __funnelshift_l(b,a,bs);
+            }
+        }
+    }
+}
+
 /*  one warp lists an oversize group for the record pipeline and adds up the k-mers its super-mers cover */
 __device__ __forceinline__ void spill_group(const BucketParams &p, long long g, u64 r0, u64 r1, u32 lane)
 { u64 s = 0;
-  for (u64 i = r0 + lane; i < r1; i += 32) s += ((p.recs[i] >> p.pbits) & 63ull) + 1ull;
+  for (u64 i = r0 + lane; i < r1; i += 32) s += sm_len(p.recs[i],p.pbits);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
   if (lane == 0)
@@ -99,31 +149,12 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
               u32 l = 0;
               if (lane < nw_)
                 { const u64 sm = p.recs[q0 + w0 + lane];
-                  l = (u32) ((sm >> p.pbits) & 63u) + 1u;
-                  u64 ps = sm & pmask;
-                  uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
-                  if (PAY)
-                    { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
-                  else
-                    { const u32 *sq = p.seq;
-                      if (p.nranks > 1)
-                        { int r = 0;                    /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
-#pragma unroll 1
-                          for (int q = 1; q < p.nranks; q++)
-                            if (ps >= p.pbase[q]) r = q;
-                          ps -= p.pbase[r]; sq = p.seqr[r];
-                        }
-                      const u32 *gp = sq + (ps >> 4);
-                      const int sh = 2*(int) (ps & 15ull);
-                      const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
-                      u32 x[9];
-#pragma unroll
-                      for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
-                      d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
-                                         __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
-                      d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
-                                         __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
-                    }
+                  l = sm_len(sm,p.pbits);
+                  u32 d[8];
+                  u32 *row = rows + lane*BK_ROW;
+                  load_supermer<PAY>(p,sm,pmask,l,false,d,row);
+                  ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
+                  ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
                 }
               /* warp prefix of the lengths: instance x of the warp belongs to the super-mer i with pre[i] <= x < pre[i] + l[i] */
               u32 incl = l;
@@ -269,15 +300,24 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
 
 
 /* ------------------------------------------------------------------------------------------------------------------ */
-/*  k_bucket_count3: the same algorithm with WARP-PRIVATE tables: a warp owns a work group (whole buckets, ~32 super-mers)
- *  from load to emit -- no block barrier anywhere in the loop (the CTA-wide variant above spends ~45 % of its warp time
- *  waiting at the four barriers per group, ncu r2b).  Groups are dealt round-robin to the resident warps.            */
+/*  k_bucket_count3: WARP-PRIVATE tables, duplicate super-mers counted once.
+ *  A warp owns a work group (whole buckets, ~32 super-mers) from load to emit -- no block barrier in the loop.  Per piece of
+ *  <= 32 super-mers (one per lane):
+ *    load     the lane's super-mer as an ORIENTED, zero-padded base string (load_supermer)
+ *    dedupe   at 50x coverage a locus is read ~50 times and its copies sit in the same bucket: the lane hashes its string and
+ *             looks for an identical one among the piece's (tiny open-addressing table over the lanes' own rows); a copy only
+ *             adds 1 to the weight of the first lane that holds the string and drops out (the reference's Supermer_Sort +
+ *             weighted k-mers, MSDsort.c:458-489 + count.c:339-542, without the sort)
+ *    expand   only the distinct super-mers are expanded, one k-mer per lane per round (REDUX.OR + popc mapping)
+ *    count    each k-mer adds its super-mer's weight to the warp's k-mer table (fingerprinted slots, SoA keys)
+ *  Emit, hash classes on overflow, spill of oversize groups: as in the CTA-wide kernel above.                            */
 
 #define BW_WARPS  4
 #define BW_TPB    (32*BW_WARPS)
 #define BW_KC     256                /* distinct keys a warp's class may hold */
 #define BW_SL     512                /* slots per warp (load <= 0.5)          */
-#define BW_WBYTES ((size_t) BW_KC*8*2 + (size_t) BW_KC*4 + (size_t) BW_SL*4 + (size_t) 32*BK_ROW*4)
+#define BW_SS     64                 /* slots of the super-mer dedupe table (32 rows) */
+#define BW_WBYTES ((size_t) BW_KC*8*2 + (size_t) BW_KC*4 + (size_t) BW_SL*4 + (size_t) 32*BK_ROW*4 + (size_t) BW_SS*4 + (size_t) 32*4)
 #define BW_SMEM   (BW_WBYTES*BW_WARPS)
 
 template<int KW, bool PAY, bool WIDE>
@@ -294,9 +334,12 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
   u32 *cnt  = (u32 *) (k1 + BW_KC);                     /* [BW_KC] */
   u32 *slot = cnt + BW_KC;                              /* [BW_SL] */
   u32 *rows = slot + BW_SL;                             /* [32][BK_ROW] */
+  u32 *ssl  = rows + 32*BK_ROW;                         /* [BW_SS] dedupe table: 0 = empty, else (fp : 17)(l - 1 : 6)(pad : 3)(lane + 1 : 6) */
+  u32 *wt   = ssl + BW_SS;                              /* [32] copies of the string lane i holds */
   const u64 pmask = (1ull << p.pbits) - 1ull;
   Entry *ent = (Entry *) p.ent;
   u32 ndist = 0;                                        /* warp-uniform: distinct keys this warp has seen */
+  u32 nsm = 0, nex = 0;                                 /* lane-private: super-mers met / expanded        */
 
   for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BW_TPB) s_hist[i] = 0;
   for (u32 i = lane; i < BW_KC; i += 32) cnt[i] = 0;
@@ -322,35 +365,47 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
           for (u64 q0 = r0; q0 < r1; q0 += 32)
             { if (*ovf) break;
               const u32 ns = (u32) ((r1 - q0 < 32ull) ? (r1 - q0) : 32ull);
-              u32 l = 0;
+              u32 l = 0, hs = 0;
+              u32 *row = rows + lane*BK_ROW;
+              ssl[lane] = 0; ssl[lane + 32] = 0;
+              wt[lane] = 1;
               if (lane < ns)
                 { const u64 sm = p.recs[q0 + lane];
-                  l = (u32) ((sm >> p.pbits) & 63u) + 1u;
-                  u64 ps = sm & pmask;
-                  uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
-                  if (PAY)
-                    { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
-                  else
-                    { const u32 *sq = p.seq;
-                      if (p.nranks > 1)
-                        { int r = 0;
-#pragma unroll 1
-                          for (int q = 1; q < p.nranks; q++)
-                            if (ps >= p.pbase[q]) r = q;
-                          ps -= p.pbase[r]; sq = p.seqr[r];
-                        }
-                      const u32 *gp = sq + (ps >> 4);
-                      const int sh = 2*(int) (ps & 15ull);
-                      const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);
-                      u32 x[9];
-#pragma unroll
-                      for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
-                      d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
-                                         __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
-                      d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
-                                         __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
-                    }
+                  l = sm_len(sm,p.pbits);
+                  u32 d[8];
+                  load_supermer<PAY>(p,sm,pmask,l,true,d,row);
+                  ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
+                  ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
+                  hs = d[0] * 0x9E3779B1u + d[1] * 0x85EBCA77u + d[2] * 0xC2B2AE3Du + d[3] * 0x27D4EB2Fu
+                     + d[4] * 0x165667B1u + d[5] * 0xD3A2646Du + d[6] * 0xFD7046C5u + d[7] * 0xB55A4F09u + l * 0x2545F491u;
+                  hs ^= hs >> 15; hs *= 0x2C1B3C6Du; hs ^= hs >> 13;
                 }
+              __threadfence_block();
+              __syncwarp();
+              /* ---- dedupe: a copy of a string another lane holds only adds to that lane's weight ---- */
+              if (lane < ns)
+                { const u32 tag = (hs & 0xffff8000u) | ((l - 1u) << 9);             /* fingerprint and length: both must agree */
+                  u32 x = hs & (BW_SS-1);
+                  for (;;)
+                    { u32 v = ((volatile u32 *) ssl)[x];
+                      if (v == 0u)
+                        { const u32 old = atomicCAS(&ssl[x],0u,tag | (lane + 1u));
+                          if (old == 0u) break;                                      /* first holder of this string */
+                          v = old;
+                        }
+                      if ((v & 0xfffffe00u) == tag)
+                        { const u32 o = (v & 63u) - 1u;
+                          const uint4 a0 = ((const uint4 *) (rows + o*BK_ROW))[0], a1 = ((const uint4 *) (rows + o*BK_ROW))[1];      /* rows are final since the barrier above */
+                          const uint4 b0 = ((const uint4 *) row)[0], b1 = ((const uint4 *) row)[1];
+                          if (((a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w)) == 0u)
+                            { atomicAdd(&wt[o],1u); l = 0; break; }
+                        }
+                      x = (x+1) & (BW_SS-1);
+                    }
+                  if (R == 1) { nsm++; nex += (l != 0u) ? 1u : 0u; }
+                }
+              __syncwarp();
+              const u32 w = wt[lane];
               u32 incl = l;
 #pragma unroll
               for (int o = 1; o < 32; o <<= 1)
@@ -359,16 +414,22 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
                 }
               const u32 T   = __shfl_sync(0xffffffffu,incl,31);
               const u32 pre = incl - l;
+              /* the lanes that still hold a super-mer, compacted into the (now dead) dedupe table: the i-th holder's
+                 (first instance : 12+)(weight : 6)(lane : 6)                                                          */
+              { const u32 hmask = __ballot_sync(0xffffffffu,l != 0u);
+                if (l != 0u) ssl[__popc(hmask & ((1u << lane) - 1u))] = (pre << 12) | (w << 6) | lane;
+              }
               __syncwarp();
               u32 before = 0;
               for (u32 g0 = 0; g0 < T; g0 += 32)
                 { const u32 rel = pre - g0;
                   const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
-                  const u32 si  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;
+                  const u32 ri  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;     /* my super-mer: the ri-th holder */
                   before += __popc(m);
-                  const u32 ps_ = __shfl_sync(0xffffffffu,pre,si & 31u);
                   if (g0 + lane < T)
-                    { const u32 j = g0 + lane - ps_;
+                    { const u32 hc_ = ssl[ri & 31u];
+                      const u32 si = hc_ & 63u, wsi = (hc_ >> 6) & 63u;
+                      const u32 j = g0 + lane - (hc_ >> 12);
                       u32 F[KW], G[KW];
                       supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
                       const Key<2> key = strands_canon<KW>(F,G);
@@ -388,14 +449,14 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
                                   if (KW > 2) k1[spare] = key.w[1];
                                   __threadfence_block();
                                   const u32 old = atomicCAS(&slot[x],0u,fp | (spare + 1u));
-                                  if (old == 0u) { atomicAdd(&cnt[spare],1u); spare = 0xffffffffu; break; }
+                                  if (old == 0u) { atomicAdd(&cnt[spare],wsi); spare = 0xffffffffu; break; }
                                   v = old;
                                 }
                               if ((v & 0xffff0000u) == fp)
                                 { const u32 ki = (v & 0xffffu) - 1u;
                                   bool eq = (((volatile u64 *) k0)[ki] == key.w[0]);
                                   if (KW > 2) eq = eq && (((volatile u64 *) k1)[ki] == key.w[1]);
-                                  if (eq) { atomicAdd(&cnt[ki],1u); break; }
+                                  if (eq) { atomicAdd(&cnt[ki],wsi); break; }
                                 }
                               x = (x+1) & (BW_SL-1);
                             }
@@ -472,8 +533,10 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
       if (c) atomicAdd(p.g_hist + i,(u64) c);
     }
   if (lane == 0 && ndist) atomicAdd(p.g_ndistinct,(u64) ndist);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { nsm += __shfl_xor_sync(0xffffffffu,nsm,o); nex += __shfl_xor_sync(0xffffffffu,nex,o); }
+  if (lane == 0 && p.g_stat != NULL && nsm) { atomicAdd(p.g_stat,(u64) nsm); atomicAdd(p.g_stat + 1,(u64) nex); }
 }
-
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /*  Spilled groups: every k-mer of the listed groups is written out as a canonical Key<NW> record (the unit of the record
@@ -492,31 +555,12 @@ __global__ void __launch_bounds__(256) k_spill_expand(BucketParams p, u32 klast,
       u32 l = 0;
       if (lane < ns)
         { const u64 sm = p.recs[q0 + lane];
-          l = (u32) ((sm >> p.pbits) & 63u) + 1u;
-          u64 ps = sm & pmask;
-          uint4 *d4 = (uint4 *) (rows + lane*BK_ROW);
-          if (PAY)
-            { d4[0] = __ldg(p.payload + 2*ps); d4[1] = __ldg(p.payload + 2*ps + 1); }
-          else
-            { const u32 *sq = p.seq;
-              if (p.nranks > 1)
-                { int r = 0;
-#pragma unroll 1
-                  for (int q = 1; q < p.nranks; q++)
-                    if (ps >= p.pbase[q]) r = q;
-                  ps -= p.pbase[r]; sq = p.seqr[r];
-                }
-              const u32 *gp = sq + (ps >> 4);
-              const int sh = 2*(int) (ps & 15ull);
-              const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);
-              u32 x[9];
-#pragma unroll
-              for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(gp + t) : 0u;
-              d4[0] = make_uint4(__funnelshift_l(x[1],x[0],sh),__funnelshift_l(x[2],x[1],sh),
-                                 __funnelshift_l(x[3],x[2],sh),__funnelshift_l(x[4],x[3],sh));
-              d4[1] = make_uint4(__funnelshift_l(x[5],x[4],sh),__funnelshift_l(x[6],x[5],sh),
-                                 __funnelshift_l(x[7],x[6],sh),__funnelshift_l(x[8],x[7],sh));
-            }
+          l = sm_len(sm,p.pbits);
+          u32 d[8];
+          u32 *row = rows + lane*BK_ROW;
+          load_supermer<PAY>(p,sm,pmask,l,false,d,row);
+          ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
+          ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
         }
       u32 incl = l;
 #pragma unroll

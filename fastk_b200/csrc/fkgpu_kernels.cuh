@@ -1131,7 +1131,7 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
 /*  Super-mer front end (the reference's own idea, split.c:1016-1393 / Appendix D of SURVEY.md, re-cut for a GPU):
  *  consecutive k-mers that share a canonical minimizer travel together as ONE 8-byte record that points into the
  *  packed reads, which stay resident in HBM:
- *      [bucket:24][len-1:6][position of the first base:34]
+ *      [bucket:<=24][len-1:6][strand:1][position of the first base:>=32]
  *  so the partition passes move < 1 B per k-mer instead of 16, and the counting kernel gathers the bases itself.
  *  Every instance of a canonical k-mer has the same minimizer (the minimum over BOTH strands' m-mers under a
  *  bijective order hash), hence the same bucket: each bucket is counted on chip with no cross-bucket merge.
@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(256) k_compact(CompactParams p)
 
 #define SUP_PBITS_MIN 32                            /* position field width (run time, SuperGeom.pbits): global position over all ranks' read streams */
 #define SUP_LMAX  64
-#define SUP_BBITS 24                                /* most bucket-id bits (bucket + 6 + position bits <= 64; two partition levels of <= 11 + 13 bits) */
+#define SUP_BBITS 24                                /* most bucket-id bits (bucket + 6 + 1 + position bits <= 64; two partition levels of <= 11 + 13 bits) */
 #define SUP_LBITS 6
 #define SUP_MAXRANKS 8                              /* read streams (one per GPU of the node) a record can point into */
 
@@ -1209,7 +1209,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
           { const u32 x = (j < 16) ? __funnelshift_l(W1,W0,2*j) : __funnelshift_l(W2,W1,2*(j-16));   /* 16 bases from position j */
             const u32 f = x >> sh;
             const u32 r = rc32(x) & mmask;                   /* the first m bases reverse-complemented land in the low 2m bits */
-            h[j] = mix32(f < r ? f : r);
+            h[j] = (mix32(f < r ? f : r) & ~1u) | (r < f ? 1u : 0u);     /* low bit: the canonical m-mer is the reverse strand here */
           }
       }
   }
@@ -1240,30 +1240,59 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
           v[j] = v[j] < u ? v[j] : u;
         }
     }
-  /* bucket id of every k-mer start; kept in the thread's own row for the emission loop's dynamic lookups */
+  /* bucket id of every k-mer start (kept in the thread's own row for the emission loop's dynamic lookups) and the strand
+     on which its minimizer is canonical (the low bit of the window minimum)                                            */
   u32 *bk = s_h + t*SUP_RS;
+  u32 smask = 0;                                    /* bit 31-j = minimizer of k-mer j sits on the reverse strand */
 #pragma unroll
   for (int j = 0; j < 32; j++)
-    { v[j] = (v[j] * 0x9E3779B1u) >> (32 - p.bbits);
+    { smask |= (v[j] & 1u) << (31-j);
+      v[j] = ((v[j] & ~1u) * 0x9E3779B1u) >> (32 - p.bbits);
       bk[j] = v[j];
     }
   V96 vv; vv.a = s_val[t]; vv.b = s_val[t+1]; vv.c = s_val[t+2];
   const u32 ok = window_ok(vv,p.k);                 /* bit 31-j = k-mer j of this thread is legal */
+  const u32 lanei = t & 31;
 
-  /* cont bit j: k-mer j continues the super-mer of k-mer j-1 (both legal, same bucket, not on a multiple of 64) */
+  /*  A super-mer is a maximal run of consecutive legal k-mers with the same bucket id, cut every SUP_LMAX k-mers counted from
+      ITS OWN START and at warp boundaries (1024 positions): up to those rare cuts its extent is a property of the sequence,
+      not of where the read sits in the stream, so the copies of a genomic locus in different reads give IDENTICAL super-mers
+      (the bucket kernel counts duplicates once, with a weight: the reference's Supermer_Sort idea, MSDsort.c:458-489).
+      cont bit j: k-mer j continues the super-mer of k-mer j-1.                                                           */
   u32 same = 0;
 #pragma unroll
   for (int j = 1; j < 32; j++) same |= (v[j] == v[j-1] ? 1u : 0u) << (31-j);
   const u32 pb  = __shfl_up_sync(0xffffffffu,v[31],1);
   const u32 pok = __shfl_up_sync(0xffffffffu,ok & 1u,1);
-  if ((t & 1) && pok && pb == v[0]) same |= 0x80000000u;     /* j = 0 of an odd thread is not a multiple of 64: may continue */
-  const u32 okprev = (ok >> 1) | ((t & 1) ? (pok << 31) : 0u);
-  const u32 cont = ok & okprev & same;
+  if (lanei != 0 && pok && pb == v[0]) same |= 0x80000000u;
+  const u32 okprev = (ok >> 1) | ((lanei != 0) ? (pok << 31) : 0u);
+  u32 cont = ok & okprev & same;
+  { /* forced cuts of runs longer than SUP_LMAX.  rs = warp-local index of the k-mer that starts the run my k-mer 0 continues:
+       it sits in the nearest lane to the left that is not wholly inside that run, as the start of its last run.          */
+    const u32 lead0 = (ok >> 31) ? (u32) (1 + __clz(~(cont << 1))) : 0u;          /* my leading run: k-mers 0 .. lead0-1 */
+    const bool c0 = (cont >> 31) != 0u;
+    const u32 inside = __ballot_sync(0xffffffffu,c0 && lead0 == 32);
+    const u32 tc = (~cont) ? (u32) (__ffs(~cont) - 1) : 32u;                      /* trailing k-mers that continue their predecessor */
+    const u32 tailstart = 31u - (tc < 32u ? tc : 31u);                            /* start of the run that reaches my last k-mer */
+    const u32 below = ~inside & ((1u << lanei) - 1u);
+    const u32 sl = below ? (u32) (31 - __clz(below)) : 0u;
+    const u32 ts = __shfl_sync(0xffffffffu,tailstart,sl);
+    if (c0)
+      { const u32 d0 = 32u*lanei - (32u*sl + ts);                                 /* k-mers of the run before my window: >= 1 */
+        const u32 off = (SUP_LMAX - (d0 & (SUP_LMAX-1))) & (SUP_LMAX-1);          /* first j with (d0 + j) a multiple of SUP_LMAX */
+        if (off < lead0) cont &= ~(0x80000000u >> off);
+      }
+  }
   const u32 starts = ok & ~cont;                    /* bit 31-j = a super-mer starts at j */
-  /* length of this thread's leading run as seen from the previous thread (k-mer 0 legal, then cont bits from j = 1) */
+  /* how far a super-mer that reaches the end of my window runs on: leading runs of the next two lanes (<= SUP_LMAX in all) */
   const u32 lead = (ok >> 31) ? (u32) (1 + __clz(~(cont << 1))) : 0u;
-  const u32 nlead = __shfl_down_sync(0xffffffffu,lead,1);
-  const u32 nb0   = __shfl_down_sync(0xffffffffu,v[0],1);
+  const u32 c0f = cont >> 31;
+  u32 n1lead = __shfl_down_sync(0xffffffffu,lead,1), n1c0 = __shfl_down_sync(0xffffffffu,c0f,1);
+  u32 n2lead = __shfl_down_sync(0xffffffffu,lead,2), n2c0 = __shfl_down_sync(0xffffffffu,c0f,2);
+  if (lanei >= 31) n1c0 = 0;
+  if (lanei >= 30) n2c0 = 0;
+  const u32 ext1 = n1c0 ? n1lead : 0u;
+  const u32 ext  = ext1 + ((ext1 == 32u && n2c0) ? n2lead : 0u);
 
   const u32 nrun = __popc(starts);
   u32 incl = nrun;
@@ -1298,25 +1327,18 @@ __global__ void __launch_bounds__(SCAN_TPB) k_super(SuperParams p)
       const u32 after = (j == 31) ? 0u : (0xffffffffu >> (j+1));
       const u32 stop = ~cont & after;
       const int e = stop ? __clz(stop) : SCAN_PPT;       /* window-local end (exclusive) */
-      int len = e - j;
+      u32 len = (u32) (e - j);
+      if (e == SCAN_PPT) len += ext;                     /* runs on into the next lanes' windows */
+      if (len > SUP_LMAX) len = SUP_LMAX;                /* cannot happen (forced cuts); keeps the length field sound */
       const u32 b = bk[j];
-      if (e == SCAN_PPT && !(t & 1) && nlead && nb0 == b) len += (int) nlead;     /* runs on into the next thread's window */
-      p.out[pos++] = ((u64) b << (64 - p.bbits)) | ((u64) (len-1) << p.pbits) | (tile0 + (u64) (base + j));
+      const u32 sb = (smask >> (31-j)) & 1u;
+      p.out[pos++] = ((u64) b << (64 - p.bbits)) | ((u64) (len-1) << (p.pbits+1)) | ((u64) sb << p.pbits) | (tile0 + (u64) (base + j));
     }
 }
 
-/* ---------------------------------------------------------------------------------------------- */
-/*  k_bucket_count: one CTA per group of whole minimizer buckets.  Streams the group's super-mers in chunks of
- *  BC_SC records: expand every k-mer (canonical form as in k_scan), hash-count it in a shared-memory table whose
- *  distinct keys live in a pool that persists across chunks.  Emits histogram contributions and, if wanted, the
- *  distinct (key | saturated count in the low 16 bits) records for the final key-order sort.
- *  A group whose distinct keys overflow the pool is redone in 2x more rounds, each round taking the k-mers whose
- *  hash falls in its residue class (the super-mers are simply re-expanded).                                   */
-
-/* template parameters of k_bucket_count: BC_TPB threads, BC_GC super-mers held in smem per piece, BC_CH new keys
- * accepted per piece, BC_DC distinct-key pool, BC_TS hash slots (>= BC_DC + BC_CH so a probe always terminates)   */
-#define BC_EMPTY 0xffffffffu
-#define BC_PERS  0x80000000u
+/*  fields of a super-mer record [bucket : bbits][# k-mers - 1 : 6][strand : 1][position of the first base : pbits]  */
+__device__ __forceinline__ u32 sm_len(u64 sm, int pbits)    { return (u32) ((sm >> (pbits+1)) & 63ull) + 1u; }
+__device__ __forceinline__ u32 sm_strand(u64 sm, int pbits) { return (u32) (sm >> pbits) & 1u; }
 
 struct BucketParams
   { const u64 *recs; const u32 *seq;
@@ -1331,12 +1353,13 @@ struct BucketParams
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
     void      *ent; u64 ent_cap; u64 *ent_counter;       /* distinct entries out (may be NULL): Key<2> (key | count), or Key<3> (key, count) when k > 56 */
     u32        ent_min;                                  /* only entries with (saturated) count >= ent_min are emitted */
-    u32       *g_fail;                                   /* set if a group could not be counted */
+    u32       *g_fail;                                   /* [0] set if a group could not be counted, [1] # of hash classes split */
     /* groups of more than `big` super-mers (a giant bucket: a high-copy repeat, a low-complexity run) are not counted on chip:
        one CTA / warp would grind through them alone.  They are listed here and counted by the record pipeline instead.     */
     u32        big;
     u32       *spill_cnt; u32 *spill_list; u32 spill_cap;
     u64       *spill_kmers;                              /* k-mers covered by the listed groups */
+    u64       *g_stat;                                   /* [0] super-mers met by the bucket kernel, [1] of them expanded (the others were copies) */
   };
 
 /*  Strand arithmetic on KW = ceil(2k/32) 32-bit words (most significant first; the 2k key bits left aligned, the
@@ -1397,247 +1420,13 @@ __device__ __forceinline__ u32 bucket_hash(const Key<2> &a)
   return h;
 }
 
-template<int BC_TPB, int BC_GC, int BC_CH, int BC_DC, int BC_TS, int KW, bool PAY>
-__global__ void __launch_bounds__(BC_TPB,1536/BC_TPB) k_bucket_count(BucketParams p, u32 klast)
-{ static_assert(BC_GC <= BC_TPB && BC_DC + BC_CH <= BC_TS && BC_DC <= 1024 && KW >= 2 && KW <= 4,"bucket kernel geometry");
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  Key<2> *pool  = (Key<2> *) s_raw;                                  /* [BC_DC]              */
-  Key<2> *rec   = pool + BC_DC;                                      /* [BC_CH]              */
-  u32    *slot  = (u32 *) (rec + BC_CH);                             /* [BC_TS]              */
-  u32    *ocnt  = slot + BC_TS;                                      /* [BC_DC]              */
-  u32    *sbase = ocnt + BC_DC;                                      /* [BC_GC][8] base words */
-  u32    *spre  = sbase + BC_GC*8;                                   /* [BC_GC+1] prefix of the lengths */
-  u32    *sg0   = spre + BC_GC + 2;                                  /* [BC_GC][4] reverse strand of each super-mer's first k-mer */
-  unsigned short *newl = (unsigned short *) (sg0 + BC_GC*4);         /* [BC_CH] slots claimed in this piece */
-  __shared__ u32 s_nnew[2], s_ovf, s_ecnt, s_hist[SC_SMALLHIST], s_wsum[BC_TPB/32];
-  __shared__ u64 s_ebase;
-
-  const long long g = blockIdx.x;
-  if (g >= p.nitems) return;
-  const u64 r0 = p.starts[g], r1 = p.ends[g];
-  if (r1 <= r0) return;
-  const int ks = 32*KW - 2*p.k;                  /* zero bits below the key in its last word */
-
-  /* work stack of (rounds, residue) classes: a class whose distinct keys overflow the pool splits in two */
-  u32 stR[28], stD[28];
-  int sp = 1;
-  stR[0] = 1; stD[0] = 0;
-  while (sp > 0)
-    { sp--;
-      const u32 rounds = stR[sp], rd = stD[sp];
-      bool failed = false;
-      if (threadIdx.x == 0 && rounds > 1) atomicAdd(p.g_fail + 1,1u);      /* statistics: residue classes run after a pool overflow */
-      for (u32 i = threadIdx.x; i < BC_TS; i += BC_TPB) slot[i] = BC_EMPTY;
-      for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB) s_hist[i] = 0;
-      if (threadIdx.x == 0) { s_nnew[0] = 0; s_nnew[1] = 0; s_ovf = 0; }
-      u32 nd = 0, par = 0;                       /* distinct keys in the pool; parity of the chunk counter in use */
-      __syncthreads();
-      for (u64 q0 = r0; q0 < r1 && !failed; q0 += BC_GC)
-        { const u32 ns = (u32) ((r1 - q0 < BC_GC) ? (r1 - q0) : BC_GC);
-          /* load one piece: thread t unpacks super-mer t; block scan of the lengths */
-          u32 l = 0;
-          if (threadIdx.x < ns)
-            { const u64 sm = p.recs[q0 + threadIdx.x];
-              l = (u32) ((sm >> p.pbits) & 63u) + 1u;
-              u64 ps = sm & ((1ull << p.pbits) - 1ull);
-              u32 *d = sbase + threadIdx.x*8;
-              if (PAY)
-                { const uint4 a = __ldg(p.payload + 2*ps), b = __ldg(p.payload + 2*ps + 1);
-                  *(uint4 *) d = a; *(uint4 *) (d + 4) = b;
-                }
-              else
-                { const u32 *sq = p.seq;
-                  if (p.nranks > 1)
-                    { int r = 0;                          /* owner = last rank whose base is <= ps; its stream may live on a peer GPU */
-#pragma unroll 1
-                      for (int q = 1; q < p.nranks; q++)
-                        if (ps >= p.pbase[q]) r = q;
-                      ps -= p.pbase[r]; sq = p.seqr[r];
-                    }
-                  const u32 *g = sq + (ps >> 4);
-                  const int sh = 2*(int) (ps & 15ull);
-                  const int nw = (int) ((2*(l + p.k - 1) + sh + 31) >> 5);          /* packed words this super-mer touches */
-                  u32 x[9];
-#pragma unroll
-                  for (int t = 0; t < 9; t++) x[t] = (t < nw) ? __ldg(g + t) : 0u;
-#pragma unroll
-                  for (int t = 0; t < 8; t++) d[t] = __funnelshift_l(x[t+1],x[t],sh);
-                }
-              /* both strands of the first k-mer: every loader thread does this together, so sliding onto the next
-                 super-mer inside the insert loop is a plain load instead of a divergent recomputation           */
-              u32 F0[KW], G0[KW];
-              supermer_strands<KW>(d,0,p.k,klast,F0,G0);
-              u32 *gq = sg0 + threadIdx.x*4;
-#pragma unroll
-              for (int t = 0; t < KW; t++) gq[t] = G0[t];
-            }
-          u32 incl = l;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1)
-            { u32 y = __shfl_up_sync(0xffffffffu,incl,o);
-              if ((threadIdx.x & 31) >= o) incl += y;
-            }
-          if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
-          __syncthreads();
-          u32 woff = 0;
-          { const u32 lane = threadIdx.x & 31;
-            u32 x = (lane < BC_TPB/32) ? s_wsum[lane] : 0u;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-              { u32 y = __shfl_up_sync(0xffffffffu,x,o);
-                if ((int) lane >= o) x += y;
-              }
-            const u32 wid = threadIdx.x >> 5;
-            woff = __shfl_sync(0xffffffffu,x,wid ? wid-1 : 0);
-            if (wid == 0) woff = 0;
-          }
-          if (threadIdx.x < BC_GC) spre[threadIdx.x+1] = woff + incl;
-          if (threadIdx.x == 0) spre[0] = 0;
-          __syncthreads();
-          const u32 total = spre[ns];
-          /* fused expand + insert: every thread takes `per` consecutive k-mer instances of the piece; the first is
-             located by binary search in the prefix and cut out of the base string, the next ones slide along the
-             same super-mer.  Only a k-mer that claims an empty slot is written to rec[] (before its CAS, so that
-             whoever finds the slot can compare against it); the others never leave registers.                   */
-          { const u32 per = (total + BC_TPB - 1) / BC_TPB;
-            const u32 i0 = threadIdx.x * per;
-            const u32 i1 = (i0 + per < total) ? (i0 + per) : total;
-            u32 myrec = 0xffffffffu;
-            if (i0 < i1)
-              { u32 lo = 0, hi = ns;
-                while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (spre[mid] <= i0) lo = mid; else hi = mid; }
-                u32 sidx = lo, j = i0 - spre[lo], slen = spre[lo+1] - spre[lo];
-                const u32 *sb = sbase + sidx*8;
-                u32 F[KW], G[KW];
-                supermer_strands<KW>(sb,(int) j,p.k,klast,F,G);
-                for (u32 i = i0; i < i1; i++)
-                  { if (i > i0)
-                      { j++;
-                        if (j >= slen)
-                          { sidx++; j = 0; slen = spre[sidx+1] - spre[sidx];
-                            sb = sbase + sidx*8;
-                            const u32 *gq = sg0 + sidx*4;
-#pragma unroll
-                            for (int t = 0; t < KW; t++) { F[t] = sb[t]; G[t] = gq[t]; }
-                            F[KW-1] &= klast;
-                          }
-                        else
-                          { const u32 qb = j + p.k - 1;
-                            strands_roll<KW>(F,G,(sb[qb >> 4] >> (30 - 2*(qb & 15))) & 3u,ks,klast);
-                          }
-                      }
-                    const Key<2> key = strands_canon<KW>(F,G);
-                    const u32 h = bucket_hash<KW>(key);
-                    if (((h >> 20) & (rounds-1)) != rd) continue;
-                    u32 x = h & (BC_TS-1);
-                    for (u32 step = 0; ; step++)
-                      { /* a probe this long means the table is (nearly) full: split the class instead of grinding on */
-                        if (step >= FKGPU_PROBE_CAP) { s_ovf = 1; break; }
-                        u32 v = ((volatile u32 *) slot)[x];
-                        if (v == BC_EMPTY)
-                          { if (myrec == 0xffffffffu)
-                              { myrec = atomicAdd(&s_nnew[par],1u);
-                                if (myrec >= BC_CH) { s_ovf = 1; myrec = 0xffffffffu; break; }
-                              }
-                            rec[myrec] = key;
-                            __threadfence_block();
-                            u32 old = atomicCAS(&slot[x],BC_EMPTY,(myrec << 16) | 1u);
-                            if (old == BC_EMPTY) { newl[myrec] = (unsigned short) x; myrec = 0xffffffffu; break; }
-                            v = old;
-                          }
-                        if (v & BC_PERS)
-                          { const u32 pi = v & ~BC_PERS;
-                            if (key_eq<2>(pool[pi],key)) { atomicAdd(&ocnt[pi],1u); break; }
-                          }
-                        else if (key_eq<2>(rec[v >> 16],key)) { atomicAdd(&slot[x],1u); break; }
-                        x = (x+1) & (BC_TS-1);
-                      }
-                  }
-              }
-            if (myrec != 0xffffffffu) newl[myrec] = 0xffffu;        /* a record allocated for a claim that lost its race */
-          }
-          __syncthreads();
-          /* migrate the new owners into the pool (holes -- lost races -- become pool entries of count 0) */
-          { const u32 nnew = s_nnew[par] < BC_CH ? s_nnew[par] : BC_CH, nd0 = nd;
-            if (nd0 + nnew > BC_DC || s_ovf) { failed = true; break; }
-            if (threadIdx.x == 0) s_nnew[par ^ 1] = 0;           /* the other counter: unused until after the next barrier */
-            for (u32 t = threadIdx.x; t < nnew; t += BC_TPB)
-              { const u32 x = newl[t];
-                if (x == 0xffffu) { ocnt[nd0 + t] = 0; continue; }
-                const u32 v = slot[x];
-                pool[nd0 + t] = rec[t];
-                ocnt[nd0 + t] = v & 0xffffu;
-                slot[x] = BC_PERS | (nd0 + t);
-              }
-            nd = nd0 + nnew; par ^= 1;
-            __syncthreads();
-          }
-        }
-      if (failed)
-        { __syncthreads();
-          if (rounds >= 4096 || sp + 2 > 28)
-            { if (threadIdx.x == 0) atomicAdd(p.g_fail,1u);
-              return;
-            }
-          stR[sp] = 2*rounds; stD[sp] = rd + rounds; sp++;
-          stR[sp] = 2*rounds; stD[sp] = rd; sp++;
-          continue;
-        }
-      /* emit this class's distinct keys (pool entries of count 0 are holes) */
-      u32 mine = 0;
-      u32 mine_e = 0;                            /* of them, those that are emitted as entries */
-      for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
-        { const u32 c = ocnt[i];
-          mine += (c != 0) ? 1u : 0u;
-          mine_e += (c >= p.ent_min) ? 1u : 0u;
-        }
-      mine = (mine << 16) | mine_e;              /* both fit 16 bits: the pool holds <= 1024 keys */
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu,mine,o);
-      if (threadIdx.x == 0) s_ecnt = 0;
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_ecnt,mine);
-      __syncthreads();
-      const u32 nreal = s_ecnt >> 16, nemit = s_ecnt & 0xffffu;
-      __syncthreads();
-      if (threadIdx.x == 0)
-        { s_ebase = (p.ent != NULL && nemit) ? atomicAdd(p.ent_counter,(u64) nemit) : 0ull;
-          s_ecnt = 0;
-        }
-      __syncthreads();
-      for (u32 i = threadIdx.x; i < nd; i += BC_TPB)
-        { const u32 c = ocnt[i];
-          if (c == 0) continue;
-          const u32 cs = c >= 0x7fffu ? 0x7fffu : c;
-          if (cs < SC_SMALLHIST) atomicAdd(&s_hist[cs],1u);
-          else atomicAdd(p.g_hist + cs,1ull);
-          if (c >= 0x7fffu) atomicAdd(p.g_maxinst,(u64) c);
-          if (p.ent != NULL && cs >= p.ent_min)
-            { const u64 at = s_ebase + atomicAdd(&s_ecnt,1u);
-              if (at < p.ent_cap)
-                { Key<2> e = pool[i];
-                  e.w[1] |= (u64) cs;
-                  ((Key<2> *) p.ent)[at] = e;
-                }
-            }
-        }
-      __syncthreads();
-      for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += BC_TPB)
-        { u32 c = s_hist[i];
-          if (c) atomicAdd(p.g_hist + i,(u64) c);
-        }
-      if (threadIdx.x == 0) atomicAdd(p.g_ndistinct,(u64) nreal);
-      __syncthreads();
-    }
-}
-
 /*  multi-GPU exchange: the 32-byte left-aligned base string (<= 64 + k - 1 <= 128 bases) of every super-mer record, in record
  *  order, gathered out of the sender's own packed reads -- it travels beside the 8-byte records in the all-to-all.       */
 __global__ void __launch_bounds__(256) k_materialise(const u64 *recs, long long n, int pbits, u64 pos_offset, int k, const u32 *seq, uint4 *payload)
 { const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u64 sm = recs[i];
-  const u32 l = (u32) ((sm >> pbits) & 63u) + 1u;
+  const u32 l = sm_len(sm,pbits);
   const u64 ps = (sm & ((1ull << pbits) - 1ull)) - pos_offset;
   const u32 *g = seq + (ps >> 4);
   const int sh = 2*(int) (ps & 15ull);
@@ -1662,7 +1451,7 @@ __global__ void __launch_bounds__(256) k_bucket_kmers(const u64 *recs, const u64
 { __shared__ u64 s_w[8];
   const u64 a = off[blockIdx.x], b = off[blockIdx.x + 1];
   u64 s = 0;
-  for (u64 i = a + threadIdx.x; i < b; i += 256) s += ((recs[i] >> pbits) & 63ull) + 1ull;
+  for (u64 i = a + threadIdx.x; i < b; i += 256) s += sm_len(recs[i],pbits);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
   if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
@@ -1678,7 +1467,7 @@ __global__ void __launch_bounds__(256) k_bucket_kmers(const u64 *recs, const u64
 __global__ void __launch_bounds__(256) k_sum_lengths(const u64 *recs, long long n, int pbits, u64 *total)
 { u64 s = 0;
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
-    s += ((recs[i] >> pbits) & 63ull) + 1ull;
+    s += sm_len(recs[i],pbits);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu,s,o);
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(total,s);

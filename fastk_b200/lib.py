@@ -318,7 +318,7 @@ class FastKGPU:
         v = (C.c_int64 * 8)()
         self._chk(self.lib.fkgpu_last_stats(self.h, v), "fkgpu_last_stats")
         return dict(path=int(v[0]), supermers=int(v[1]), entries=int(v[2]), groups=int(v[3]), rounds=int(v[4]), split_classes=int(v[5]),
-                    spilled_kmers=int(v[6]))
+                    spilled_kmers=int(v[6]), supermers_expanded=int(v[7]))
 
     def last_path(self):
         return int(self.lib.fkgpu_last_path(self.h))

@@ -158,7 +158,7 @@ int  fkgpu_scatter_prefix(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t 
 int  fkgpu_count_records(fkgpu_ctx *ctx, void *d_records, int64_t nrecords, int fetch_table, fkgpu_result *res);
 
 /*  Multi-GPU stages of the super-mer path (k in 18..64; fastk_b200/multigpu.py drives them, one process per GPU).
- *  A super-mer record is 8 bytes, [minimizer bucket : <= 22][# k-mers - 1 : 6][GLOBAL position of its first base : 36],
+ *  A super-mer record is 8 bytes, [minimizer bucket : <= 24][# k-mers - 1 : 6][strand of the minimizer : 1][GLOBAL position of its first base : >= 32],
  *  where the global position space is the concatenation of every rank's packed read stream (rank r starts at
  *  pos_base[r]).  Ranks own contiguous bucket ranges; ONE all-to-all moves the 8-byte records (not the k-mers), and the
  *  counting kernel of the owner gathers the bases straight from the source rank's HBM over NVLink (peer pointers obtained
@@ -203,7 +203,9 @@ int  fkgpu_entries_sort(fkgpu_ctx *ctx, void *d_entries, int64_t n, int fetch_ta
 /*  Instrumentation for bench.py: # of kernel launches issued by this context so far, and the
  *  accumulated CUDA-event time / algorithmic bytes of the dominant kernel family (final sort+count). */
 int64_t fkgpu_launch_count(fkgpu_ctx *ctx);
-int     fkgpu_last_stats(fkgpu_ctx *ctx, int64_t *v /*[4]: path, super-mer records, distinct entries sorted, work groups*/);
+int     fkgpu_last_stats(fkgpu_ctx *ctx, int64_t *v /*[8]: path, super-mer records, distinct entries sorted, work groups, rounds,
+                                                         hash classes split, k-mers of oversize buckets sent to the record pipeline,
+                                                         super-mers expanded (the others were copies counted by weight)*/);
 int     fkgpu_last_path(fkgpu_ctx *ctx);     /* which pipeline served the last count: 0 = 16-byte records, 1 = super-mers */
 int     fkgpu_stage_times(fkgpu_ctx *ctx, float *ms /*[FKGPU_NSTAGES]*/, double *bytes /*[FKGPU_NSTAGES]*/);
 #define FKGPU_NSTAGES 14
