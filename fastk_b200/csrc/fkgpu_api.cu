@@ -132,6 +132,7 @@ struct fkgpu_ctx
     /* profile lookup table built by finish when cfg.do_profile */
     DevBuf eprof, qoff, pkeys, pcnts, pidx, praw, pout, psrc, pdst, plen;
     long long ptab_n = 0; int ptab_B = 0; long long last_npos = 0;
+    bool rel_table = false;     /* -p:<table>: the lookup table was loaded from an existing k-mer table, nothing is counted */
     int weighted = 0;      /* the records being sorted are distinct (key|count) entries of the super-mer path */
     int res_nw = 2;        /* words per key of the staged / profile-table keys of the last result            */
     int last_path = 0;     /* 0 = record path, 1 = super-mer path                                            */
@@ -1581,7 +1582,7 @@ static int stream_begin(fkgpu_ctx *c)
       fkgpu_packed_words(cap,&sw,&vw);
       ok = !(c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4));
     }
-  const bool scan = ok && super_path_ok(c) && c->cfg.bc_prefix == 0 && (c->cfg.do_profile || one_round_fits(c,nub));
+  const bool scan = ok && !c->rel_table && super_path_ok(c) && c->cfg.bc_prefix == 0 && (c->cfg.do_profile || one_round_fits(c,nub));
   if (scan)
     { c->sgeom = super_geom(c->cfg.kmer,cap);
       ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,entry_words(c->cfg.kmer)) == 0) && !c->segs.ensure(sizeof(SuperCounters));
@@ -1719,6 +1720,17 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
         }
     }
   stage_end(c,FKGPU_ST_PACK);
+  if (c->rel_table)
+    { /* -p:<table>: only profiles are produced, against the loaded table (FastK.c:328-337: no histogram, -t ignored) */
+      cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+      CU(cudaStreamSynchronize(c->st));
+      collect_times(c,res);
+      memset(c->h_hist,0,sizeof(c->h_hist));
+      res->hist = c->h_hist;
+      c->last_path = 0;
+      single_run(c,res);
+      return FKGPU_OK;
+    }
   return count_packed_any(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false,c->stream_on && c->stream_scan);
 }
 
@@ -2065,6 +2077,35 @@ static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const 
       }
   pp.offs.push_back(pp.run);
   return profiles_run<NW>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,c->last_npos,pp,nreads,off,prof);
+}
+
+template<int NW>
+static int load_profile_table_t(fkgpu_ctx *c, const uint8_t *records, int64_t n)
+{ const int tw = c->kbytes + 2;
+  const u64 U = (u64) n;
+  int B = ilog2_ceil(U + 1) - 2; if (B < 8) B = 8; if (B > 26) B = 26;
+  if (c->table.ensure((size_t) U * tw + 64) || c->pkeys.ensure((size_t) (U + 1) * sizeof(Key<NW>)) || c->pcnts.ensure((size_t) (U + 1) * 2)
+      || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %lld k-mers)",(long long) n);
+  if (U > 0)
+    { CU(cudaMemcpyAsync(c->table.p,records,(size_t) U * tw,cudaMemcpyHostToDevice,c->st));
+      k_records_to_keys<NW><<<(unsigned) ((U + 255) / 256),256,0,c->st>>>((const uint8_t *) c->table.p,U,c->kbytes,(Key<NW> *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
+    }
+  k_build_index<NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const Key<NW> *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
+  CU(cudaStreamSynchronize(c->st));
+  c->ptab_n = (long long) U; c->ptab_B = B; c->res_nw = NW; c->rel_table = true;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_load_profile_table(fkgpu_ctx *c, const uint8_t *records, int64_t n)
+{ if (c == NULL || n < 0 || (n > 0 && records == NULL)) return set_err(FKGPU_E_ARG,"fkgpu_load_profile_table: bad argument");
+  if (!c->cfg.do_profile) return set_err(FKGPU_E_STATE,"fkgpu_load_profile_table: the context was created without do_profile");
+  CU(cudaSetDevice(c->cfg.device));
+  const int tw = c->kbytes + 2;
+  for (int64_t i = 1; i < n; i++)                      /* the lookup is a binary search: the records must be strictly increasing */
+    if (memcmp(records + (i-1)*tw,records + i*tw,(size_t) c->kbytes) >= 0)
+      return set_err(FKGPU_E_ARG,"fkgpu_load_profile_table: records %lld and %lld are not in increasing key order",(long long) (i-1),(long long) i);
+  return (c->NW == 1) ? load_profile_table_t<1>(c,records,n) : load_profile_table_t<2>(c,records,n);
 }
 
 extern "C" int fkgpu_profiles_packed(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,

@@ -1501,6 +1501,20 @@ __global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<(NW =
     }
 }
 
+/*  table records [kbytes key][u16 LE count] (a .ktab as the host read it back) -> the lookup arrays of k_profile  */
+template<int NW>
+__global__ void __launch_bounds__(256) k_records_to_keys(const uint8_t *tab, u64 n, int kbytes, Key<NW> *keys, uint16_t *cnts)
+{ const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t *e = tab + i * (u64) (kbytes + 2);
+  Key<NW> r;
+#pragma unroll
+  for (int m = 0; m < NW; m++) r.w[m] = 0;
+  for (int b = 0; b < kbytes; b++) r.w[b >> 3] |= (u64) e[b] << (56 - 8*(b & 7));
+  keys[i] = r;
+  cnts[i] = (uint16_t) ((u32) e[kbytes] | ((u32) e[kbytes+1] << 8));
+}
+
 template<int NW>
 __global__ void k_build_index(const Key<NW> *keys, u64 n, int B, u64 *idx)
 { u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;

@@ -32,6 +32,7 @@
 static char *Prog_Name = "FastK";
 
 static int   VERBOSE, COMPRESS, KMER = 40, DO_TABLE, DO_PROFILE, BC_PREFIX, NTHREADS = 4, ITHREADS;
+static char   *PRO_NAME;               /* -p:<table>: profiles relative to this k-mer table */
 static int64_t SORT_MEMORY;            /* -M in bytes; 0 = not given: use what the device has */
 static char *OUT_NAME;
 static char  OUT_DIR[4096], OUT_ROOT[4096];
@@ -324,8 +325,7 @@ int main(int argc, char *argv[])
             BC_PREFIX = atoi(a+3);
             break;
           case 'p':
-            if (a[2] == ':')
-              { fprintf(stderr,"%s: -p:<table> (relative profiles) is not supported by the GPU path yet\n",Prog_Name); exit(1); }
+            if (a[2] == ':') { PRO_NAME = a+3; DO_PROFILE = 1; break; }      /* relative profiles (FastK.c:269-281) */
             /* fall through */
           default:
             if (a[1] == 't' && isdigit((unsigned char) a[2])) { DO_TABLE = atoi(a+2); break; }
@@ -394,6 +394,20 @@ int main(int argc, char *argv[])
   cfg.nthreads = ITHREADS; cfg.reserve_bases = work; cfg.mem_limit = SORT_MEMORY;
   if (fkgpu_create(&cfg,&CTX) != 0)
     { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
+  if (PRO_NAME != NULL)
+    { /* what Split_Table does for the reference (split.c:1943-2131): bring the table to where the profiles are made */
+      int tk, tcut; uint8_t *trec; int64_t tn;
+      if (fk_read_ktab(PRO_NAME,&tk,&tcut,&trec,&tn))
+        { fprintf(stderr,"%s: Cannot open FastK table %s\n",Prog_Name,PRO_NAME); exit(1); }
+      if (tk != KMER)
+        { fprintf(stderr,"%s: -p table k-mer size (%d) != k-mer specified (%d)\n",Prog_Name,tk,KMER); exit(1); }
+      if (DO_TABLE && VERBOSE) fprintf(stderr,"%s: Warning: -p:%s overides -t option\n",Prog_Name,PRO_NAME);
+      DO_TABLE = 0;
+      if (fkgpu_load_profile_table(CTX,trec,tn) != 0)
+        { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
+      free(trec);
+      if (VERBOSE) fprintf(stderr,"  Profiles relative to %s: %lld %d-mers with counts >= %d\n",PRO_NAME,(long long) tn,tk,tcut);
+    }
   have_out = 1;
   fk_remove_outputs(OUT_DIR,OUT_ROOT);
 
@@ -449,7 +463,7 @@ int main(int argc, char *argv[])
       if (res.nruns > 1) fprintf(stderr,"  Counted in %d rounds (sorted runs merged while the table parts are written)\n",res.nruns);
     }
 
-  if (fk_write_hist(OUT_DIR,OUT_ROOT,KMER,res.hist,res.max_inst))
+  if (PRO_NAME == NULL && fk_write_hist(OUT_DIR,OUT_ROOT,KMER,res.hist,res.max_inst))
     { fprintf(stderr,"%s: Cannot write to %s/%s.hist.  Enough disk space?\n",Prog_Name,OUT_DIR,OUT_ROOT); Clean_Exit(1); }
   if (DO_TABLE > 0)
     { if (VERBOSE) fprintf(stderr,"\nPhase 3 (-t option): Writing K-mer Table Parts\n");

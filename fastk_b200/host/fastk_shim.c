@@ -75,6 +75,18 @@ void Split_Kmers(Input_Partition *io, char *root)
   cfg.reserve_bases = EST_POSITIONS;
   cfg.mem_limit = getenv("FASTK_GPU_MEM_GB") ? (int64_t) (atof(getenv("FASTK_GPU_MEM_GB")) * 1073741824.) : 0;
   if (fkgpu_create(&cfg,&CTX) != 0) fail("fkgpu_create");
+  if (PRO_TABLE != NULL)
+    { /* -p:<table>: what Split_Table (split.c:1943-2131) does for the reference's merge join -- bring the table to where the
+         profiles are made -- done here, before the reads stream in, through the reference's own table reader               */
+      Kmer_Stream *S = PRO_TABLE;
+      uint8 *rec = (uint8 *) malloc((size_t) (S->nels > 0 ? S->nels : 1) * S->tbyte);
+      int64  i = 0;
+      if (rec == NULL) { fprintf(stderr,"%s: Out of memory (loading the -p table)\n",Prog_Name); Clean_Exit(1); }
+      for (First_Kmer_Entry(S); S->csuf != NULL && i < S->nels; Next_Kmer_Entry(S))
+        Current_Entry(S,rec + (i++)*S->tbyte);
+      if (fkgpu_load_profile_table(CTX,rec,i) != 0) fail("fkgpu_load_profile_table");
+      free(rec);
+    }
   NUM_RID = (int64 *) calloc(ITHREADS > 0 ? ITHREADS : 1,sizeof(int64));
   Scan_All_Input(io);
 }
@@ -85,9 +97,9 @@ void Distribute_Block(DATA_BLOCK *block, int tid)
 }
 
 void Split_Table(char *root)
-{ (void) root;
-  fprintf(stderr,"\n%s: -p:<table> (relative profiles) is not supported by the GPU path\n",Prog_Name);
-  Clean_Exit(1);
+{ (void) root;            /* the table went to the device in Split_Kmers: nothing is split into minimizer parts here */
+  if (VERBOSE)
+    fprintf(stderr,"\n  Profiles will be relative to %s (%lld %d-mers on the device)\n",PRO_NAME,(long long) PRO_TABLE->nels,KMER);
 }
 
 void Sorting(char *path, char *root)

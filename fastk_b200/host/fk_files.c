@@ -184,6 +184,77 @@ int fk_write_ktab_runs(const char *dir, const char *root, int kmer, int cutoff, 
 int fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int nparts, const uint8_t *entries, int64_t n)
 { return fk_write_ktab_runs(dir,root,kmer,cutoff,nparts,&entries,&n,1); }
 
+/* reads back a k-mer table: the stub <dir>/<root>.ktab (kmer, nparts, cutoff, prefix bytes, cumulative prefix index) and its
+   hidden parts <dir>/.<root>.ktab.<p> (kmer, n, then n x [suffix][u16 count]); the prefix of entry e is the first x with
+   e < idx[x] (README.md:936-1010, the reader of libfastk.c:843-965 restated for a sequential pass)                       */
+int fk_read_ktab(const char *name, int *kmer, int *cutoff, uint8_t **records, int64_t *nrec)
+{ char *path = (char *) malloc(strlen(name) + 64), *dir, *root, *slash;
+  int64_t *idx = NULL, ilen, e = 0, x = 0, n = 0;
+  uint8_t *rec = NULL, *buf = NULL;
+  int k, nparts, minval, ib, kb, tw, pw, p, f, bad = 1;
+  size_t ln;
+  if (path == NULL) return 1;
+  strcpy(path,name);
+  ln = strlen(path);
+  if (ln > 5 && strcmp(path + ln - 5,".ktab") == 0) path[ln-5] = '\0';
+  slash = strrchr(path,'/');
+  if (slash == NULL) { dir = strdup("."); root = strdup(path); }
+  else { *slash = '\0'; dir = strdup(path[0] ? path : "/"); root = strdup(slash+1); }
+  { char *stub = (char *) malloc(strlen(dir) + strlen(root) + 64);
+    sprintf(stub,"%s/%s.ktab",dir,root);
+    f = open(stub,O_RDONLY);
+    free(stub);
+  }
+  if (f < 0) goto done;
+  if (read(f,&k,sizeof(int)) != (ssize_t) sizeof(int) || read(f,&nparts,sizeof(int)) != (ssize_t) sizeof(int)
+      || read(f,&minval,sizeof(int)) != (ssize_t) sizeof(int) || read(f,&ib,sizeof(int)) != (ssize_t) sizeof(int)
+      || ib < 1 || ib > 3 || k < 1 || nparts < 1)
+    { close(f); goto done; }
+  ilen = 1ll << (8*ib);
+  idx = (int64_t *) malloc(sizeof(int64_t) * (size_t) ilen);
+  if (idx == NULL || read(f,idx,sizeof(int64_t) * (size_t) ilen) != (ssize_t) (sizeof(int64_t) * (size_t) ilen)) { close(f); goto done; }
+  close(f);
+  n = idx[ilen-1];
+  kb = (2*k+7) >> 3; tw = kb+2; pw = tw - ib;
+  rec = (uint8_t *) malloc((size_t) (n > 0 ? n : 1) * tw);
+  buf = (uint8_t *) malloc((size_t) pw << 16);
+  if (rec == NULL || buf == NULL) goto done;
+  for (p = 1; p <= nparts; p++)
+    { char *part = (char *) malloc(strlen(dir) + strlen(root) + 64);
+      int pk; int64_t pn, got;
+      sprintf(part,"%s/.%s.ktab.%d",dir,root,p);
+      f = open(part,O_RDONLY);
+      free(part);
+      if (f < 0) goto done;
+      if (read(f,&pk,sizeof(int)) != (ssize_t) sizeof(int) || read(f,&pn,sizeof(int64_t)) != (ssize_t) sizeof(int64_t) || pk != k || e + pn > n)
+        { close(f); goto done; }
+      for (got = 0; got < pn; )
+        { int64_t want = pn - got, i;
+          ssize_t r;
+          if (want > (1 << 16)) want = 1 << 16;
+          r = read(f,buf,(size_t) want * pw);
+          if (r != (ssize_t) (want * pw)) { close(f); goto done; }
+          for (i = 0; i < want; i++, e++)
+            { uint8_t *o = rec + e*tw;
+              int b;
+              while (x < ilen && e >= idx[x]) x++;
+              if (x >= ilen) { close(f); goto done; }
+              for (b = 0; b < ib; b++) o[b] = (uint8_t) (x >> (8*(ib-1-b)));
+              memcpy(o+ib,buf + i*pw,(size_t) pw);
+            }
+          got += want;
+        }
+      close(f);
+    }
+  if (e != n) goto done;
+  *kmer = k; *cutoff = minval; *records = rec; *nrec = n;
+  rec = NULL;
+  bad = 0;
+done:
+  free(path); free(dir); free(root); free(idx); free(rec); free(buf);
+  return bad;
+}
+
 int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out)
 { uint8_t *o = out;
   int64_t  i;

@@ -27,6 +27,10 @@ int  fk_write_ktab(const char *dir, const char *root, int kmer, int cutoff, int 
 int  fk_write_ktab_runs(const char *dir, const char *root, int kmer, int cutoff, int nparts,
                         const uint8_t *const *runs, const int64_t *ns, int nruns);
 
+/* a k-mer table read back into n records [kmer_bytes key][u16 LE count] in key order (malloc'ed: the caller frees);
+   name = <dir>/<root> with or without the .ktab extension (as Open_Kmer_Stream takes it, libfastk.c:843).  0 = ok. */
+int  fk_read_ktab(const char *name, int *kmer, int *cutoff, uint8_t **records, int64_t *n);
+
 /* greedy profile code of one read's count vector; returns # of bytes written (out needs 2*plen+2) */
 int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out);
 

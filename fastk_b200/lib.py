@@ -65,6 +65,8 @@ def load_library(path=None):
     lib.fkgpu_profiles_packed.argtypes = [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32), i64, C.POINTER(i64),
                                           C.POINTER(C.POINTER(i64)), C.POINTER(C.POINTER(C.c_uint16))]
     lib.fkgpu_profiles_packed.restype = C.c_int
+    lib.fkgpu_load_profile_table.argtypes = [vp, C.POINTER(C.c_uint8), i64]
+    lib.fkgpu_load_profile_table.restype = C.c_int
     lib.fkgpu_read_counts.argtypes = [vp, C.POINTER(i64)]
     lib.fkgpu_read_counts.restype = C.c_int
     lib.fkgpu_packed_words.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
@@ -121,7 +123,7 @@ def load_library(path=None):
 
 
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
-           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
+           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_load_profile_table", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
            "fkgpu_super_supported", "fkgpu_entry_bytes", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
@@ -338,6 +340,13 @@ class FastKGPU:
         tot = int(offs[-1])
         p = np.ctypeslib.as_array(prof, shape=(max(tot, 1),))[:tot]
         return (offs.copy(), p.copy()) if copy else (offs, p)
+
+    def load_profile_table(self, table):
+        """-p:<table>: table = (n, kmer_bytes + 2) uint8 records in key order; finish() then counts nothing and profiles() are
+        relative to this table"""
+        t = np.ascontiguousarray(table, dtype=np.uint8)
+        self._chk(self.lib.fkgpu_load_profile_table(self.h, t.ctypes.data_as(C.POINTER(C.c_uint8)), t.shape[0]),
+                  "fkgpu_load_profile_table")
 
     def profiles(self, copy=True):
         """-> (off int64 [nreads+1], prof uint16): prof[off[r]:off[r+1]] = counts of read r (tid-major read order).

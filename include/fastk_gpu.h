@@ -113,6 +113,13 @@ int  fkgpu_finish(fkgpu_ctx *ctx, int fetch_table, fkgpu_result *res);
  *  host memory owned by the context.                                                             */
 int  fkgpu_profiles(fkgpu_ctx *ctx, int64_t *nreads, const int64_t **off, const uint16_t **prof);
 
+/*  Relative profiles, -p:<table> (FastK.c:269-281; replaces Split_Table split.c:1943-2131 and the merge join of
+ *  count.c:675-792).  records = n table records [kmer_bytes key][u16 LE count] in increasing key order, as read back from an
+ *  existing .ktab (any cutoff).  Call it on a do_profile context BEFORE fkgpu_finish: finish then only packs the reads --
+ *  nothing is counted, no histogram, no table (FastK.c:328-337) -- and fkgpu_profiles reports at every position the count
+ *  the loaded table holds for the canonical k-mer there, 0 if it is absent.                                          */
+int  fkgpu_load_profile_table(fkgpu_ctx *ctx, const uint8_t *records, int64_t n);
+
 /*  # of whole reads each tid delivered (continuation pieces of a split read are not counted twice); part t+1 of
  *  the .prof output holds the reads of tid t (merge.c:926-928).  per_tid has cfg.nthreads entries.          */
 int  fkgpu_read_counts(fkgpu_ctx *ctx, int64_t *per_tid);

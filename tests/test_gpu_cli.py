@@ -103,3 +103,25 @@ def test_cli_multi_round_with_small_memory(oracle_lib, exe_name, tmp_path):
     kt = util.read_ktab_files(d, "out")
     assert kt["stub"] == g["ktab_stub"] and kt["payload"] == g["ktab_payload"]
     util.check_parts_on_first_byte_boundaries(kt)
+
+
+@pytest.mark.parametrize("exe_name", ["ours", "refhost"])
+def test_cli_relative_profiles(oracle_lib, exe_name, tmp_path):
+    """FastK -p:<table>: build the table with the program under test (-t2), then profile other reads against it: only
+    .prof is written (no .hist, no .ktab: FastK.c:328-337) and every decoded profile equals the reference's own."""
+    g = util.golden_relative()
+    d = str(tmp_path)
+    exe = OURS if exe_name == "ours" else REFHOST
+    if not os.path.exists(exe):
+        pytest.skip(exe + " not built")
+    r = subprocess.run([exe, "-k%d" % g["k"], "-t%d" % g["table_cutoff"], "-T4", "-P" + d, "-N" + os.path.join(d, "tab"), g["table_src"]],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "-k%d" % g["k"], "-p:" + os.path.join(d, "tab"), "-T%d" % g["T"], "-P" + d, "-N" + os.path.join(d, "out"), g["src"]],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not os.path.exists(os.path.join(d, "out.hist")) and not os.path.exists(os.path.join(d, "out.ktab"))
+    prof, off, nparts = util.decode_prof_files(d, "out", oracle_lib)
+    assert np.array_equal(off, g["prof_off"]) and np.array_equal(prof, g["prof"])
+    r = subprocess.run([exe, "-k21", "-p:" + os.path.join(d, "tab"), "-P" + d, "-N" + os.path.join(d, "bad"), g["src"]], capture_output=True, text=True)
+    assert r.returncode == 1 and "k-mer size" in r.stderr

@@ -281,3 +281,25 @@ def test_multi_round_count_leaves_disjoint_sorted_runs(oracle_lib, k, cutoff, li
         assert np.array_equal(res.merged_runs(), want["table"])
     finally:
         g.close()
+
+
+def test_relative_profiles_against_a_loaded_table(oracle_lib):
+    """-p:<table>: the table (oracle count of the golden c1_k40 reads at cutoff 2) is loaded, the query reads are only
+    packed, and every profile must equal what the REFERENCE produced for the same table and reads (tests/golden/relative)."""
+    import util
+    g = util.golden_relative()
+    tab = oracle_lib.count(util.read_seq_file(g["table_src"]), g["k"], cutoff=g["table_cutoff"])["table"]
+    reads = util.read_seq_file(g["src"])
+    eng = FastKGPU(k=g["k"], table_cutoff=0, profile=True, nthreads=2)
+    try:
+        eng.load_profile_table(tab)
+        half = len(reads) // 2
+        for t, part in enumerate((reads[:half], reads[half:])):
+            for bases, boff in synth.blocks(part, max_bytes=20_000):
+                eng.ingest(bases, boff.astype(np.int32), tid=t)
+        res = eng.finish(fetch_table=False)
+        assert res.ntable == 0 and res.nkmers == 0
+        off, prof = eng.profiles()
+        assert np.array_equal(off, g["prof_off"]) and np.array_equal(prof, g["prof"])
+    finally:
+        eng.close()

@@ -26,6 +26,7 @@ def fkfiles(tmp_path_factory):
     L.fk_encode_profile.argtypes = [C.POINTER(C.c_uint16), C.c_int64, C.POINTER(C.c_uint8)]
     L.fk_encode_profile.restype = C.c_int64
     L.fk_table_split.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.fk_read_ktab.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int64)]
     L.fk_write_ktab_runs.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
                                      C.POINTER(C.c_int64), C.c_int]
     return L
@@ -162,3 +163,21 @@ def test_remove_outputs_only_touches_its_own_files(fkfiles, tmp_path):
     fkfiles.fk_remove_outputs.argtypes = [C.c_char_p, C.c_char_p]
     fkfiles.fk_remove_outputs(d.encode(), b"r")
     assert sorted(os.listdir(d)) == sorted(other)
+
+
+@pytest.mark.parametrize("name", util.golden_cases())
+def test_table_reader_round_trip(oracle_lib, fkfiles, name, tmp_path):
+    """fk_read_ktab (the -p:<table> loader of our host program): stub + hidden parts -> full [key][count] records."""
+    g = util.golden(name)
+    r = oracle_lib.count(util.read_seq_file(g["src"]), g["k"], cutoff=g["t"])
+    tab = np.ascontiguousarray(r["table"], dtype=np.uint8)
+    d = str(tmp_path).encode()
+    assert fkfiles.fk_write_ktab(d, b"w", g["k"], g["t"], g["T"], tab.ctypes.data_as(C.POINTER(C.c_uint8)), len(tab)) == 0
+    for nm in (os.path.join(str(tmp_path), "w"), os.path.join(str(tmp_path), "w.ktab")):
+        k, cut, n = C.c_int(), C.c_int(), C.c_int64()
+        rec = C.POINTER(C.c_uint8)()
+        assert fkfiles.fk_read_ktab(nm.encode(), C.byref(k), C.byref(cut), C.byref(rec), C.byref(n)) == 0
+        assert k.value == g["k"] and cut.value == g["t"] and n.value == len(tab)
+        back = np.ctypeslib.as_array(rec, shape=(n.value * tab.shape[1],)).reshape(n.value, tab.shape[1])
+        assert np.array_equal(back, tab)
+    assert fkfiles.fk_read_ktab(os.path.join(str(tmp_path), "missing").encode(), C.byref(k), C.byref(cut), C.byref(rec), C.byref(n)) != 0

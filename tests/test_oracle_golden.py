@@ -96,3 +96,14 @@ def test_oracle_matches_reference_live(oracle_lib, ref_bin, tmp_path, name, c):
     if name == "saturate":
         h = util.read_hist_file(os.path.join(od, "x.hist"))
         assert h["hist"][32767] == 17 and h["max_inst"] == 600446
+
+
+def test_oracle_relative_profiles_match_reference(oracle_lib):
+    """-p:<table> (FastK.c:269-281): the oracle's restatement -- look every canonical k-mer up in the table, 0 if absent --
+    against the profiles the reference itself produced (tests/golden/relative, decoded by its Profex)."""
+    g = util.golden_relative()
+    want = util.oracle_relative_profiles(oracle_lib, util.read_seq_file(g["table_src"]), g["k"], g["table_cutoff"],
+                                         util.read_seq_file(g["src"]))
+    assert len(want) == g["nreads"] == len(g["prof_off"]) - 1
+    for r, p in enumerate(want):
+        assert np.array_equal(p, g["prof"][g["prof_off"][r]:g["prof_off"][r + 1]]), f"relative profile of read {r} differs"

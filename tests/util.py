@@ -117,3 +117,35 @@ def decode_prof_files(d, root, oracle):
             prev = int(e)
         total += n
     return (np.concatenate(prof) if prof else np.zeros(0, np.uint16)), np.array(off, dtype=np.int64), nparts
+
+
+def golden_relative(name="rel_k40"):
+    """relative-profile fixture (-p:<table>): the reference's own profiles of <name>.fa against the table it built for
+    table_src at table_cutoff (tests/golden/make_golden_relative.py)"""
+    d = os.path.join(GOLD, "relative")
+    meta = json.load(open(os.path.join(d, name + ".json")))
+    meta["src"] = os.path.join(d, name + ".fa")
+    meta["table_src"] = os.path.join(GOLD, meta["table_src"])
+    z = np.load(os.path.join(d, name + ".prof.npz"))
+    meta["prof"], meta["prof_off"] = z["prof"], z["off"]
+    return meta
+
+
+def oracle_relative_profiles(oracle, table_reads, k, cutoff, reads):
+    """what -p:<table> must report: per position the (saturated) count the table holds, 0 for k-mers below its cutoff"""
+    import ctypes as C
+    from fastk_b200.synth import to_block
+    bases, boff = to_block(table_reads)
+    boff = np.ascontiguousarray(boff, dtype=np.int64)
+    t = oracle.lib.fko_count(bases, boff.ctypes.data_as(C.POINTER(C.c_int64)), len(table_reads), k, 0)
+    try:
+        out = []
+        for r in reads:
+            buf = np.zeros(max(len(r), 1), dtype=np.uint16)
+            pl = oracle.lib.fko_profile(t, r, len(r), 0, buf.ctypes.data_as(C.POINTER(C.c_uint16)))
+            p = buf[:pl].copy()
+            p[p < cutoff] = 0
+            out.append(p)
+        return out
+    finally:
+        oracle.lib.fko_free_table(t)
