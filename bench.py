@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--e2e-order", default="rr", choices=["rr", "contig"], help="e2e arm: how DATA_BLOCKs are dealt to the ingest threads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference run: no cpu_baseline and NO parity check")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--mg-impl", default="c", choices=["c", "py"], help="N>1: the exchange inside the C library (NCCL, fkgpu_count_packed_multi) "
+                    "or driven from Python over torch.distributed (fastk_b200/multigpu.py)")
     ap.add_argument("--mem-limit-gb", type=float, default=0.0, help="fkgpu_config.mem_limit (the host's -M): below the one-round "
                     "working set the count takes several rounds")
     ap.add_argument("--device-gen", action="store_true", help="generate the reads on the device chunk by chunk (batches too large "
@@ -295,7 +297,15 @@ def main():
     eng = FastKGPU(k=k, table_cutoff=a.cutoff, profile=a.profile, device=local, nthreads=nthr,
                    reserve_bases=0 if a.device_gen else npos, mem_limit=int(a.mem_limit_gb * (1 << 30)))
     runner = None
-    if world > 1:
+    cmulti = world > 1 and a.mg_impl == "c"
+    if cmulti:
+        # one NCCL communicator inside the library: rank 0 makes the id, torch.distributed only hands it round (plumbing)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(eng.comm_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+    if world > 1 and not cmulti:
         # packed reads live in library-owned buffers that every peer maps over CUDA IPC (NVLink gathers in the count kernel)
         from fastk_b200 import multigpu
         runner = multigpu.MultiGPUCounter(eng, world, rank, dev)
@@ -315,7 +325,13 @@ def main():
     torch.cuda.empty_cache()
 
     want_table = a.cutoff > 0
-    if world > 1:
+    if cmulti:
+        def one_step():
+            r = eng.count_packed_multi(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
+            r.local_ntable, r.ntable = r.ntable, eng.comm_info()["ntable"]         # report the global table size
+            r.path, r.exchange = "super-mer", "payload (NCCL inside the library)"
+            return r
+    elif world > 1:
         def one_step():
             return runner.count_packed(seq_ptr, val_ptr, npos, fetch_table=want_table, copy_table=False)
     elif a.profile:
@@ -342,7 +358,7 @@ def main():
     for _ in range(a.steps):
         res = one_step()
         dev_ms += res.ms_total
-        for kname, v in (res.stage_ms if world > 1 else eng.stage_times()).items():
+        for kname, v in (res.stage_ms if runner is not None else eng.stage_times()).items():
             stage_ms[kname] = stage_ms.get(kname, 0.0) + v
     barrier()
     t1 = time.perf_counter()
@@ -354,11 +370,11 @@ def main():
     elapsed = float(el.item())
     value = nbases * world * a.steps / elapsed / 1e9
     problems = invariants(res.hist, res.max_inst, res.nkmers, res.ndistinct)
-    stats = eng.last_stats() if world == 1 else None
+    stats = eng.last_stats() if runner is None else None
 
     # ---- e2e arm (single GPU): host DATA_BLOCKs -> fkgpu_ingest x nthr threads -> finish -> table in pinned host memory
     e2e, r2 = None, None
-    if not a.no_e2e and world == 1:
+    if not a.no_e2e and (world == 1 or cmulti):
         rows_per_block = max(1, min(10000, (1_000_000 - 1) // (L + 1)))
         boff_full = (np.arange(rows_per_block + 1, dtype=np.int64) * (L + 1)).astype(np.int32)
         base_ptr = host_ascii.data_ptr()
@@ -378,6 +394,8 @@ def main():
         e2e_split = {"ingest_ms": 0.0, "finish_ms": 0.0, "profile_ms": 0.0}
 
         def e2e_step():
+            if world > 1:
+                dist.barrier(device_ids=[local])
             ta = time.perf_counter()
             eng.reset()
             th = [threading.Thread(target=worker, args=(t,)) for t in range(nthr)]
@@ -386,7 +404,7 @@ def main():
             for t in th:
                 t.join()
             tb = time.perf_counter()
-            r = eng.finish(fetch_table=want_table, copy_table=False)
+            r = eng.finish(fetch_table=want_table, copy_table=False)      # collective when a communicator is attached
             tc = time.perf_counter()
             if a.profile:
                 r.prof_off, r.prof = eng.profiles(copy=False)
@@ -406,10 +424,14 @@ def main():
             r2 = e2e_step()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if world > 1:
+            el2 = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(el2, op=dist.ReduceOp.MAX)
+            t1 = t0 + float(el2.item())
         d2h = int(r2.ntable * (r2.kmer_bytes + 2) + 32768 * 8)
         if a.profile:
             d2h += int(len(r2.prof) * 2 + len(r2.prof_off) * 8)
-        e2e = {"value": nbases * a.steps / (t1 - t0) / 1e9, "unit": "Gbases/s",
+        e2e = {"value": nbases * world * a.steps / (t1 - t0) / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(npos), "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * (t1 - t0) / a.steps,
                "ingest_ms_per_step": e2e_split["ingest_ms"] / a.steps,
@@ -452,10 +474,23 @@ def main():
                 np2 = (r1 - r0) * (L + 1)
                 pad = torch.zeros(64, dtype=torch.uint8, device=dev)
                 mine = torch.cat([mine.view(-1), pad])
-                s2, v2 = runner.alloc_reads(np2)
+                if cmulti:
+                    sw2, vw2 = eng.packed_words(np2)
+                    ds2 = torch.zeros(sw2, dtype=torch.int32, device=dev)
+                    dv2 = torch.zeros(vw2, dtype=torch.int32, device=dev)
+                    s2, v2 = ds2.data_ptr(), dv2.data_ptr()
+                else:
+                    s2, v2 = runner.alloc_reads(np2)
+                torch.cuda.synchronize()
                 eng.pack_ascii_dev(mine.data_ptr(), np2, s2, v2)
                 torch.cuda.synchronize()
-                got = runner.count_packed(s2, v2, np2, fetch_table=want_table, copy_table=False)
+                if cmulti:
+                    got = eng.count_packed_multi(s2, v2, np2, fetch_table=want_table, copy_table=False)
+                    info = eng.comm_info()
+                    got.table_sizes, got.local, got.path = info["table_sizes"], got, "super-mer"
+                    got.local_ntable = got.ntable
+                else:
+                    got = runner.count_packed(s2, v2, np2, fetch_table=want_table, copy_table=False)
                 del mine
                 ghist, gmax = got.hist, got.max_inst
                 table = None
@@ -463,14 +498,16 @@ def main():
                     tw = got.kmer_bytes + 2
                     mx = max(got.table_sizes)
                     loc = torch.zeros((mx, tw), dtype=torch.uint8, device=dev)
-                    if got.local.ntable:
-                        loc[:got.local.ntable] = torch.from_numpy(got.local.view_table()).to(dev)
+                    nloc = got.local_ntable if cmulti else got.local.ntable
+                    if nloc:
+                        loc[:nloc] = torch.from_numpy(got.local.view_table()[:nloc]).to(dev)
                     parts = [torch.zeros((mx, tw), dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
                     dist.gather(loc, parts, dst=0)
                     if rank == 0:
                         table = np.concatenate([parts[r][:got.table_sizes[r]].cpu().numpy() for r in range(world)])
                     del loc, parts
-                via = f"multigpu.count_packed over {world} ranks (exchange: {getattr(got, 'exchange', got.path)})"
+                via = (f"fkgpu_count_packed_multi over {world} ranks (NCCL inside the library)" if cmulti else
+                       f"multigpu.count_packed over {world} ranks (exchange: {getattr(got, 'exchange', got.path)})")
             if rank == 0:
                 bad = formats.compare_with_fastk_files(tmpdir, "cpu_out", k, a.cutoff, ghist, gmax, table)
                 parity = {"checked": True, "ok": not bad, "against": "oracle/_ref/FastK (.hist bins + max_inst, .ktab prefix index, "
@@ -496,8 +533,10 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     W = 8 if k <= 32 else 16
     N, U = res.nkmers, res.ndistinct
-    if world == 1:
+    if stats is not None:
         st = stats
+        if world > 1:
+            N, U = N // world, U // world            # rank 0's share: its own stage times against per-rank counts
     else:
         # rank 0's share of the job: its own stage times against its own record / entry counts
         st = dict(path=1 if res.path == "super-mer" else 0, supermers=getattr(res, "supermers", 0),
@@ -547,6 +586,19 @@ def main():
                              "frac": round(sum(alg.values()) / 1e9 / (dev_ms / a.steps / 1e3) / peak, 4) if dev_ms > 0 else None},
                 "stages": per_stage}
 
+    if world == 1:
+        parallelism = "single GPU"
+    elif cmulti:
+        parallelism = ("1 process/GPU; one NCCL communicator inside the C library: grouped ncclSend/ncclRecv all-to-all of the 8-byte "
+                       "super-mer records and of their 32-byte base strings, then of the distinct entries by key prefix")
+    elif st["path"] == 1:
+        parallelism = ("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, "
+                       + ("bases gathered from peer HBM over NVLink inside the count kernel"
+                          if getattr(res, "exchange", "") == "peer-gather" else
+                          "their 32-byte base strings in a second all-to-all overlapped with the record partition")
+                       + ", then all-to-all of the distinct entries by key prefix")
+    else:
+        parallelism = "1 process/GPU; prefix-range all-to-all of k-mer records over NCCL"
     if rank == 0:
         line = {"metric": "Gbases/sec counted (k=%d)" % k, "value": value, "unit": "Gbases/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
@@ -561,13 +613,7 @@ def main():
                            "timed_region": "packed reads resident in HBM -> sorted [key][count] table + histogram in pinned host memory",
                            "l2_policy": "inputs_larger_than_L2 (packed reads %.0f MB, records %.1f GB)"
                            % (npos * 0.375 / 1e6, N * W / 1e9),
-                           "parallelism": (("1 process/GPU; all-to-all of 8-byte super-mer records over NCCL, "
-                                            + ("bases gathered from peer HBM over NVLink inside the count kernel"
-                                               if getattr(res, "exchange", "") == "peer-gather" else
-                                               "their 32-byte base strings in a second all-to-all overlapped with the record partition")
-                                            + ", then all-to-all of the distinct entries by key prefix")
-                                           if st["path"] == 1 else "1 process/GPU; prefix-range all-to-all of k-mer records over NCCL")
-                           if world > 1 else "single GPU"},
+                           "parallelism": parallelism},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "parity_checked": bool(parity.get("checked") and parity.get("ok") and not problems), "parity": parity,
                 "invariant_violations": problems}

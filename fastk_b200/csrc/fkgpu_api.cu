@@ -63,6 +63,8 @@ struct PinBuf
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
   };
 
+#include "fkgpu_multi.cuh"
+
 #define FKGPU_D2H_CHUNKS 8          /* the table leaves the device in this many key ranges, each copied while the next is sorted */
 #define CHUNK_BYTES (8u << 20)         /* pinned staging chunk per ingest thread; also the granule of the streamed pack + scan */
 
@@ -133,6 +135,7 @@ struct fkgpu_ctx
     DevBuf eprof, qoff, pkeys, pcnts, pidx, praw, pout, psrc, pdst, plen;
     long long ptab_n = 0; int ptab_B = 0; long long last_npos = 0;
     bool rel_table = false;     /* -p:<table>: the lookup table was loaded from an existing k-mer table, nothing is counted */
+    MultiState *mg = nullptr;   /* multi-GPU: communicator + exchange buffers (fkgpu_comm_init) */
     int weighted = 0;      /* the records being sorted are distinct (key|count) entries of the super-mer path */
     int res_nw = 2;        /* words per key of the staged / profile-table keys of the last result            */
     int last_path = 0;     /* 0 = record path, 1 = super-mer path                                            */
@@ -195,6 +198,8 @@ extern "C" int fkgpu_create(const fkgpu_config *cfg, fkgpu_ctx **out)
   return FKGPU_OK;
 }
 
+static void mg_destroy(fkgpu_ctx *c);
+
 extern "C" void fkgpu_destroy(fkgpu_ctx *c)
 { if (c == NULL) return;
   cudaSetDevice(c->cfg.device);
@@ -211,6 +216,7 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
                      &c->rstart_d,&c->prof_d,&c->eprof,&c->qoff,&c->pkeys,&c->pcnts,&c->pidx,&c->praw,&c->pout,&c->psrc,&c->pdst,&c->plen };
   for (auto b : bufs) b->release();
   c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
+  if (c->mg) mg_destroy(c);
   for (auto r : c->h_runs) { r->release(); delete r; }
   c->bufC.release(); c->roff1.release(); c->l1k.release(); c->spillA.release(); c->spillB.release(); c->spill_list.release();
   for (auto &e : c->ev_sorted) cudaEventDestroy(e);
@@ -1582,7 +1588,7 @@ static int stream_begin(fkgpu_ctx *c)
       fkgpu_packed_words(cap,&sw,&vw);
       ok = !(c->seq.ensure((size_t) sw * 4) || c->val.ensure((size_t) vw * 4));
     }
-  const bool scan = ok && !c->rel_table && super_path_ok(c) && c->cfg.bc_prefix == 0 && (c->cfg.do_profile || one_round_fits(c,nub));
+  const bool scan = ok && !c->rel_table && c->mg == NULL && super_path_ok(c) && c->cfg.bc_prefix == 0 && (c->cfg.do_profile || one_round_fits(c,nub));
   if (scan)
     { c->sgeom = super_geom(c->cfg.kmer,cap);
       ok = (prepare_common(c,nub,std::max(c->sgeom.P1,1),true,entry_words(c->cfg.kmer)) == 0) && !c->segs.ensure(sizeof(SuperCounters));
@@ -1666,6 +1672,8 @@ extern "C" int fkgpu_pack_ascii_dev(fkgpu_ctx *c, const char *d_ascii, int64_t n
   return FKGPU_OK;
 }
 
+static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res);
+
 extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
 { if (c == NULL || res == NULL) return set_err(FKGPU_E_ARG,"fkgpu_finish: NULL argument");
   if (c->finished) return set_err(FKGPU_E_STATE,"fkgpu_finish: already finished (use fkgpu_reset)");
@@ -1731,6 +1739,8 @@ extern "C" int fkgpu_finish(fkgpu_ctx *c, int fetch_table, fkgpu_result *res)
       single_run(c,res);
       return FKGPU_OK;
     }
+  if (c->mg != NULL)
+    return count_packed_multi(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res);
   return count_packed_any(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,npos,fetch_table,res,false,c->stream_on && c->stream_scan);
 }
 
@@ -2019,6 +2029,302 @@ extern "C" int fkgpu_entries_sort(fkgpu_ctx *c, void *d_entries, int64_t n, int 
   collect_times(c,res);
   res->nkmers = 0; res->ndistinct = n;
   return FKGPU_OK;
+}
+
+
+/* ------------------------------------------------------------------------------------------------ */
+/*  multi-GPU count inside the library (fkgpu_multi.cuh has the design)                              */
+
+static void mg_destroy(fkgpu_ctx *c)
+{ MultiState *m = c->mg;
+  if (m == NULL) return;
+  fkmg::Api *na = fkmg::api();
+  if (m->comm && na) na->CommDestroy(m->comm);
+  DevBuf *bufs[] = { &m->small,&m->payload,&m->rrec,&m->rscr,&m->rpay,&m->epart,&m->erecv };
+  for (auto b : bufs) b->release();
+  delete m;
+  c->mg = NULL;
+}
+
+extern "C" int fkgpu_comm_id(uint8_t *id)
+{ fkmg::Api *na = fkmg::api();
+  if (id == NULL) return set_err(FKGPU_E_ARG,"fkgpu_comm_id: NULL argument");
+  if (na == NULL) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_comm_id: libnccl.so.2 could not be loaded (set FKGPU_NCCL_LIB)");
+  fkmg::UniqueId u;
+  NC(na->GetUniqueId(&u));
+  static_assert(sizeof(u) == FKGPU_COMM_ID_BYTES,"NCCL unique id size");
+  memcpy(id,&u,sizeof(u));
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_comm_init(fkgpu_ctx *c, int nranks, int rank, const uint8_t *id)
+{ if (c == NULL || id == NULL || nranks < 1 || rank < 0 || rank >= nranks) return set_err(FKGPU_E_ARG,"fkgpu_comm_init: bad argument");
+  fkmg::Api *na = fkmg::api();
+  if (na == NULL) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_comm_init: libnccl.so.2 could not be loaded (set FKGPU_NCCL_LIB)");
+  CU(cudaSetDevice(c->cfg.device));
+  if (c->mg) mg_destroy(c);
+  MultiState *m = new (std::nothrow) MultiState();
+  if (m == NULL) return set_err(FKGPU_E_NOMEM,"fkgpu_comm_init: out of host memory");
+  fkmg::UniqueId u;
+  memcpy(&u,id,sizeof(u));
+  int r = na->CommInitRank(&m->comm,nranks,u,rank);
+  if (r != 0) { delete m; return set_err(FKGPU_E_CUDA,"ncclCommInitRank failed: %s",na->GetErrorString ? na->GetErrorString(r) : "NCCL error"); }
+  m->nranks = nranks; m->rank = rank;
+  c->mg = m;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_comm_info(fkgpu_ctx *c, int64_t *v, int64_t *table_sizes)
+{ if (c == NULL || v == NULL) return set_err(FKGPU_E_ARG,"fkgpu_comm_info: NULL argument");
+  if (c->mg == NULL) return set_err(FKGPU_E_STATE,"fkgpu_comm_info: no communicator (fkgpu_comm_init)");
+  MultiState *m = c->mg;
+  int64_t off = 0;
+  for (int r = 0; r < m->rank && r < (int) m->table_sizes.size(); r++) off += m->table_sizes[r];
+  v[0] = m->nranks; v[1] = m->rank; v[2] = m->global_ntable; v[3] = off; v[4] = m->sent_records; v[5] = m->sent_entries;
+  if (table_sizes)
+    for (int r = 0; r < m->nranks; r++) table_sizes[r] = r < (int) m->table_sizes.size() ? m->table_sizes[r] : 0;
+  return FKGPU_OK;
+}
+
+/*  every rank contributes n u64 values; -> all of them, rank-major, on the host (one all-gather, one synchronize) */
+static int mg_gather_u64(fkgpu_ctx *c, const u64 *mine, int n, std::vector<u64> &all)
+{ MultiState *m = c->mg;
+  fkmg::Api *na = fkmg::api();
+  const int W = m->nranks;
+  if (m->small.ensure((size_t) (W + 1) * n * 8 + 64)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  u64 *d_mine = (u64 *) m->small.p, *d_all = d_mine + n;
+  CU(cudaMemcpyAsync(d_mine,mine,(size_t) n * 8,cudaMemcpyHostToDevice,c->st));
+  NC(na->AllGather(d_mine,d_all,(size_t) n,fkmg::kUint64,m->comm,c->st));
+  all.resize((size_t) W * n);
+  CU(cudaMemcpyAsync(all.data(),d_all,(size_t) W * n * 8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return FKGPU_OK;
+}
+
+/*  variable-size all-to-all of elements of eb bytes: slice r of `send` (element offset soff[r], scnt[r] elements) goes to rank
+    r, the slice of rank r lands at element offset roff[r] of `recv`; one NCCL group, the own slice is a device copy          */
+static int mg_alltoall(fkgpu_ctx *c, const void *send, const std::vector<u64> &soff, const std::vector<u64> &scnt,
+                       void *recv, const std::vector<u64> &roff, const std::vector<u64> &rcnt, size_t eb)
+{ MultiState *m = c->mg;
+  fkmg::Api *na = fkmg::api();
+  NC(na->GroupStart());
+  for (int r = 0; r < m->nranks; r++)
+    { if (r == m->rank) continue;
+      if (scnt[r]) NC(na->Send((const char *) send + soff[r] * eb,(size_t) scnt[r] * eb,fkmg::kUint8,r,m->comm,c->st));
+      if (rcnt[r]) NC(na->Recv((char *) recv + roff[r] * eb,(size_t) rcnt[r] * eb,fkmg::kUint8,r,m->comm,c->st));
+    }
+  NC(na->GroupEnd());
+  if (scnt[m->rank])
+    CU(cudaMemcpyAsync((char *) recv + roff[m->rank] * eb,(const char *) send + soff[m->rank] * eb,(size_t) scnt[m->rank] * eb,
+                       cudaMemcpyDeviceToDevice,c->st));
+  return FKGPU_OK;
+}
+
+/*  plan of one exchange: what this rank sends to everyone (from the group starts `off` of its locally partitioned items and
+    the agreed cut points `beg`), what it receives (all-gather of the send counts)                                          */
+struct MgPlan { std::vector<u64> soff, scnt, roff, rcnt; u64 nsend = 0, nrecv = 0; };
+
+static int mg_plan(fkgpu_ctx *c, const std::vector<u64> &off, const std::vector<int> &beg, MgPlan &pl)
+{ MultiState *m = c->mg;
+  const int W = m->nranks;
+  pl.soff.resize(W); pl.scnt.resize(W); pl.roff.resize(W); pl.rcnt.resize(W);
+  for (int r = 0; r < W; r++) { pl.soff[r] = off[beg[r]]; pl.scnt[r] = off[beg[r+1]] - off[beg[r]]; }
+  std::vector<u64> all;
+  int rc = mg_gather_u64(c,pl.scnt.data(),W,all);
+  if (rc) return rc;
+  pl.nsend = 0; pl.nrecv = 0;
+  for (int r = 0; r < W; r++)
+    { pl.rcnt[r] = all[(size_t) r * W + m->rank];
+      pl.roff[r] = pl.nrecv; pl.nrecv += pl.rcnt[r];
+      pl.nsend += pl.scnt[r];
+    }
+  return FKGPU_OK;
+}
+
+static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, int fetch_table, fkgpu_result *res)
+{ MultiState *m = c->mg;
+  fkmg::Api *na = fkmg::api();
+  const int W = m->nranks, me = m->rank;
+  if (!super_path_ok(c)) return set_err(FKGPU_E_UNSUPPORTED,"multi-GPU count: k = %d is outside the super-mer path (18..64)",c->cfg.kmer);
+  if (c->cfg.do_profile) return set_err(FKGPU_E_UNSUPPORTED,"multi-GPU count: -p needs the whole table on one device");
+  const int EW = entry_words(c->cfg.kmer);
+  const size_t EB = (size_t) 8 * EW;
+  const bool want_entries = c->cfg.do_table > 0;
+  memset(c->used,0,sizeof(c->used));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+
+  /* ---- global position space: rank r's stream starts at pos_base[r] (multiples of 64) */
+  std::vector<u64> all;
+  { u64 mine = (u64) npos;
+    int rc = mg_gather_u64(c,&mine,1,all);
+    if (rc) return rc;
+  }
+  std::vector<u64> pbase(W + 1,0);
+  for (int r = 0; r < W; r++) pbase[r+1] = pbase[r] + ((all[r] + 63) / 64) * 64;
+  const long long total = (long long) pbase[W];
+  const SuperGeom g = super_geom(c->cfg.kmer,total);
+  if (g.pbits > 64 - SUP_LBITS - 2) return set_err(FKGPU_E_ARG,"multi-GPU count: %lld positions do not fit a super-mer record",total);
+
+  /* ---- scan own reads, level-1 partition by bucket */
+  int rc = prepare_common(c,npos,std::max(g.P1,1),false,2);
+  if (rc) return rc;
+  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  SuperCounters *d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  const size_t abytes = (size_t) (npos + 4) * 16;
+  const u64 scap = (u64) (abytes / 2 / sizeof(u64)) - 8;
+  Key<1> *SA = (Key<1> *) c->bufA.p;
+  Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
+  stage_begin(c,FKGPU_ST_SUPERSCAN);
+  rc = super_scan_stage(c,d_seq,d_val,npos,g,pbase[me],(u64 *) SA,scap,d_cnt);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERSCAN);
+  SuperCounters hc;
+  CU(cudaMemcpyAsync(&hc,d_cnt,sizeof(hc),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  /* a rank whose super-mers overflow its staging buffer must not leave the others waiting in a collective: agree first */
+  { u64 ok = (hc.nrec <= scap) ? 1 : 0;
+    rc = mg_gather_u64(c,&ok,1,all);
+    if (rc) return rc;
+    for (int r = 0; r < W; r++)
+      if (!all[r]) return set_err(FKGPU_E_UNSUPPORTED,"multi-GPU count: rank %d produced more super-mers than its staging buffer holds",r);
+  }
+  const long long S = (long long) hc.nrec;
+  const int b1 = g.bbits ? g.P1 : 0, n1 = 1 << b1;
+  stage_begin(c,FKGPU_ST_SUPERPART);
+  rc = super_level1(c,SA,SB,S,b1);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SUPERPART);
+
+  /* ---- owners of the buckets: all-reduced level-1 histogram -> contiguous ranges */
+  if (m->small.ensure((size_t) (FKGPU_HIST_BINS + 2*n1 + 64) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  std::vector<u64> gh(n1), off(n1 + 1);
+  { u64 *d_g = (u64 *) m->small.p;
+    NC(na->AllReduce(c->hist1.p,d_g,(size_t) n1,fkmg::kUint64,fkmg::kSum,m->comm,c->st));
+    CU(cudaMemcpyAsync(gh.data(),d_g,(size_t) n1 * 8,cudaMemcpyDeviceToHost,c->st));
+    CU(cudaMemcpyAsync(off.data(),c->off1.p,(size_t) (n1 + 1) * 8,cudaMemcpyDeviceToHost,c->st));
+    CU(cudaStreamSynchronize(c->st));
+  }
+  std::vector<int> beg;
+  fkmg::splitters(gh.data(),n1,W,beg);
+  MgPlan pl;
+  rc = mg_plan(c,off,beg,pl);
+  if (rc) return rc;
+  m->sent_records = (int64_t) (pl.nsend - pl.scnt[me]);
+
+  /* ---- the base string of every record (32 bytes, left aligned) travels beside it */
+  if (m->payload.ensure((size_t) (S + 8) * 32) || m->rrec.ensure((size_t) (pl.nrecv + 8) * 8) || m->rscr.ensure((size_t) (pl.nrecv + 8) * 8)
+      || m->rpay.ensure((size_t) (pl.nrecv + 8) * 32))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (exchange buffers: %lld records out, %llu in)",S,pl.nrecv);
+  stage_begin(c,FKGPU_ST_SCATTER);
+  if (S > 0)
+    { k_materialise<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(uint4 *) m->payload.p); KCHECK(); }
+  rc = mg_alltoall(c,SB,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8);
+  if (rc) return rc;
+  rc = mg_alltoall(c,m->payload.p,pl.soff,pl.scnt,m->rpay.p,pl.roff,pl.rcnt,32);
+  if (rc) return rc;
+  stage_end(c,FKGPU_ST_SCATTER);
+  const long long nrecv = (long long) pl.nrecv;
+  if (nrecv > 0)
+    { k_reindex<<<(unsigned) ((nrecv + 255) / 256),256,0,c->st>>>((u64 *) m->rrec.p,nrecv,g.pbits); KCHECK(); }
+
+  /* ---- count the owned buckets; the entries are bounded by the k-mers the received records cover */
+  u64 nk = 0;
+  { u64 *d_nk = (u64 *) m->small.p;
+    CU(cudaMemsetAsync(d_nk,0,8,c->st));
+    if (nrecv > 0)
+      { k_sum_lengths<<<c->sms * 4,256,0,c->st>>>((const u64 *) m->rrec.p,nrecv,g.pbits,d_nk); KCHECK(); }
+    CU(cudaMemcpyAsync(&nk,d_nk,8,cudaMemcpyDeviceToHost,c->st));
+    CU(cudaStreamSynchronize(c->st));
+  }
+  void *ent = NULL;
+  if (want_entries)
+    { if (c->bufB.ensure((size_t) (nk + 4) * EB)) return set_err(FKGPU_E_NOMEM,"out of device memory (entries of %llu k-mers)",nk);
+      ent = c->bufB.p;
+    }
+  rc = prepare_small(c,std::max(g.P1,1));                 /* histogram + scalars start from zero; hist1 / off1 are re-used below */
+  if (rc) return rc;
+  if (c->segs.ensure(sizeof(SuperCounters))) return set_err(FKGPU_E_NOMEM,"out of device memory");
+  d_cnt = (SuperCounters *) c->segs.p;
+  CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
+  Misc hm; long long gmax = 0;
+  rc = super_count_stage(c,g,(Key<1> *) m->rrec.p,(Key<1> *) m->rscr.p,nrecv,NULL,1,NULL,NULL,m->rpay.p,NULL,ent,nk,d_cnt,&hc,&hm,&gmax);
+  if (rc) return rc;
+  const u64 nent = want_entries ? hc.nent : 0;
+  bank_times(c);
+
+  /* ---- table: distinct entries to the owners of their key range, key order there */
+  res->ntable = 0; res->table = NULL; res->table_dev = NULL;
+  m->sent_entries = 0;
+  if (want_entries)
+    { const int eb1 = 11, ne = 1 << eb1;
+      if (m->epart.ensure((size_t) (nent + 8) * EB) || m->small.ensure((size_t) (FKGPU_HIST_BINS + 4*ne + 64) * 8))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (entry partition)");
+      u64 *d_h = (u64 *) m->small.p, *d_o = d_h + ne, *d_g = d_o + ne + 1;
+      stage_begin(c,FKGPU_ST_L2HIST);
+      rc = (EW == 3) ? entries_partition_t<3>(c,ent,(int64_t) nent,eb1,m->epart.p,(uint64_t *) d_h,(uint64_t *) d_o)
+                     : entries_partition_t<2>(c,ent,(int64_t) nent,eb1,m->epart.p,(uint64_t *) d_h,(uint64_t *) d_o);
+      if (rc) return rc;
+      stage_end(c,FKGPU_ST_L2HIST);
+      std::vector<u64> gh2(ne), off2(ne + 1);
+      NC(na->AllReduce(d_h,d_g,(size_t) ne,fkmg::kUint64,fkmg::kSum,m->comm,c->st));
+      CU(cudaMemcpyAsync(gh2.data(),d_g,(size_t) ne * 8,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaMemcpyAsync(off2.data(),d_o,(size_t) (ne + 1) * 8,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      std::vector<int> beg2;
+      fkmg::splitters(gh2.data(),ne,W,beg2);
+      MgPlan p2;
+      rc = mg_plan(c,off2,beg2,p2);
+      if (rc) return rc;
+      m->sent_entries = (int64_t) (p2.nsend - p2.scnt[me]);
+      if (m->erecv.ensure((size_t) (p2.nrecv + 8) * EB) || c->bufA.ensure((size_t) (p2.nrecv + 8) * EB))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (%llu entries in)",p2.nrecv);
+      rc = mg_alltoall(c,m->epart.p,p2.soff,p2.scnt,m->erecv.p,p2.roff,p2.rcnt,EB);
+      if (rc) return rc;
+      bank_times(c);
+      fkgpu_result tr; memset(&tr,0,sizeof(tr));
+      rc = entries_sort_stage(c,m->erecv.p,c->bufA.p,(long long) p2.nrecv,fetch_table,&tr);
+      if (rc) return rc;
+      rc = d2h_join(c);
+      if (rc) return rc;
+      res->ntable = tr.ntable; res->table = tr.table; res->table_dev = tr.table_dev;
+    }
+
+  /* ---- global histogram and scalars; table sizes in rank (= key) order */
+  { u64 *d_x = (u64 *) m->small.p, *d_s = d_x + FKGPU_HIST_BINS;
+    u64 sc[3] = { hm.maxinst, nk, hm.ndistinct };
+    CU(cudaMemcpyAsync(d_s,sc,sizeof(sc),cudaMemcpyHostToDevice,c->st));
+    NC(na->AllReduce(c->ghist.p,d_x,(size_t) FKGPU_HIST_BINS,fkmg::kUint64,fkmg::kSum,m->comm,c->st));
+    NC(na->AllReduce(d_s,d_s,3,fkmg::kUint64,fkmg::kSum,m->comm,c->st));
+    CU(cudaMemcpyAsync(c->h_hist,d_x,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+    CU(cudaMemcpyAsync(sc,d_s,sizeof(sc),cudaMemcpyDeviceToHost,c->st));
+    CU(cudaStreamSynchronize(c->st));
+    res->hist = c->h_hist;
+    res->max_inst = (int64_t) sc[0]; res->nkmers = (int64_t) sc[1]; res->ndistinct = (int64_t) sc[2];
+    u64 nt = (u64) res->ntable;
+    rc = mg_gather_u64(c,&nt,1,all);
+    if (rc) return rc;
+    m->table_sizes.assign(W,0); m->global_ntable = 0;
+    for (int r = 0; r < W; r++) { m->table_sizes[r] = (int64_t) all[r]; m->global_ntable += (int64_t) all[r]; }
+  }
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  single_run(c,res);
+  c->last_path = 1; c->last_ndist = (long long) hm.ndistinct;
+  c->st_super = S; c->st_ent = (long long) nent; c->st_groups = gmax; c->st_split = hc.pad; c->st_spill = c->st_spill_acc; c->st_expanded = c->st_exp_acc;
+  return FKGPU_OK;
+}
+
+extern "C" int fkgpu_count_packed_multi(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                                        int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL || npos < 0 || (npos > 0 && (d_seq == NULL || d_val == NULL)))
+    return set_err(FKGPU_E_ARG,"fkgpu_count_packed_multi: bad argument");
+  if (c->mg == NULL) return set_err(FKGPU_E_STATE,"fkgpu_count_packed_multi: no communicator (fkgpu_comm_init)");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  res->nbases = npos;
+  return count_packed_multi(c,d_seq,d_val,npos,fetch_table,res);
 }
 
 /*  pieces: copy praw[src[i] .. src[i]+len[i]) to the output at dst[i]; offs = profile start of every read (+ total)  */

@@ -117,6 +117,14 @@ def load_library(path=None):
     lib.fkgpu_entries_partition.restype = C.c_int
     lib.fkgpu_entries_sort.argtypes = [vp, vp, i64, C.c_int, C.POINTER(_Result)]
     lib.fkgpu_entries_sort.restype = C.c_int
+    lib.fkgpu_comm_id.argtypes = [u8p]
+    lib.fkgpu_comm_id.restype = C.c_int
+    lib.fkgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
+    lib.fkgpu_comm_init.restype = C.c_int
+    lib.fkgpu_comm_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.fkgpu_comm_info.restype = C.c_int
+    lib.fkgpu_count_packed_multi.argtypes = [vp, vp, vp, i64, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_count_packed_multi.restype = C.c_int
     if path is None:
         _lib = lib
     return lib
@@ -127,7 +135,8 @@ EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
            "fkgpu_super_supported", "fkgpu_entry_bytes", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
-           "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_payload", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort"]
+           "fkgpu_ipc_close", "fkgpu_super_scan", "fkgpu_super_payload", "fkgpu_super_count", "fkgpu_entries_partition", "fkgpu_entries_sort",
+           "fkgpu_comm_id", "fkgpu_comm_init", "fkgpu_comm_info", "fkgpu_count_packed_multi"]
 
 
 class FkResult:
@@ -257,6 +266,30 @@ class FastKGPU:
         r = _Result()
         self._chk(self.lib.fkgpu_count_records(self.h, d_rec_ptr, n, 1 if fetch_table else 0, C.byref(r)),
                   "fkgpu_count_records")
+        return FkResult(r, copy_table)
+
+    # ---- multi-GPU count inside the library (NCCL communicator; collective calls) ----------------------------------
+    def comm_id(self):
+        b = (C.c_uint8 * 128)()
+        self._chk(self.lib.fkgpu_comm_id(b), "fkgpu_comm_id")
+        return bytes(b)
+
+    def comm_init(self, nranks, rank, comm_id: bytes):
+        b = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        self._chk(self.lib.fkgpu_comm_init(self.h, nranks, rank, b), "fkgpu_comm_init")
+        self.nranks, self.rank = nranks, rank
+
+    def comm_info(self):
+        v = (C.c_int64 * 6)()
+        ts = (C.c_int64 * max(1, getattr(self, "nranks", 1)))()
+        self._chk(self.lib.fkgpu_comm_info(self.h, v, ts), "fkgpu_comm_info")
+        return dict(nranks=int(v[0]), rank=int(v[1]), ntable=int(v[2]), table_offset=int(v[3]), sent_records=int(v[4]),
+                    sent_entries=int(v[5]), table_sizes=[int(x) for x in ts])
+
+    def count_packed_multi(self, d_seq_ptr, d_val_ptr, npos, fetch_table=False, copy_table=True):
+        r = _Result()
+        self._chk(self.lib.fkgpu_count_packed_multi(self.h, d_seq_ptr, d_val_ptr, npos, 1 if fetch_table else 0, C.byref(r)),
+                  "fkgpu_count_packed_multi")
         return FkResult(r, copy_table)
 
     # ---- multi-GPU stages of the super-mer path (include/fastk_gpu.h) ------------------------------------------

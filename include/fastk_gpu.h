@@ -207,6 +207,25 @@ int  fkgpu_entries_partition(fkgpu_ctx *ctx, const void *d_entries, int64_t n, i
                              uint64_t *d_hist, uint64_t *d_offsets);
 int  fkgpu_entries_sort(fkgpu_ctx *ctx, void *d_entries, int64_t n, int fetch_table, fkgpu_result *res);
 
+/* ---- multi-GPU count inside the library ---------------------------------------------
+ *  One context per GPU (one process per GPU, or one thread per GPU of a single process), joined by one NCCL communicator
+ *  (libnccl.so.2 is bound at run time; single-GPU users need no NCCL).  Reads are data-parallel: every rank ingests / packs
+ *  ITS reads.  fkgpu_count_packed_multi (and fkgpu_finish on a context with a communicator) is COLLECTIVE: super-mer records
+ *  and their base strings are exchanged so that every minimizer bucket is counted by one owner, the distinct entries are
+ *  exchanged by key prefix and sorted by their owner.  Result per rank: res->hist / nkmers / ndistinct / max_inst are GLOBAL,
+ *  res->table is this rank's key range; rank order == key order, so the global table is the rank-ordered concatenation
+ *  (fkgpu_comm_info gives the sizes) -- what the reference gets from Merge_Tables (table.c:346-533).
+ *   fkgpu_comm_id     a fresh communicator id (rank 0 calls it and hands the bytes to the others)
+ *   fkgpu_comm_init   collective: joins rank `rank` of `nranks`
+ *   fkgpu_comm_info   v[6] = nranks, rank, global table records, table offset of this rank, records sent, entries sent;
+ *                     table_sizes (may be NULL) [nranks] records per rank                                                    */
+#define FKGPU_COMM_ID_BYTES 128
+int  fkgpu_comm_id  (uint8_t *id /*[FKGPU_COMM_ID_BYTES]*/);
+int  fkgpu_comm_init(fkgpu_ctx *ctx, int nranks, int rank, const uint8_t *id);
+int  fkgpu_comm_info(fkgpu_ctx *ctx, int64_t *v /*[6]*/, int64_t *table_sizes /*[nranks] or NULL*/);
+int  fkgpu_count_packed_multi(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
+                              int fetch_table, fkgpu_result *res);
+
 /*  Instrumentation for bench.py: # of kernel launches issued by this context so far, and the
  *  accumulated CUDA-event time / algorithmic bytes of the dominant kernel family (final sort+count). */
 int64_t fkgpu_launch_count(fkgpu_ctx *ctx);

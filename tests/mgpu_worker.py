@@ -31,11 +31,34 @@ def main():
     bases, boff = synth.to_block(reads)
     npos = len(bases)
     a = torch.frombuffer(bytearray(bases + b"\0" * 64), dtype=torch.uint8).to(dev)
-    mg = multigpu.MultiGPUCounter(eng, world, rank, dev)
-    d_seq, d_val = mg.alloc_reads(npos)        # library-owned: the peers map them over CUDA IPC (super-mer path)
-    eng.pack_ascii_dev(a.data_ptr(), npos, d_seq, d_val)
-    torch.cuda.synchronize()
-    out = mg.count_packed(d_seq, d_val, npos, fetch_table=True)
+    impl = sys.argv[3] if len(sys.argv) > 3 else "py"
+    mg = None
+    if impl == "c":
+        # the exchange inside the C library: one NCCL communicator, fkgpu_count_packed_multi is collective
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(eng.comm_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(world, rank, idt.cpu().numpy().tobytes())
+        sw, vw = eng.packed_words(npos)
+        ts, tv = torch.zeros(sw, dtype=torch.int32, device=dev), torch.zeros(vw, dtype=torch.int32, device=dev)
+        d_seq, d_val = ts.data_ptr(), tv.data_ptr()
+        torch.cuda.synchronize()
+        eng.pack_ascii_dev(a.data_ptr(), npos, d_seq, d_val)
+        torch.cuda.synchronize()
+        res = eng.count_packed_multi(d_seq, d_val, npos, fetch_table=True)
+        info = eng.comm_info()
+        out = multigpu.MultiResult()
+        out.path, out.local, out.kmer_bytes = "super-mer", res, res.kmer_bytes
+        out.hist, out.max_inst, out.nkmers, out.ndistinct = res.hist, res.max_inst, res.nkmers, res.ndistinct
+        out.ntable, out.table_sizes = info["ntable"], info["table_sizes"]
+    else:
+        mg = multigpu.MultiGPUCounter(eng, world, rank, dev)
+        d_seq, d_val = mg.alloc_reads(npos)        # library-owned: the peers map them over CUDA IPC (super-mer path)
+        torch.cuda.synchronize()
+        eng.pack_ascii_dev(a.data_ptr(), npos, d_seq, d_val)
+        torch.cuda.synchronize()
+        out = mg.count_packed(d_seq, d_val, npos, fetch_table=True)
     want_path = sys.argv[2] if len(sys.argv) > 2 else None
     assert want_path is None or out.path == want_path, (out.path, want_path)
     tw = out.kmer_bytes + 2
@@ -61,7 +84,8 @@ def main():
             ok = 0
             print("MGPU_FAIL", e)
     dist.barrier(device_ids=[local])
-    mg.close_peers()
+    if mg is not None:
+        mg.close_peers()
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
