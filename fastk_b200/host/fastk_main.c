@@ -38,12 +38,37 @@ static char *OUT_NAME;
 static char  OUT_DIR[4096], OUT_ROOT[4096];
 static int   have_out;
 
-static fkgpu_ctx *CTX;
+/*  FASTK_GPUS=<n> counts on n GPUs (devices FASTK_GPU .. FASTK_GPU+n-1): one context per GPU, joined by one NCCL communicator
+    inside the library; reader thread t feeds context t mod n.  Minimizer buckets and key ranges are exchanged over NVLink
+    and every GPU returns its key range of the table: the rank-ordered ranges are the runs the table writer merges.       */
+#define MAX_GPUS 16
+static fkgpu_ctx *CTXS[MAX_GPUS];
+static int        NGPUS = 1;
+#define CTX (CTXS[0])
 
 static void Clean_Exit(int status)
-{ if (have_out) fk_remove_outputs(OUT_DIR,OUT_ROOT);
-  if (CTX) fkgpu_destroy(CTX);
+{ int g;
+  if (have_out) fk_remove_outputs(OUT_DIR,OUT_ROOT);
+  if (NGPUS > 1) _exit(status);           /* peers may sit in a collective: do not wait for their contexts */
+  for (g = 0; g < NGPUS; g++)
+    if (CTXS[g]) fkgpu_destroy(CTXS[g]);
   exit(status);
+}
+
+typedef struct { int g; const uint8_t *id; int fetch; fkgpu_result res; int rc; char err[1024]; } Gpu_Job;
+
+static void *comm_thread(void *arg)
+{ Gpu_Job *J = (Gpu_Job *) arg;
+  J->rc = fkgpu_comm_init(CTXS[J->g],NGPUS,J->g,J->id);
+  if (J->rc) snprintf(J->err,sizeof(J->err),"%s",fkgpu_last_error());
+  return NULL;
+}
+
+static void *finish_thread(void *arg)
+{ Gpu_Job *J = (Gpu_Job *) arg;
+  J->rc = fkgpu_finish(CTXS[J->g],J->fetch,&J->res);
+  if (J->rc) snprintf(J->err,sizeof(J->err),"%s",fkgpu_last_error());
+  return NULL;
 }
 
 static double now(void)
@@ -82,7 +107,7 @@ typedef struct
 
 static void block_flush(Reader *R, Block *B, int rem)
 { if (B->nreads > 0)
-    { if (fkgpu_ingest(CTX,R->tid,B->bases,B->boff,B->nreads,rem) != 0)
+    { if (fkgpu_ingest(CTXS[R->tid % NGPUS],R->tid / NGPUS,B->bases,B->boff,B->nreads,rem) != 0)
         { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error());
           R->err = 1;
         }
@@ -391,9 +416,30 @@ int main(int argc, char *argv[])
   memset(&cfg,0,sizeof(cfg));
   cfg.kmer = KMER; cfg.do_table = DO_TABLE; cfg.do_profile = DO_PROFILE; cfg.bc_prefix = BC_PREFIX;
   cfg.device = getenv("FASTK_GPU") ? atoi(getenv("FASTK_GPU")) : 0;
-  cfg.nthreads = ITHREADS; cfg.reserve_bases = work; cfg.mem_limit = SORT_MEMORY;
-  if (fkgpu_create(&cfg,&CTX) != 0)
-    { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
+  NGPUS = getenv("FASTK_GPUS") ? atoi(getenv("FASTK_GPUS")) : 1;
+  if (NGPUS < 1 || NGPUS > MAX_GPUS) { fprintf(stderr,"%s: FASTK_GPUS must be in [1,%d]\n",Prog_Name,MAX_GPUS); exit(1); }
+  if (NGPUS > ITHREADS) NGPUS = ITHREADS;
+  if (NGPUS > 1 && DO_PROFILE) { fprintf(stderr,"%s: -p needs the whole table on one GPU: run without FASTK_GPUS\n",Prog_Name); exit(1); }
+  cfg.nthreads = (ITHREADS + NGPUS - 1) / NGPUS; cfg.reserve_bases = work / NGPUS + (NGPUS > 1 ? work / (8*NGPUS) : 0); cfg.mem_limit = SORT_MEMORY;
+  { int g;
+    for (g = 0; g < NGPUS; g++)
+      { fkgpu_config cg = cfg;
+        cg.device = cfg.device + g;
+        if (fkgpu_create(&cg,&CTXS[g]) != 0)
+          { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
+      }
+    if (NGPUS > 1)
+      { uint8_t   id[FKGPU_COMM_ID_BYTES];
+        Gpu_Job   job[MAX_GPUS];
+        pthread_t th[MAX_GPUS];
+        if (fkgpu_comm_id(id) != 0) { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); exit(1); }
+        for (g = 0; g < NGPUS; g++) { job[g].g = g; job[g].id = id; pthread_create(th+g,NULL,comm_thread,job+g); }
+        for (g = 0; g < NGPUS; g++) pthread_join(th[g],NULL);
+        for (g = 0; g < NGPUS; g++)
+          if (job[g].rc) { fprintf(stderr,"%s: GPU %d: %s\n",Prog_Name,g,job[g].err); exit(1); }
+        if (VERBOSE) fprintf(stderr,"  Counting on %d GPUs (one NCCL communicator inside the library)\n",NGPUS);
+      }
+  }
   if (PRO_NAME != NULL)
     { /* what Split_Table does for the reference (split.c:1943-2131): bring the table to where the profiles are made */
       int tk, tcut; uint8_t *trec; int64_t tn;
@@ -453,14 +499,35 @@ int main(int argc, char *argv[])
 
   if (VERBOSE) fprintf(stderr,"\nPhase 2: Sorting & Counting K-mers on the GPU\n");
   fkgpu_result res;
-  if (fkgpu_finish(CTX,DO_TABLE > 0,&res) != 0)
-    { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); Clean_Exit(1); }
+  const uint8_t *mruns[MAX_GPUS]; int64_t mrun_n[MAX_GPUS];
+  if (NGPUS == 1)
+    { if (fkgpu_finish(CTX,DO_TABLE > 0,&res) != 0)
+        { fprintf(stderr,"%s: %s\n",Prog_Name,fkgpu_last_error()); Clean_Exit(1); }
+    }
+  else
+    { /* the finish is collective: one thread per GPU; GPU g returns the g-th key range of the table */
+      static Gpu_Job job[MAX_GPUS];
+      pthread_t th[MAX_GPUS];
+      int g;
+      for (g = 0; g < NGPUS; g++) { job[g].g = g; job[g].fetch = DO_TABLE > 0; pthread_create(th+g,NULL,finish_thread,job+g); }
+      for (g = 0; g < NGPUS; g++) pthread_join(th[g],NULL);
+      for (g = 0; g < NGPUS; g++)
+        if (job[g].rc) { fprintf(stderr,"%s: GPU %d: %s\n",Prog_Name,g,job[g].err); Clean_Exit(1); }
+      res = job[0].res;
+      res.ntable = 0; res.nbases = 0; res.nreads = 0;
+      for (g = 0; g < NGPUS; g++)
+        { mruns[g] = job[g].res.table; mrun_n[g] = job[g].res.ntable;
+          res.ntable += job[g].res.ntable; res.nbases += job[g].res.nbases; res.nreads += job[g].res.nreads;
+          if (job[g].res.ms_total > res.ms_total) res.ms_total = job[g].res.ms_total;
+        }
+      res.nruns = NGPUS; res.run_table = mruns; res.run_ntable = mrun_n;
+    }
   t2 = now();
   if (VERBOSE)
     { fprintf(stderr,"  %lld %d-mers, %lld distinct; device %.3f ms (pack %.3f ms), wall %.3fs\n",
               (long long) res.nkmers,KMER,(long long) res.ndistinct,res.ms_total,res.ms_pack,t2-t1);
       fprintf(stderr,"  %.3f Gbases/s on the device\n",res.ms_total > 0 ? res.nbases/1e6/res.ms_total : 0.);
-      if (res.nruns > 1) fprintf(stderr,"  Counted in %d rounds (sorted runs merged while the table parts are written)\n",res.nruns);
+      if (res.nruns > 1 && NGPUS == 1) fprintf(stderr,"  Counted in %d rounds (sorted runs merged while the table parts are written)\n",res.nruns);
     }
 
   if (PRO_NAME == NULL && fk_write_hist(OUT_DIR,OUT_ROOT,KMER,res.hist,res.max_inst))
@@ -493,6 +560,6 @@ int main(int argc, char *argv[])
               t3-t0,t1-t0,t2-t1,t3-t2,ru.ru_maxrss/1024);
     }
   have_out = 0;
-  fkgpu_destroy(CTX);
+  { int g; for (g = 0; g < NGPUS; g++) fkgpu_destroy(CTXS[g]); }
   return 0;
 }

@@ -125,3 +125,23 @@ def test_cli_relative_profiles(oracle_lib, exe_name, tmp_path):
     assert np.array_equal(off, g["prof_off"]) and np.array_equal(prof, g["prof"])
     r = subprocess.run([exe, "-k21", "-p:" + os.path.join(d, "tab"), "-P" + d, "-N" + os.path.join(d, "bad"), g["src"]], capture_output=True, text=True)
     assert r.returncode == 1 and "k-mer size" in r.stderr
+
+
+def test_cli_multi_gpu_host_program(tmp_path):
+    """FASTK_GPUS=<n>: our host program drives one context per GPU (NCCL communicator inside the library), every GPU returns
+    its key range of the table and the writer lays the rank-ordered ranges down as one .ktab: files equal the golden ones."""
+    import fastk_b200
+    n = fastk_b200.load_library().fkgpu_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    g = util.golden("c1_k40")
+    d = str(tmp_path)
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    r = subprocess.run([OURS, "-k40", "-t1", "-T%d" % max(g["T"], world), "-v", "-P" + d, "-N" + os.path.join(d, "out"), g["src"]],
+                       capture_output=True, text=True, env=dict(os.environ, FASTK_GPUS=str(world)), timeout=600)
+    assert r.returncode == 0, r.stderr
+    h = util.read_hist_file(os.path.join(d, "out.hist"))
+    assert np.array_equal(h["hist"][1:], g["hist"][1:]) and h["max_inst"] == g["hist_header"][4]
+    kt = util.read_ktab_files(d, "out")
+    assert kt["payload"] == g["ktab_payload"] and kt["stub"][16:] == g["ktab_stub"][16:]
+    util.check_parts_on_first_byte_boundaries(kt)
