@@ -214,8 +214,14 @@ static void *reader_thread(void *arg)
 
   B.bases = (char *) malloc(DT_BLOCK + 8);
   B.boff  = (int32_t *) malloc(sizeof(int32_t)*(DT_READS+2));
-  B.nreads = 0; B.fill = 0; B.boff[0] = 0;
   memset(&P,0,sizeof(P));
+  if (buf == NULL || B.bases == NULL || B.boff == NULL)
+    { fprintf(stderr,"%s: Out of memory (reader thread buffers)\n",Prog_Name);
+      R->err = 1;
+      free(buf); free(B.bases); free(B.boff);
+      return NULL;
+    }
+  B.nreads = 0; B.fill = 0; B.boff[0] = 0;
   for (f = R->bfile; f <= R->efile && !R->err; f++)
     { File_Object *F = R->files + f;
       int64_t beg = (f == R->bfile) ? R->bpos : 0;
@@ -226,6 +232,12 @@ static void *reader_thread(void *arg)
           int n;
           if (g == NULL) { fprintf(stderr,"%s: Cannot open %s\n",Prog_Name,F->path); R->err = 1; break; }
           while ((n = gzread(g,buf,1 << 22)) > 0) parse_bytes(R,&B,&P,buf,n);
+          if (n < 0 || !gzeof(g))            /* corrupt or truncated .gz: a partial count must not look like a result */
+            { int e = 0;
+              const char *msg = gzerror(g,&e);
+              fprintf(stderr,"%s: Error reading %s: %s\n",Prog_Name,F->path,(e != 0 && msg != NULL) ? msg : "truncated compressed file");
+              R->err = 1;
+            }
           gzclose(g);
         }
       else
@@ -237,7 +249,12 @@ static void *reader_thread(void *arg)
             { int64_t want = end-pos; ssize_t n;
               if (want > (1 << 22)) want = 1 << 22;
               n = read(fd,buf,(size_t) want);
-              if (n <= 0) break;
+              if (n <= 0)
+                { fprintf(stderr,"%s: Error reading %s (%s at byte %lld of %lld)\n",Prog_Name,F->path,
+                          n < 0 ? "read failed" : "file is shorter than it was",(long long) pos,(long long) end);
+                  R->err = 1;
+                  break;
+                }
               parse_bytes(R,&B,&P,buf,n);
               pos += n;
             }

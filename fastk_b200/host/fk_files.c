@@ -269,7 +269,7 @@ int64_t fk_encode_profile(const uint16_t *prof, int64_t plen, uint8_t *out)
           continue;
         }
       if (lz) { *o++ = (uint8_t) lz; lz = 0; }
-      if (d > -32 && d < 32) *o++ = (uint8_t) (0x40 | (d & 0x3f));
+      if (d >= -31 && d <= 31) *o++ = (uint8_t) (0x40 | (d & 0x3f));     /* one byte for |d| < 32, as count.c:912-913 */
       else
         { uint16_t u = (uint16_t) d;
           *o++ = (uint8_t) ((u >> 8) | 0x80);

@@ -9,7 +9,11 @@ def main(rep, kernel, top=30):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv",
                           "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hi = [i for i, r in enumerate(rows) if len(r) > 8 and r[0] == "Line No"][0]
+    his = [i for i, r in enumerate(rows) if len(r) > 8 and r[0] == "Line No"]
+    if not his:
+        print("no source page for a kernel matching %r in %s (was it captured with --import-source on and -lineinfo?)" % (kernel, rep))
+        return
+    hi = his[0]
     h = rows[hi]
     iins, ismp = h.index("Instructions Executed"), h.index("# Samples")
     data, tot, tots = [], 0, 0

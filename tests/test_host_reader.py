@@ -134,3 +134,18 @@ def test_reference_io_module_through_the_shim(refhost_stub, tmp_path):
     got = [ln for ln in open(out, "rb").read().split(b"\n")[:-1] if not ln.startswith(b"#tid")]
     assert sorted(len(x) for x in got) == sorted(len(x) for x in reads)
     assert got == reads
+
+
+def test_truncated_gz_is_an_error_not_a_short_input(stub_cli, tmp_path):
+    """A corrupt / truncated .gz must end the run with an error (and no outputs), never count the part that could be read."""
+    d = str(tmp_path)
+    reads = make_reads(3000, 150, 91)
+    fa = os.path.join(d, "t.fa")
+    synth.write_fasta(reads, fa)
+    raw = gzip.compress(open(fa, "rb").read())
+    gz = os.path.join(d, "cut.fa.gz")
+    open(gz, "wb").write(raw[:len(raw) * 2 // 3])
+    r = subprocess.run([stub_cli, "-N" + os.path.join(d, "o"), "-t1", gz], capture_output=True, text=True,
+                       env=dict(os.environ, FKSTUB_OUT=os.path.join(d, "delivered.txt")))
+    assert r.returncode == 1 and "Error reading" in r.stderr, (r.returncode, r.stderr)
+    assert not os.path.exists(os.path.join(d, "o.hist")) and not os.path.exists(os.path.join(d, "o.ktab"))
