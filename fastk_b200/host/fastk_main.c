@@ -232,12 +232,13 @@ static void *reader_thread(void *arg)
           int n;
           if (g == NULL) { fprintf(stderr,"%s: Cannot open %s\n",Prog_Name,F->path); R->err = 1; break; }
           while ((n = gzread(g,buf,1 << 22)) > 0) parse_bytes(R,&B,&P,buf,n);
-          if (n < 0 || !gzeof(g))            /* corrupt or truncated .gz: a partial count must not look like a result */
-            { int e = 0;
-              const char *msg = gzerror(g,&e);
-              fprintf(stderr,"%s: Error reading %s: %s\n",Prog_Name,F->path,(e != 0 && msg != NULL) ? msg : "truncated compressed file");
-              R->err = 1;
-            }
+          { int e = 0;                       /* corrupt or truncated .gz: a partial count must not look like a result */
+            const char *msg = gzerror(g,&e);
+            if (n < 0 || !gzeof(g) || (e != Z_OK && e != Z_STREAM_END))
+              { fprintf(stderr,"%s: Error reading %s: %s\n",Prog_Name,F->path,(e != Z_OK && msg != NULL && msg[0]) ? msg : "truncated compressed file");
+                R->err = 1;
+              }
+          }
           gzclose(g);
         }
       else
