@@ -2414,6 +2414,76 @@ extern "C" int fkgpu_load_profile_table(fkgpu_ctx *c, const uint8_t *records, in
   return (c->NW == 1) ? load_profile_table_t<1>(c,records,n) : load_profile_table_t<2>(c,records,n);
 }
 
+/*  GPU Fastmerge (Fastmerge.c:168-450): the records of ntab sorted tables are put in key order together by the
+ *  entry sort (two-level prefix partition + in-smem ordering, the path every count ends with), then runs of equal k-mers are
+ *  merged: counts added and saturated, histogram of the merged counts.  res->max_inst only holds what the unsaturated members
+ *  of saturated sums stood for (Fastmerge.c:321-327): the caller adds the max_inst of the input histograms (Fastmerge.c:1009). */
+extern "C" int fkgpu_merge_tables(fkgpu_ctx *c, const uint8_t *const *tables, const int64_t *n, int ntab, int fetch_table, fkgpu_result *res)
+{ if (c == NULL || res == NULL || ntab < 1 || tables == NULL || n == NULL) return set_err(FKGPU_E_ARG,"fkgpu_merge_tables: bad argument");
+  if (c->cfg.do_table < 1 || c->cfg.do_profile) return set_err(FKGPU_E_STATE,"fkgpu_merge_tables: needs a context with do_table >= 1 and no do_profile");
+  CU(cudaSetDevice(c->cfg.device));
+  init_result(c,res);
+  const int tw = c->kbytes + 2, EW = entry_words(c->cfg.kmer);
+  const size_t EB = (size_t) 8 * EW;
+  long long N = 0;
+  for (int t = 0; t < ntab; t++)
+    { if (n[t] < 0 || (n[t] > 0 && tables[t] == NULL)) return set_err(FKGPU_E_ARG,"fkgpu_merge_tables: table %d is missing",t);
+      N += n[t];
+    }
+  int rc = prepare_small(c,1);
+  if (rc) return rc;
+  if (c->spillA.ensure((size_t) N * tw + 64) || c->bufB.ensure((size_t) (N + 4) * EB) || c->bufA.ensure((size_t) (N + 4) * EB)
+      || c->scnt.ensure((size_t) (N + 2) * 4) || c->poff.ensure((size_t) (N + 2) * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (merging %lld table records)",N);
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  { size_t at = 0;
+    for (int t = 0; t < ntab; t++)
+      if (n[t] > 0)
+        { CU(cudaMemcpyAsync((uint8_t *) c->spillA.p + at,tables[t],(size_t) n[t] * tw,cudaMemcpyHostToDevice,c->st));
+          at += (size_t) n[t] * tw;
+        }
+  }
+  res->ntable = 0; res->table = NULL; res->table_dev = NULL;
+  if (N > 0)
+    { const unsigned gr = (unsigned) ((N + 255) / 256);
+      if (EW == 3) k_table_to_entries<3><<<gr,256,0,c->st>>>((const uint8_t *) c->spillA.p,(u64) N,c->kbytes,(Key<3> *) c->bufB.p,0,(u64) N);
+      else         k_table_to_entries<2><<<gr,256,0,c->st>>>((const uint8_t *) c->spillA.p,(u64) N,c->kbytes,(Key<2> *) c->bufB.p,0,(u64) N);
+      KCHECK();
+      fkgpu_result tmp; memset(&tmp,0,sizeof(tmp));
+      rc = entries_sort_stage(c,c->bufB.p,c->bufA.p,N,0,&tmp);            /* -> c->table: N records in key order, equal keys adjacent */
+      if (rc) return rc;
+      if (tmp.ntable != N) return set_err(FKGPU_E_CUDA,"internal: the merge sort returned %lld of %lld records",(long long) tmp.ntable,N);
+      Misc *d_misc = (Misc *) c->misc.p;
+      u32 *head = (u32 *) c->scnt.p;
+      k_run_heads<<<gr,256,0,c->st>>>((const uint8_t *) c->table.p,(u64) N,c->kbytes,head); KCHECK();
+      rc = run_large_scan<2>(c,head,N,(u64 *) c->poff.p,&d_misc->total_pass);
+      if (rc) return rc;
+      u64 U = 0;
+      CU(cudaMemcpyAsync(&U,&d_misc->total_pass,8,cudaMemcpyDeviceToHost,c->st));
+      CU(cudaStreamSynchronize(c->st));
+      if (c->spillB.ensure((size_t) U * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of device memory (merged table of %llu records)",U);
+      CU(cudaMemsetAsync(c->ghist.p,0,FKGPU_HIST_BINS * 8,c->st));
+      CU(cudaMemsetAsync(&d_misc->maxinst,0,8,c->st));
+      k_merge_runs<<<gr,256,0,c->st>>>((const uint8_t *) c->table.p,(u64) N,c->kbytes,head,(const u64 *) c->poff.p,(uint8_t *) c->spillB.p,
+                                       (u64 *) c->ghist.p,&d_misc->maxinst); KCHECK();
+      res->ntable = (int64_t) U; res->table_dev = (const uint8_t *) c->spillB.p;
+      if (fetch_table)
+        { if (c->h_table.ensure((size_t) U * tw + 64)) return set_err(FKGPU_E_NOMEM,"out of pinned host memory (merged table)");
+          CU(cudaMemcpyAsync(c->h_table.p,c->spillB.p,(size_t) U * tw,cudaMemcpyDeviceToHost,c->st));
+          res->table = (const uint8_t *) c->h_table.p;
+        }
+    }
+  Misc hm;
+  CU(cudaMemcpyAsync(c->h_hist,c->ghist.p,sizeof(c->h_hist),cudaMemcpyDeviceToHost,c->st));
+  CU(cudaMemcpyAsync(&hm,c->misc.p,sizeof(hm),cudaMemcpyDeviceToHost,c->st));
+  cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
+  CU(cudaStreamSynchronize(c->st));
+  collect_times(c,res);
+  res->hist = c->h_hist; res->max_inst = (int64_t) hm.maxinst; res->ndistinct = res->ntable; res->nkmers = 0;
+  single_run(c,res);
+  return FKGPU_OK;
+}
+
 extern "C" int fkgpu_profiles_packed(fkgpu_ctx *c, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
                                      const int64_t *read_start, const int32_t *read_len, int64_t nreads_in,
                                      int64_t *nreads, const int64_t **off, const uint16_t **prof)

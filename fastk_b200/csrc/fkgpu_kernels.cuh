@@ -918,7 +918,11 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
         { const u64 b = srtB[j];
           const u32 pb = (u32) (b >> 32);
           bool lt = pb < pa;
-          if (pb == pa && j != e) lt = key_lt<NW>(rec[(u32) b >> 16],rec[(u32) a >> 16]);
+          if (pb == pa && j != e)
+            { /* entries that agree in every bit (the same k-mer with the same count from two merged tables) order by position */
+              const Key<NW> kb = rec[(u32) b >> 16], ka = rec[(u32) a >> 16];
+              lt = key_lt<NW>(kb,ka) || (j < e && key_eq<NW>(kb,ka));
+            }
           rank += lt ? 1u : 0u;
         }
       srt[rank] = a;
@@ -1499,6 +1503,43 @@ __global__ void __launch_bounds__(256) k_compact_keys(CompactParams p, Key<(NW =
           cnts[o+q] = (uint16_t) cnt[q];
         }
     }
+}
+
+/*  Merging tables (Fastmerge.c:168-450 on the device): the records of all tables, sorted together, hold runs of equal keys.
+ *  k_run_heads flags the first record of every run; k_merge_runs (one thread per record, heads only) adds the counts of its
+ *  run -- saturating at 32767, histogram of the merged counts, and for a saturated sum the instances its unsaturated
+ *  members stood for go to max_inst (Fastmerge.c:311-331) -- and writes the merged record at its rank among the heads.     */
+__global__ void __launch_bounds__(256) k_run_heads(const uint8_t *tab, u64 n, int kbytes, u32 *head)
+{ const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int tw = kbytes + 2;
+  bool h = (i == 0);
+  if (!h)
+    { const uint8_t *a = tab + i * (u64) tw, *b = a - tw;
+      for (int x = 0; x < kbytes; x++) h = h || (a[x] != b[x]);
+    }
+  head[i] = h ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_merge_runs(const uint8_t *tab, u64 n, int kbytes, const u32 *head, const u64 *pos, uint8_t *out,
+                                                    u64 *g_hist, u64 *g_maxinst)
+{ const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !head[i]) return;
+  const int tw = kbytes + 2;
+  const uint8_t *e = tab + i * (u64) tw;
+  u64 sum = 0, small = 0;
+  for (u64 j = i; j < n && (j == i || !head[j]); j++)
+    { const uint8_t *r = tab + j * (u64) tw;
+      const u32 c = (u32) r[kbytes] | ((u32) r[kbytes+1] << 8);
+      sum += c;
+      if (c < 0x7fffu) small += c;
+    }
+  const u32 sc = sum > 0x7fffull ? 0x7fffu : (u32) sum;
+  atomicAdd(g_hist + sc,1ull);
+  if (sum > 0x7fffull && small) atomicAdd(g_maxinst,small);
+  uint8_t *o = out + pos[i] * (u64) tw;
+  for (int x = 0; x < kbytes; x++) o[x] = e[x];
+  o[kbytes] = (uint8_t) (sc & 0xffu); o[kbytes+1] = (uint8_t) (sc >> 8);
 }
 
 /*  table records [kbytes key][u16 LE count] (a .ktab as the host read it back) -> the lookup arrays of k_profile  */

@@ -67,6 +67,8 @@ def load_library(path=None):
     lib.fkgpu_profiles_packed.restype = C.c_int
     lib.fkgpu_load_profile_table.argtypes = [vp, C.POINTER(C.c_uint8), i64]
     lib.fkgpu_load_profile_table.restype = C.c_int
+    lib.fkgpu_merge_tables.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(i64), C.c_int, C.c_int, C.POINTER(_Result)]
+    lib.fkgpu_merge_tables.restype = C.c_int
     lib.fkgpu_read_counts.argtypes = [vp, C.POINTER(i64)]
     lib.fkgpu_read_counts.restype = C.c_int
     lib.fkgpu_packed_words.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
@@ -131,7 +133,7 @@ def load_library(path=None):
 
 
 EXPORTS = ["fkgpu_create", "fkgpu_destroy", "fkgpu_reset", "fkgpu_last_error", "fkgpu_device_count",
-           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_load_profile_table", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
+           "fkgpu_ingest", "fkgpu_finish", "fkgpu_profiles", "fkgpu_profiles_packed", "fkgpu_load_profile_table", "fkgpu_merge_tables", "fkgpu_read_counts", "fkgpu_packed_words", "fkgpu_pack_ascii_dev",
            "fkgpu_count_packed", "fkgpu_record_bytes", "fkgpu_prefix_hist", "fkgpu_scatter_prefix",
            "fkgpu_count_records", "fkgpu_launch_count", "fkgpu_last_path", "fkgpu_last_stats", "fkgpu_stage_times",
            "fkgpu_super_supported", "fkgpu_entry_bytes", "fkgpu_super_bucket_bits", "fkgpu_reads_alloc", "fkgpu_ipc_export", "fkgpu_ipc_open",
@@ -380,6 +382,15 @@ class FastKGPU:
         t = np.ascontiguousarray(table, dtype=np.uint8)
         self._chk(self.lib.fkgpu_load_profile_table(self.h, t.ctypes.data_as(C.POINTER(C.c_uint8)), t.shape[0]),
                   "fkgpu_load_profile_table")
+
+    def merge_tables(self, tables, fetch_table=True):
+        """GPU Fastmerge: tables = list of (n_i, kmer_bytes + 2) uint8 arrays in key order -> FkResult of the merged table"""
+        ts = [np.ascontiguousarray(t, dtype=np.uint8) for t in tables]
+        ptrs = (C.POINTER(C.c_uint8) * len(ts))(*[t.ctypes.data_as(C.POINTER(C.c_uint8)) for t in ts])
+        ns = (C.c_int64 * len(ts))(*[t.shape[0] for t in ts])
+        r = _Result()
+        self._chk(self.lib.fkgpu_merge_tables(self.h, ptrs, ns, len(ts), 1 if fetch_table else 0, C.byref(r)), "fkgpu_merge_tables")
+        return FkResult(r, True)
 
     def profiles(self, copy=True):
         """-> (off int64 [nreads+1], prof uint16): prof[off[r]:off[r+1]] = counts of read r (tid-major read order).

@@ -120,6 +120,13 @@ int  fkgpu_profiles(fkgpu_ctx *ctx, int64_t *nreads, const int64_t **off, const 
  *  the loaded table holds for the canonical k-mer there, 0 if it is absent.                                          */
 int  fkgpu_load_profile_table(fkgpu_ctx *ctx, const uint8_t *records, int64_t n);
 
+/*  GPU Fastmerge (Fastmerge.c:168-450): merges ntab k-mer tables of the same k, each n[t] records [kmer_bytes key][u16 LE count]
+ *  in increasing key order (host memory), into one: the counts of equal k-mers are added and saturate at 32767; res->hist is
+ *  the histogram of the merged counts; res->max_inst holds only the instances that unsaturated members of saturated sums
+ *  stood for (Fastmerge.c:321-327) -- add the max_inst of the input histograms to it (Fastmerge.c:1009).  The context must
+ *  have been created with do_table >= 1, no do_profile, and the tables' k.                                          */
+int  fkgpu_merge_tables(fkgpu_ctx *ctx, const uint8_t *const *tables, const int64_t *n, int ntab, int fetch_table, fkgpu_result *res);
+
 /*  # of whole reads each tid delivered (continuation pieces of a split read are not counted twice); part t+1 of
  *  the .prof output holds the reads of tid t (merge.c:926-928).  per_tid has cfg.nthreads entries.          */
 int  fkgpu_read_counts(fkgpu_ctx *ctx, int64_t *per_tid);

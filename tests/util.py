@@ -149,3 +149,31 @@ def oracle_relative_profiles(oracle, table_reads, k, cutoff, reads):
         return out
     finally:
         oracle.lib.fko_free_table(t)
+
+
+def merge_tables_oracle(tables, kb):
+    """Fastmerge.c:311-331 restated in numpy for the tests: tables = list of (n, kb+2) uint8 record arrays in key order.
+    -> (merged records, hist[32768], max_inst part): counts of equal k-mers added and saturated at 32767, histogram of the
+    merged counts, and for sums above 32767 the counts of their unsaturated members go to max_inst."""
+    allr = np.concatenate([t for t in tables if len(t)]) if any(len(t) for t in tables) else np.zeros((0, kb + 2), np.uint8)
+    pad = np.zeros((len(allr), 16), dtype=np.uint8)
+    pad[:, :kb] = allr[:, :kb]
+    w = pad.view(">u8")
+    order = np.lexsort((w[:, 1], w[:, 0]))
+    allr = allr[order]
+    cnt = allr[:, kb].astype(np.int64) | (allr[:, kb + 1].astype(np.int64) << 8)
+    keys = w[order]
+    head = np.ones(len(allr), dtype=bool)
+    if len(allr) > 1:
+        head[1:] = (keys[1:] != keys[:-1]).any(axis=1)
+    gid = np.cumsum(head) - 1
+    ng = int(gid[-1]) + 1 if len(allr) else 0
+    tot = np.bincount(gid, weights=cnt, minlength=ng).astype(np.int64)
+    small = np.bincount(gid, weights=np.where(cnt < 0x7fff, cnt, 0), minlength=ng).astype(np.int64)
+    sat = np.minimum(tot, 0x7fff)
+    out = allr[head].copy()
+    out[:, kb] = sat & 0xff
+    out[:, kb + 1] = sat >> 8
+    hist = np.bincount(sat, minlength=32768).astype(np.int64)
+    hist[0] = 0
+    return out, hist, int(small[tot > 0x7fff].sum())
