@@ -293,7 +293,7 @@ def main():
         ascii_dev = host_ascii.to(dev, non_blocking=True)
     else:
         a.no_e2e, a.no_cpu = True, True
-    nthr = a.ingest_threads or max(1, min(16, os.cpu_count() or 1))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367)
+    nthr = a.ingest_threads or max(1, min(16, (os.cpu_count() or 1) // world))      # ingest threads = ITHREADS of the reference (its -T, FastK.c:367); the host cores are shared by the ranks
     eng = FastKGPU(k=k, table_cutoff=a.cutoff, profile=a.profile, device=local, nthreads=nthr,
                    reserve_bases=0 if a.device_gen else npos, mem_limit=int(a.mem_limit_gb * (1 << 30)))
     runner = None
@@ -355,8 +355,11 @@ def main():
     t0 = time.perf_counter()
     stage_ms = {}
     dev_ms = 0.0
+    step_ms = []
     for _ in range(a.steps):
+        ts0 = time.perf_counter()
         res = one_step()
+        step_ms.append(round(1e3 * (time.perf_counter() - ts0), 2))
         dev_ms += res.ms_total
         for kname, v in (res.stage_ms if runner is not None else eng.stage_times()).items():
             stage_ms[kname] = stage_ms.get(kname, 0.0) + v
@@ -602,7 +605,7 @@ def main():
     if rank == 0:
         line = {"metric": "Gbases/sec counted (k=%d)" % k, "value": value, "unit": "Gbases/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
-                "device_ms_per_step": dev_ms / a.steps,
+                "device_ms_per_step": dev_ms / a.steps, "step_wall_ms": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),

@@ -1204,7 +1204,7 @@ static int super_bucket_range(fkgpu_ctx *c, const SuperGeom &g, const Key<1> *l1
     bp.ent_min = (u32) ((c->cfg.do_profile || c->cfg.do_table < 1) ? 1 : std::min(c->cfg.do_table,0x7fff));
     bp.g_fail = &d_cnt->fail;
     /* groups beyond this many super-mers leave the chip (FKGPU_BIG overrides; the old kernel streams everything) */
-    bp.big = (u32) (bigv > 0 ? bigv : (bcv == 3 ? 256 : 2048));
+    bp.big = (u32) (bigv > 0 ? bigv : 2048);
     bp.g_stat = &d_cnt->sm_seen;
     bp.spill_cnt = &d_cnt->nspill; bp.spill_list = (u32 *) c->spill_list.p; bp.spill_cap = spill_cap; bp.spill_kmers = &d_cnt->spill_kmers;
     if (bcv == 3)
