@@ -606,6 +606,7 @@ def main():
         line = {"metric": "Gbases/sec counted (k=%d)" % k, "value": value, "unit": "Gbases/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
                 "device_ms_per_step": dev_ms / a.steps, "step_wall_ms": step_ms,
+                "all_stage_ms": {kn: round(v / a.steps, 3) for kn, v in stage_ms.items() if v > 0},
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "reads_per_gpu": nreads, "kmers_per_gpu": int(N),
                            "distinct_per_gpu": int(U), "table_records": int(res.ntable),

@@ -2040,6 +2040,8 @@ static void mg_destroy(fkgpu_ctx *c)
   if (m == NULL) return;
   fkmg::Api *na = fkmg::api();
   if (m->comm && na) na->CommDestroy(m->comm);
+  if (m->ev_rec) cudaEventDestroy(m->ev_rec);
+  if (m->ev_pay) cudaEventDestroy(m->ev_pay);
   DevBuf *bufs[] = { &m->small,&m->payload,&m->rrec,&m->rscr,&m->rpay,&m->epart,&m->erecv };
   for (auto b : bufs) b->release();
   delete m;
@@ -2070,6 +2072,8 @@ extern "C" int fkgpu_comm_init(fkgpu_ctx *c, int nranks, int rank, const uint8_t
   int r = na->CommInitRank(&m->comm,nranks,u,rank);
   if (r != 0) { delete m; return set_err(FKGPU_E_CUDA,"ncclCommInitRank failed: %s",na->GetErrorString ? na->GetErrorString(r) : "NCCL error"); }
   m->nranks = nranks; m->rank = rank;
+  CU(cudaEventCreateWithFlags(&m->ev_rec,cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&m->ev_pay,cudaEventDisableTiming));
   c->mg = m;
   return FKGPU_OK;
 }
@@ -2104,19 +2108,19 @@ static int mg_gather_u64(fkgpu_ctx *c, const u64 *mine, int n, std::vector<u64> 
 /*  variable-size all-to-all of elements of eb bytes: slice r of `send` (element offset soff[r], scnt[r] elements) goes to rank
     r, the slice of rank r lands at element offset roff[r] of `recv`; one NCCL group, the own slice is a device copy          */
 static int mg_alltoall(fkgpu_ctx *c, const void *send, const std::vector<u64> &soff, const std::vector<u64> &scnt,
-                       void *recv, const std::vector<u64> &roff, const std::vector<u64> &rcnt, size_t eb)
+                       void *recv, const std::vector<u64> &roff, const std::vector<u64> &rcnt, size_t eb, cudaStream_t st)
 { MultiState *m = c->mg;
   fkmg::Api *na = fkmg::api();
   NC(na->GroupStart());
   for (int r = 0; r < m->nranks; r++)
     { if (r == m->rank) continue;
-      if (scnt[r]) NC(na->Send((const char *) send + soff[r] * eb,(size_t) scnt[r] * eb,fkmg::kUint8,r,m->comm,c->st));
-      if (rcnt[r]) NC(na->Recv((char *) recv + roff[r] * eb,(size_t) rcnt[r] * eb,fkmg::kUint8,r,m->comm,c->st));
+      if (scnt[r]) NC(na->Send((const char *) send + soff[r] * eb,(size_t) scnt[r] * eb,fkmg::kUint8,r,m->comm,st));
+      if (rcnt[r]) NC(na->Recv((char *) recv + roff[r] * eb,(size_t) rcnt[r] * eb,fkmg::kUint8,r,m->comm,st));
     }
   NC(na->GroupEnd());
   if (scnt[m->rank])
     CU(cudaMemcpyAsync((char *) recv + roff[m->rank] * eb,(const char *) send + soff[m->rank] * eb,(size_t) scnt[m->rank] * eb,
-                       cudaMemcpyDeviceToDevice,c->st));
+                       cudaMemcpyDeviceToDevice,st));
   return FKGPU_OK;
 }
 
@@ -2216,14 +2220,19 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   if (m->payload.ensure((size_t) (S + 8) * 32) || m->rrec.ensure((size_t) (pl.nrecv + 8) * 8) || m->rscr.ensure((size_t) (pl.nrecv + 8) * 8)
       || m->rpay.ensure((size_t) (pl.nrecv + 8) * 32))
     return set_err(FKGPU_E_NOMEM,"out of device memory (exchange buffers: %lld records out, %llu in)",S,pl.nrecv);
+  /* the records go first, on the compute stream; their base strings follow on the copy stream, so that the 4x larger payload
+     crosses NVLink while this rank already partitions the records it received (the counting kernel waits for ev_pay)      */
   stage_begin(c,FKGPU_ST_SCATTER);
-  if (S > 0)
-    { k_materialise<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(uint4 *) m->payload.p); KCHECK(); }
-  rc = mg_alltoall(c,SB,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8);
-  if (rc) return rc;
-  rc = mg_alltoall(c,m->payload.p,pl.soff,pl.scnt,m->rpay.p,pl.roff,pl.rcnt,32);
+  rc = mg_alltoall(c,SB,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8,c->st);
   if (rc) return rc;
   stage_end(c,FKGPU_ST_SCATTER);
+  CU(cudaEventRecord(m->ev_rec,c->st));
+  CU(cudaStreamWaitEvent(c->cst,m->ev_rec,0));
+  if (S > 0)
+    { k_materialise<<<(unsigned) ((S + 255) / 256),256,0,c->cst>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(uint4 *) m->payload.p); KCHECK(); }
+  rc = mg_alltoall(c,m->payload.p,pl.soff,pl.scnt,m->rpay.p,pl.roff,pl.rcnt,32,c->cst);
+  if (rc) return rc;
+  CU(cudaEventRecord(m->ev_pay,c->cst));
   const long long nrecv = (long long) pl.nrecv;
   if (nrecv > 0)
     { k_reindex<<<(unsigned) ((nrecv + 255) / 256),256,0,c->st>>>((u64 *) m->rrec.p,nrecv,g.pbits); KCHECK(); }
@@ -2248,7 +2257,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   d_cnt = (SuperCounters *) c->segs.p;
   CU(cudaMemsetAsync(d_cnt,0,sizeof(SuperCounters),c->st));
   Misc hm; long long gmax = 0;
-  rc = super_count_stage(c,g,(Key<1> *) m->rrec.p,(Key<1> *) m->rscr.p,nrecv,NULL,1,NULL,NULL,m->rpay.p,NULL,ent,nk,d_cnt,&hc,&hm,&gmax);
+  rc = super_count_stage(c,g,(Key<1> *) m->rrec.p,(Key<1> *) m->rscr.p,nrecv,NULL,1,NULL,NULL,m->rpay.p,(void *) m->ev_pay,ent,nk,d_cnt,&hc,&hm,&gmax);
   if (rc) return rc;
   const u64 nent = want_entries ? hc.nent : 0;
   bank_times(c);
@@ -2279,7 +2288,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
       m->sent_entries = (int64_t) (p2.nsend - p2.scnt[me]);
       if (m->erecv.ensure((size_t) (p2.nrecv + 8) * EB) || c->bufA.ensure((size_t) (p2.nrecv + 8) * EB))
         return set_err(FKGPU_E_NOMEM,"out of device memory (%llu entries in)",p2.nrecv);
-      rc = mg_alltoall(c,m->epart.p,p2.soff,p2.scnt,m->erecv.p,p2.roff,p2.rcnt,EB);
+      rc = mg_alltoall(c,m->epart.p,p2.soff,p2.scnt,m->erecv.p,p2.roff,p2.rcnt,EB,c->st);
       if (rc) return rc;
       bank_times(c);
       fkgpu_result tr; memset(&tr,0,sizeof(tr));

@@ -82,6 +82,7 @@ static void splitters(const u64 *h, int n, int world, std::vector<int> &beg)
 struct MultiState
   { fkmg::Comm comm = nullptr;
     int nranks = 1, rank = 0;
+    cudaEvent_t ev_rec = nullptr, ev_pay = nullptr;   /* records exchanged / base strings exchanged */
     DevBuf small;                      /* device scratch for the little collectives */
     DevBuf payload, rrec, rscr, rpay, epart, erecv;
     std::vector<int64_t> table_sizes;  /* result: table records of every rank, in rank (= key) order */
