@@ -1958,6 +1958,8 @@ extern "C" int fkgpu_super_count(fkgpu_ctx *c, uint64_t *d_records, int64_t nrec
   const u32 *seqr[SUP_MAXRANKS]; u64 pb[SUP_MAXRANKS];
   for (int r = 0; r < SUP_MAXRANKS; r++)
     { seqr[r] = d_payload ? NULL : seq_of_rank[r < nranks ? r : 0]; pb[r] = d_payload ? 0 : (u64) pos_base[r < nranks ? r : 0]; }
+  if (d_payload != NULL && ((unsigned long long) nrecords * 8ull) >> g.pbits)
+    return set_err(FKGPU_E_ARG,"fkgpu_super_count: %lld payload strings exceed the position field of a record",(long long) nrecords);
   if (d_payload != NULL && nrecords > 0)
     { k_reindex<<<(unsigned) ((nrecords + 255) / 256),256,0,c->st>>>((u64 *) d_records,(long long) nrecords,g.pbits); KCHECK(); }
   SuperCounters hc; Misc hm; long long gmax = 0;
@@ -2060,7 +2062,7 @@ extern "C" int fkgpu_comm_id(uint8_t *id)
 }
 
 extern "C" int fkgpu_comm_init(fkgpu_ctx *c, int nranks, int rank, const uint8_t *id)
-{ if (c == NULL || id == NULL || nranks < 1 || rank < 0 || rank >= nranks) return set_err(FKGPU_E_ARG,"fkgpu_comm_init: bad argument");
+{ if (c == NULL || id == NULL || nranks < 1 || nranks > 2*SUP_MAXRANKS || rank < 0 || rank >= nranks) return set_err(FKGPU_E_ARG,"fkgpu_comm_init: bad argument (at most %d ranks)",2*SUP_MAXRANKS);
   fkmg::Api *na = fkmg::api();
   if (na == NULL) return set_err(FKGPU_E_UNSUPPORTED,"fkgpu_comm_init: libnccl.so.2 could not be loaded (set FKGPU_NCCL_LIB)");
   CU(cudaSetDevice(c->cfg.device));
@@ -2216,26 +2218,61 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   if (rc) return rc;
   m->sent_records = (int64_t) (pl.nsend - pl.scnt[me]);
 
-  /* ---- the base string of every record (32 bytes, left aligned) travels beside it */
-  if (m->payload.ensure((size_t) (S + 8) * 32) || m->rrec.ensure((size_t) (pl.nrecv + 8) * 8) || m->rscr.ensure((size_t) (pl.nrecv + 8) * 8)
-      || m->rpay.ensure((size_t) (pl.nrecv + 8) * 32))
-    return set_err(FKGPU_E_NOMEM,"out of device memory (exchange buffers: %lld records out, %llu in)",S,pl.nrecv);
-  /* the records go first, on the compute stream; their base strings follow on the copy stream, so that the 4x larger payload
-     crosses NVLink while this rank already partitions the records it received (the counting kernel waits for ev_pay)      */
+  /* ---- the base string of every record travels beside it, compact: ceil((l + k - 1) / 16) words, back to back.
+          Words per record -> exclusive scan -> strings + the records to send (position = word offset inside the slice)     */
+  if (c->scnt.ensure((size_t) (S + 2) * 4) || c->poff.ensure((size_t) (S + 2) * 8))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (payload offsets)");
+  Misc *d_misc0 = (Misc *) c->misc.p;
+  u64 wtotal = 0;
+  std::vector<u64> wcut(W + 1,0);
   stage_begin(c,FKGPU_ST_SCATTER);
-  rc = mg_alltoall(c,SB,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8,c->st);
+  if (S > 0)
+    { k_payload_words<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,g.k,(u32 *) c->scnt.p); KCHECK(); }
+  rc = run_large_scan<2>(c,(const u32 *) c->scnt.p,S,(u64 *) c->poff.p,&d_misc0->total_pass);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(&wtotal,&d_misc0->total_pass,8,cudaMemcpyDeviceToHost,c->st));
+  for (int r = 0; r < W; r++)
+    if (pl.soff[r] < (u64) S) CU(cudaMemcpyAsync(&wcut[r],(const u64 *) c->poff.p + pl.soff[r],8,cudaMemcpyDeviceToHost,c->st));
+  CU(cudaStreamSynchronize(c->st));
+  for (int r = 0; r < W; r++) if (pl.soff[r] >= (u64) S) wcut[r] = wtotal;
+  wcut[W] = wtotal;
+  /* what crosses, in words: the slices are contiguous and in rank order, so slice r = words [wcut[r], wcut[r+1]);
+     an all-gather of the counts plans the receive side                                                                  */
+  MgPlan pw;
+  pw.soff.resize(W); pw.scnt.resize(W); pw.roff.resize(W); pw.rcnt.resize(W);
+  for (int r = 0; r < W; r++) { pw.soff[r] = wcut[r]; pw.scnt[r] = wcut[r+1] - wcut[r]; }
+  rc = mg_gather_u64(c,pw.scnt.data(),W,all);
+  if (rc) return rc;
+  pw.nrecv = 0;
+  for (int r = 0; r < W; r++) { pw.rcnt[r] = all[(size_t) r * W + me]; pw.roff[r] = pw.nrecv; pw.nrecv += pw.rcnt[r]; }
+  if (m->payload.ensure((size_t) (wtotal + 16) * 4) || m->rrec.ensure((size_t) (pl.nrecv + 8) * 8) || m->rscr.ensure((size_t) (pl.nrecv + 8) * 8)
+      || m->rpay.ensure((size_t) (pw.nrecv + 16) * 4))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (exchange buffers: %lld records out, %llu in)",S,pl.nrecv);
+  /* SA is free again (the scan's output went through the partition into SB): it takes the records to send */
+  SliceTable sst; memset(&sst,0,sizeof(sst));
+  sst.n = W;
+  for (int r = 0; r < W; r++) sst.start[r] = pl.soff[r];      /* empty slices share their start with the next one: the last start <= i wins */
+  if (S > 0)
+    { k_materialise_compact<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(const u64 *) c->poff.p,
+                                                                        sst,(u64 *) SA,(u32 *) m->payload.p); KCHECK();
+    }
+  /* the records go first, on the compute stream; their base strings follow on the copy stream, so that the larger payload
+     crosses NVLink while this rank already partitions the records it received (the counting kernel waits for ev_pay)      */
+  rc = mg_alltoall(c,SA,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8,c->st);
   if (rc) return rc;
   stage_end(c,FKGPU_ST_SCATTER);
   CU(cudaEventRecord(m->ev_rec,c->st));
   CU(cudaStreamWaitEvent(c->cst,m->ev_rec,0));
-  if (S > 0)
-    { k_materialise<<<(unsigned) ((S + 255) / 256),256,0,c->cst>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(uint4 *) m->payload.p); KCHECK(); }
-  rc = mg_alltoall(c,m->payload.p,pl.soff,pl.scnt,m->rpay.p,pl.roff,pl.rcnt,32,c->cst);
+  rc = mg_alltoall(c,m->payload.p,pw.soff,pw.scnt,m->rpay.p,pw.roff,pw.rcnt,4,c->cst);
   if (rc) return rc;
   CU(cudaEventRecord(m->ev_pay,c->cst));
   const long long nrecv = (long long) pl.nrecv;
   if (nrecv > 0)
-    { k_reindex<<<(unsigned) ((nrecv + 255) / 256),256,0,c->st>>>((u64 *) m->rrec.p,nrecv,g.pbits); KCHECK(); }
+    { SliceTable rst; memset(&rst,0,sizeof(rst));
+      rst.n = W;
+      for (int r = 0; r < W; r++) { rst.start[r] = pl.roff[r]; rst.add[r] = pw.roff[r]; }
+      k_rebase_slices<<<(unsigned) ((nrecv + 255) / 256),256,0,c->st>>>((u64 *) m->rrec.p,nrecv,rst); KCHECK();
+    }
 
   /* ---- count the owned buckets; the entries are bounded by the k-mers the received records cover */
   u64 nk = 0;

@@ -43,8 +43,11 @@ template<bool PAY>
 __device__ __forceinline__ void load_supermer(const BucketParams &p, u64 sm, u64 pmask, u32 l, bool orient, u32 *d, u32 *row)
 { u64 ps = sm & pmask;
   if (PAY)
-    { const uint4 a = __ldg(p.payload + 2*ps), b = __ldg(p.payload + 2*ps + 1);
-      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    { /* exchanged base strings: left aligned, ps = word offset, only the words the string occupies are there */
+      const u32 *pw = (const u32 *) p.payload + ps;
+      const int nwo = (int) ((l + (u32) p.k - 1u + 15u) >> 4);
+#pragma unroll
+      for (int t = 0; t < 8; t++) d[t] = (t < nwo) ? __ldg(pw + t) : 0u;
     }
   else
     { const u32 *sq = p.seq;
@@ -358,7 +361,11 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
     };
   auto prefetch_bases = [&](u64 sm)
     { const u64 ps = sm & pmask;
-      if (PAY) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.payload + 2*ps));
+      if (PAY)
+        { const u32 *pw = (const u32 *) p.payload + ps;
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(pw));
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(pw + 7));
+        }
       else if (p.nranks == 1)
         { const u32 *gp = p.seq + (ps >> 4);
           asm volatile("prefetch.global.L2 [%0];" :: "l"(gp));

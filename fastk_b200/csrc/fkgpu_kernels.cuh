@@ -1351,7 +1351,8 @@ struct BucketParams
     int        nranks;                                   /* 1: every record points into seq                                 */
     int        pbits;                                    /* width of the position field of a record                         */
     const uint4 *payload;                                /* PAY instantiation: position field = index of the super-mer's 32-byte left-aligned
-                                                            base string in this array (multi-GPU: exchanged with the records)   */
+                                                            base string in this array (multi-GPU: exchanged with the records); the
+                                                            position field is a WORD offset into it                               */
     const u64 *starts; const u64 *ends; long long nitems;
     int        k;
     u64       *g_hist; u64 *g_maxinst; u64 *g_ndistinct;
@@ -1444,10 +1445,60 @@ __global__ void __launch_bounds__(256) k_materialise(const u64 *recs, long long 
   payload[2*i+1] = make_uint4(d[4],d[5],d[6],d[7]);
 }
 
-/*  after the exchange the position field of received record i becomes i, the index of its payload */
+/*  after the exchange the position field of received record i becomes the WORD offset of its base string in the payload:
+    8*i for the fixed 32-byte strings of k_materialise                                                                     */
 __global__ void __launch_bounds__(256) k_reindex(u64 *recs, long long n, int pbits)
 { const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) recs[i] = (recs[i] & ~((1ull << pbits) - 1ull)) | (u64) i;
+  if (i < n) recs[i] = (recs[i] & ~((1ull << pbits) - 1ull)) | (u64) (8*i);
+}
+
+/*  Compact payload of the in-library exchange: a super-mer's base string travels as ceil((l + k - 1) / 16) words (15 bytes
+    on average at k = 40 instead of 32).  k_payload_words: words of every record; after an exclusive scan (woff),
+    k_materialise_compact writes the strings back to back and the record to send, whose position field becomes the word
+    offset of its string INSIDE ITS DESTINATION'S SLICE (slice r = records [sstart[r], sstart[r+1]) ); the receiver adds
+    the word offset at which the slice of every source landed (k_rebase_slices).                                          */
+__global__ void __launch_bounds__(256) k_payload_words(const u64 *recs, long long n, int pbits, int k, u32 *nw)
+{ const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) nw[i] = (sm_len(recs[i],pbits) + (u32) k - 1u + 15u) >> 4;
+}
+
+struct SliceTable { u64 start[SUP_MAXRANKS*2 + 1]; u64 add[SUP_MAXRANKS*2 + 1]; int n; };
+
+__global__ void __launch_bounds__(256) k_materialise_compact(const u64 *recs, long long n, int pbits, u64 pos_offset, int k, const u32 *seq,
+                                                             const u64 *woff, SliceTable st, u64 *send, u32 *payload)
+{ const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 sm = recs[i];
+  const u32 l = sm_len(sm,pbits);
+  const u64 pmask = (1ull << pbits) - 1ull;
+  const u64 ps = (sm & pmask) - pos_offset;
+  const u32 *g = seq + (ps >> 4);
+  const int sh = 2*(int) (ps & 15ull);
+  const int nwr = (int) ((2*(l + k - 1) + sh + 31) >> 5);       /* packed words the string touches in the reads */
+  const int nwo = (int) ((l + (u32) k - 1u + 15u) >> 4);         /* words it occupies left aligned               */
+  u32 x[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) x[t] = (t < nwr) ? __ldg(g + t) : 0u;
+  const u64 w0 = woff[i];
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+    if (t < nwo) payload[w0 + t] = __funnelshift_l(x[t+1],x[t],sh);
+  int r = 0;
+#pragma unroll 1
+  for (int q = 1; q < st.n; q++)
+    if ((u64) i >= st.start[q]) r = q;
+  send[i] = (sm & ~pmask) | (w0 - woff[st.start[r]]);
+}
+
+/*  received records [start[r], start[r+1]) came from source r, whose strings landed at word offset add[r]  */
+__global__ void __launch_bounds__(256) k_rebase_slices(u64 *recs, long long n, SliceTable st)
+{ const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = 0;
+#pragma unroll 1
+  for (int q = 1; q < st.n; q++)
+    if ((u64) i >= st.start[q]) r = q;
+  recs[i] += st.add[r];
 }
 
 /* k-mers covered by the records of every level-1 bucket b = [off[b], off[b+1]): one CTA per bucket (plans the bucket-range rounds) */
