@@ -1023,16 +1023,17 @@ static int entry_words(int kmer) { return kmer > 56 ? 3 : 2; }
 struct SuperCounters { u64 nrec, nkmers, nent, spill_kmers, spill_cursor, sm_seen, sm_expanded; u32 fail, pad, nspill, pad2; };
 
 /*  npos_total = positions over ALL ranks' read streams (multi-GPU: every rank must derive the same bucket-id width) */
-static SuperGeom super_geom(int k, long long npos_total)
+static SuperGeom super_geom(int k, long long npos_total, long long npos_field = -1)
 { SuperGeom g;
+  if (npos_field < 0) npos_field = npos_total;          /* positions the position field of a record must address */
   g.k = k; g.m = std::min(16,k - 8); g.w = k - g.m + 1;
   g.p2 = 1; while (2*g.p2 <= g.w) g.p2 <<= 1;
   const long long sest = std::max<long long>(1,npos_total / 10);        /* expected # of super-mers */
   int bbits = ilog2_ceil((unsigned long long) std::max<long long>(1,sest / 32));
   /* record = [bucket : bbits][# k-mers - 1 : 6][strand : 1][global position : pbits].  The bucket count grows with the input (22 bits up
      to 4 G positions, one more per doubling) so that buckets keep ~40 super-mers however many GPUs feed them.            */
-  g.pbits = std::max(SUP_PBITS_MIN,ilog2_ceil((unsigned long long) npos_total + 1));
-  int bcap = 22 + std::max(0,g.pbits - 32);
+  g.pbits = std::max(SUP_PBITS_MIN,ilog2_ceil((unsigned long long) npos_field + 1));
+  int bcap = 22 + std::max(0,ilog2_ceil((unsigned long long) npos_total + 1) - 32);
   bcap = std::min(bcap,std::min(SUP_BBITS,64 - SUP_LBITS - 1 - g.pbits));
   if (bbits > bcap) bbits = bcap;
   { static int forced = -2;                 /* FKGPU_BBITS: force the bucket-id width (tests exercise the 8-GPU geometry on one GPU) */
@@ -1437,11 +1438,11 @@ static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *
   const bool want_entries = c->cfg.do_table > 0;
   if (c->cfg.do_profile)
     return set_err(FKGPU_E_NOMEM,"out of device memory: -p needs the whole table on the device and a multi-round count does not keep it");
-  /* this path sizes the big buffers itself */
-  c->bufA.release(); c->bufB.release(); c->bufC.release(); c->table.release();
+  /* this path sizes the big buffers itself; what the context already holds of them is part of the budget (a second count of
+     the same input re-uses them as they are: no cudaMalloc / cudaFree in the steady state)                                */
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr,&tot));
-  size_t budget = (size_t) (fr * 0.94);
+  size_t budget = (size_t) ((fr + c->bufA.cap + c->bufB.cap + c->bufC.cap + c->table.cap) * 0.94);
   { const size_t lim = mem_limit_of(c); if (lim && lim < budget) budget = lim; }
   int rc = prepare_small(c,std::max(g.P1,1));
   if (rc) return rc;
@@ -1454,6 +1455,7 @@ static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *
   for (int attempt = 0; ; attempt++)
     { if ((size_t) (scap + 8) * 17 + budget / 8 > budget)
         return set_err(FKGPU_E_NOMEM,"out of device memory: %lld super-mer records do not fit the %zu MB budget",scap,budget >> 20);
+      if (c->bufA.cap > (size_t) (scap + 8) * 40) c->bufA.release();          /* left over from a one-round count: far too large */
       if (c->bufA.ensure((size_t) (scap + 8) * 16) || c->segs.ensure(sizeof(SuperCounters)))
         return set_err(FKGPU_E_NOMEM,"out of device memory (super-mer records)");
       CU(cudaMemsetAsync(c->segs.p,0,sizeof(SuperCounters),c->st));
@@ -1493,6 +1495,9 @@ static int count_packed_super_rounds(fkgpu_ctx *c, const u32 *d_seq, const u32 *
   if (want_entries)
     { /* small stuff (bucket offsets, group lists, per-item counters) rides in the slack; 4 more bytes per entry for its count */
       const size_t used = c->bufA.cap + std::min((size_t) 256 << 20,budget / 8);
+      { const size_t want = (size_t) ((budget > used ? budget - used : 0) / (2*EB + (size_t) tw + 4)) * EB;
+        if (c->bufB.cap > want + want/2 + ((size_t) 64 << 20)) { c->bufB.release(); c->bufC.release(); c->table.release(); }   /* sized for another mode */
+      }
       if (budget <= used) return set_err(FKGPU_E_NOMEM,"out of device memory: nothing left for the entry buffers (budget %zu MB)",budget >> 20);
       ecap = (long long) ((budget - used) / (2*EB + (size_t) tw + 4));
       if (ecap > (long long) nkmers) ecap = (long long) nkmers;
@@ -2168,8 +2173,13 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   std::vector<u64> pbase(W + 1,0);
   for (int r = 0; r < W; r++) pbase[r+1] = pbase[r] + ((all[r] + 63) / 64) * 64;
   const long long total = (long long) pbase[W];
-  const SuperGeom g = super_geom(c->cfg.kmer,total);
-  if (g.pbits > 64 - SUP_LBITS - 2) return set_err(FKGPU_E_ARG,"multi-GPU count: %lld positions do not fit a super-mer record",total);
+  /* the base strings are gathered by the SENDER, so a record only has to address its own rank's stream: the position field
+     stays at the width of the longest local stream and the bits saved go to the bucket id (more, smaller buckets as the
+     job grows: dedup and the on-chip tables see the same ~40 super-mers per bucket at 8 GPUs as at 1)                  */
+  long long longest = 0;
+  for (int r = 0; r < W; r++) longest = std::max<long long>(longest,(long long) (pbase[r+1] - pbase[r]));
+  const SuperGeom g = super_geom(c->cfg.kmer,total,longest);
+  if (g.pbits > 64 - SUP_LBITS - 2) return set_err(FKGPU_E_ARG,"multi-GPU count: %lld positions do not fit a super-mer record",longest);
 
   /* ---- scan own reads, level-1 partition by bucket */
   int rc = prepare_common(c,npos,std::max(g.P1,1),false,2);
@@ -2182,7 +2192,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   Key<1> *SA = (Key<1> *) c->bufA.p;
   Key<1> *SB = (Key<1> *) ((char *) c->bufA.p + ((abytes / 2) & ~(size_t) 15));
   stage_begin(c,FKGPU_ST_SUPERSCAN);
-  rc = super_scan_stage(c,d_seq,d_val,npos,g,pbase[me],(u64 *) SA,scap,d_cnt);
+  rc = super_scan_stage(c,d_seq,d_val,npos,g,0,(u64 *) SA,scap,d_cnt);
   if (rc) return rc;
   stage_end(c,FKGPU_ST_SUPERSCAN);
   SuperCounters hc;
@@ -2253,7 +2263,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   sst.n = W;
   for (int r = 0; r < W; r++) sst.start[r] = pl.soff[r];      /* empty slices share their start with the next one: the last start <= i wins */
   if (S > 0)
-    { k_materialise_compact<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,pbase[me],g.k,d_seq,(const u64 *) c->poff.p,
+    { k_materialise_compact<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,0,g.k,d_seq,(const u64 *) c->poff.p,
                                                                         sst,(u64 *) SA,(u32 *) m->payload.p); KCHECK();
     }
   /* the records go first, on the compute stream; their base strings follow on the copy stream, so that the larger payload

@@ -38,9 +38,9 @@ namespace fk {
 /*  Super-mer record -> its base string (l + k - 1 bases, 2 bits each) left aligned in d[0..8).  With `orient` the bits beyond
  *  the string are cleared and the string is reverse-complemented when the record says its minimizer is canonical on the
  *  reverse strand: copies of one genomic locus, read from either strand, then give the SAME string (and the same length), which
- *  is what lets the bucket kernel count duplicate super-mers once.  `row` (the lane's own 8 words of shared memory) is scratch. */
+ *  is what lets the bucket kernel count duplicate super-mers once.                                                        */
 template<bool PAY>
-__device__ __forceinline__ void load_supermer(const BucketParams &p, u64 sm, u64 pmask, u32 l, bool orient, u32 *d, u32 *row)
+__device__ __forceinline__ void load_supermer(const BucketParams &p, u64 sm, u64 pmask, u32 l, bool orient, u32 *d)
 { u64 ps = sm & pmask;
   if (PAY)
     { /* exchanged base strings: left aligned, ps = word offset, only the words the string occupies are there */
@@ -74,16 +74,20 @@ __device__ __forceinline__ void load_supermer(const BucketParams &p, u64 sm, u64
       for (int t = 0; t < 8; t++)
         d[t] = ((u32) t < wq) ? d[t] : (((u32) t == wq && wb) ? (d[t] & (0xffffffffu << (32u - wb))) : 0u);
       if (sm_strand(sm,p.pbits))
-        { /* reverse complement of the 128-base slot, then drop the 128 - nb pad bases that lead it */
+        { /* reverse complement of the 128-base slot, then drop the 128 - nb pad bases that lead it: a left shift by a
+             run-time number of words (three select stages, all in registers) and bits (funnel shifts)                */
+          u32 z[8];
 #pragma unroll
-          for (int t = 0; t < 8; t++) row[t] = rc32(d[7-t]);
+          for (int t = 0; t < 8; t++) z[t] = rc32(d[7-t]);
           const u32 sh2 = 2u*(128u - nb), ws = sh2 >> 5, bs = sh2 & 31u;
 #pragma unroll
-          for (int t = 0; t < 8; t++)
-            { const u32 a = ((u32) t + ws < 8u) ? row[t + ws] : 0u;
-              const u32 b = ((u32) t + ws + 1u < 8u) ? row[t + ws + 1] : 0u;
-              d[t] = __funnelshift_l(b,a,bs);
-            }
+          for (int t = 0; t < 8; t++) z[t] = (ws & 4u) ? ((t + 4 < 8) ? z[(t + 4) & 7] : 0u) : z[t];
+#pragma unroll
+          for (int t = 0; t < 8; t++) z[t] = (ws & 2u) ? ((t + 2 < 8) ? z[(t + 2) & 7] : 0u) : z[t];
+#pragma unroll
+          for (int t = 0; t < 8; t++) z[t] = (ws & 1u) ? ((t + 1 < 8) ? z[(t + 1) & 7] : 0u) : z[t];
+#pragma unroll
+          for (int t = 0; t < 8; t++) d[t] = __funnelshift_l((t + 1 < 8) ? z[(t + 1) & 7] : 0u,z[t],bs);
         }
     }
 }
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
                   l = sm_len(sm,p.pbits);
                   u32 d[8];
                   u32 *row = rows + lane*BK_ROW;
-                  load_supermer<PAY>(p,sm,pmask,l,false,d,row);
+                  load_supermer<PAY>(p,sm,pmask,l,false,d);
                   ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
                   ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
                 }
@@ -304,31 +308,33 @@ __global__ void __launch_bounds__(BK_TPB,4) k_bucket_count2(BucketParams p, u32 
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /*  k_bucket_count3: WARP-PRIVATE tables, duplicate super-mers counted once.
- *  A warp owns a work group (whole buckets, ~32 super-mers) from load to emit -- no block barrier in the loop.  Per piece of
- *  <= 32 super-mers (one per lane):
- *    load     the lane's super-mer as an ORIENTED, zero-padded base string (load_supermer)
+ *  A warp owns a work group (whole buckets, ~32 super-mers) from load to emit -- no block barrier in the loop.
+ *    load     <= 32 super-mers at a time, one per lane, as ORIENTED zero-padded base strings in registers (load_supermer)
  *    dedupe   at 50x coverage a locus is read ~50 times and its copies sit in the same bucket: the lane hashes its string and
- *             looks for an identical one among the piece's (tiny open-addressing table over the lanes' own rows); a copy only
- *             adds 1 to the weight of the first lane that holds the string and drops out (the reference's Supermer_Sort +
- *             weighted k-mers, MSDsort.c:458-489 + count.c:339-542, without the sort)
- *    expand   only the distinct super-mers are expanded, one k-mer per lane per round (REDUX.OR + popc mapping)
- *    count    each k-mer adds its super-mer's weight to the warp's k-mer table (fingerprinted slots, SoA keys)
+ *             looks it up among the group's REPRESENTATIVES (BW_RP rows of shared memory behind a small open-addressing
+ *             table); a copy only adds 1 to its representative's weight, a new string becomes a representative (the
+ *             reference's Supermer_Sort + weighted k-mers, MSDsort.c:458-489 + count.c:339-542, without the sort)
+ *    flush    when the rows are full, and at the end of the group: only the representatives are expanded, one k-mer per lane
+ *             per round (REDUX.OR + popc mapping), and each k-mer adds its representative's weight to the warp's k-mer table
+ *             (fingerprinted slots, SoA keys)
+ *  Bounds -> records -> base sectors of the NEXT groups are software-pipelined (loads two groups ahead, L2 prefetch one ahead).
  *  Emit, hash classes on overflow, spill of oversize groups: as in the CTA-wide kernel above.                            */
 
 #define BW_WARPS  4
 #define BW_TPB    (32*BW_WARPS)
 #define BW_KC     256                /* distinct keys a warp's class may hold */
 #define BW_SL     512                /* slots per warp (load <= 0.5)          */
-#define BW_SS     64                 /* slots of the super-mer dedupe table (32 rows) */
-#define BW_WBYTES ((size_t) BW_KC*8*2 + (size_t) BW_KC*4 + (size_t) BW_SL*4 + (size_t) 32*BK_ROW*4 + (size_t) BW_SS*4 + (size_t) 32*4)
+#define BW_RP     32                 /* representative super-mers a warp holds between flushes */
+#define BW_RT     (2*BW_RP)          /* slots of their table                                   */
+#define BW_WBYTES ((size_t) BW_KC*8*2 + (size_t) BW_KC*4 + (size_t) BW_SL*4 + (size_t) BW_RP*BK_ROW*4 + (size_t) BW_RT*4 + (size_t) BW_RP*4 + (size_t) 32*4)
 #define BW_SMEM   (BW_WBYTES*BW_WARPS)
 
 template<int KW, bool PAY, bool WIDE>
 __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 klast)
-{ static_assert(KW >= 2 && KW <= 4 && (!WIDE || KW == 4) && BW_KC < 65535 && BW_SL >= 2*BW_KC,"bucket kernel geometry");
+{ static_assert(KW >= 2 && KW <= 4 && (!WIDE || KW == 4) && BW_KC < 65535 && BW_SL >= 2*BW_KC && BW_RP % 32 == 0 && BW_RP <= 128,"bucket kernel geometry");
   typedef Key<WIDE ? 3 : 2> Entry;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ u32 s_hist[SC_SMALLHIST], s_nk[BW_WARPS], s_ov[BW_WARPS];
+  __shared__ u32 s_hist[SC_SMALLHIST], s_nk[BW_WARPS], s_ov[BW_WARPS], s_nrep[BW_WARPS];
 
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wb = s_raw + (size_t) warp * BW_WBYTES;
@@ -336,9 +342,10 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
   u64 *k1   = k0 + BW_KC;                               /* [BW_KC] */
   u32 *cnt  = (u32 *) (k1 + BW_KC);                     /* [BW_KC] */
   u32 *slot = cnt + BW_KC;                              /* [BW_SL] */
-  u32 *rows = slot + BW_SL;                             /* [32][BK_ROW] */
-  u32 *ssl  = rows + 32*BK_ROW;                         /* [BW_SS] dedupe table: 0 = empty, else (fp : 17)(l - 1 : 6)(pad : 3)(lane + 1 : 6) */
-  u32 *wt   = ssl + BW_SS;                              /* [32] copies of the string lane i holds */
+  u32 *rows = slot + BW_SL;                             /* [BW_RP][BK_ROW] strings of the representatives */
+  u32 *rt   = rows + BW_RP*BK_ROW;                      /* [BW_RT] their table: 0 = empty, else (fp : 17)(l - 1 : 6)(0)(row + 1 : 8) */
+  u32 *rm   = rt + BW_RT;                               /* [BW_RP] (copies << 8) | l ; 0 = a row that lost its race */
+  u32 *cp   = rm + BW_RP;                               /* [32] holders of one flush batch, compacted */
   const u64 pmask = (1ull << p.pbits) - 1ull;
   Entry *ent = (Entry *) p.ent;
   u32 ndist = 0;                                        /* warp-uniform: distinct keys this warp has seen */
@@ -348,10 +355,6 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
   for (u32 i = lane; i < BW_KC; i += 32) cnt[i] = 0;
   __syncthreads();
 
-  /*  Software pipeline over the warp's groups: the bounds of a group are loaded three groups ahead, its first 64 records two
-      groups ahead, and the packed-read sectors those records point at are prefetched into L2 one group ahead -- the three
-      dependent global accesses (bounds -> record -> bases) otherwise sit on the critical path of every ~40-super-mer group
-      (ncu r2e: 36 % of the stall samples).                                                                              */
   const long long nwarps = (long long) gridDim.x * BW_WARPS;
   auto bounds = [&](long long gg, u64 &a, u64 &b)
     { if (gg < p.nitems) { a = __ldg(p.starts + gg); b = __ldg(p.ends + gg); } else { a = 0; b = 0; } };
@@ -372,6 +375,83 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
           asm volatile("prefetch.global.L2 [%0];" :: "l"(gp + 8));
         }
     };
+  volatile u32 *ovf = &s_ov[warp];
+  u32 spare = 0xffffffffu;                              /* a key index this lane allocated and has not used yet */
+  u32 R = 1, rd = 0;                                    /* current hash class: keys with ((h >> 20) & (R-1)) == rd */
+
+  /* expand the representatives held now (weights final), count their k-mers, empty the rows */
+  auto flush = [&]()
+    { __syncwarp();
+      const u32 nrr = ((volatile u32 *) s_nrep)[warp];
+      const u32 nr  = nrr < (u32) BW_RP ? nrr : (u32) BW_RP;
+      for (u32 b0 = 0; b0 < nr && !*ovf; b0 += 32)
+        { const u32 me_ = (b0 + lane < nr) ? rm[b0 + lane] : 0u;
+          const u32 w = me_ >> 8;
+          const u32 l = w ? (me_ & 0xffu) : 0u;
+          if (R == 1 && l) nex++;
+          u32 incl = l;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            { const u32 y = __shfl_up_sync(0xffffffffu,incl,o);
+              if ((int) lane >= o) incl += y;
+            }
+          const u32 T   = __shfl_sync(0xffffffffu,incl,31);
+          const u32 pre = incl - l;
+          { const u32 hmask = __ballot_sync(0xffffffffu,l != 0u);
+            if (l != 0u) cp[__popc(hmask & ((1u << lane) - 1u))] = (pre << 16) | ((b0 + lane) << 8) | 0u;
+          }
+          __syncwarp();
+          u32 before = 0;
+          for (u32 g0 = 0; g0 < T; g0 += 32)
+            { const u32 rel = pre - g0;
+              const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
+              const u32 ri  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;     /* my super-mer: the ri-th holder of the batch */
+              before += __popc(m);
+              if (g0 + lane < T)
+                { const u32 hc_ = cp[ri & 31u];
+                  const u32 si = (hc_ >> 8) & 0xffu;                                   /* its row */
+                  const u32 wsi = rm[si] >> 8;
+                  const u32 j = g0 + lane - (hc_ >> 16);
+                  u32 F[KW], G[KW];
+                  supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
+                  const Key<2> key = strands_canon<KW>(F,G);
+                  const u32 h = bucket_hash<KW>(key);
+                  if (((h >> 20) & (R-1)) == rd)
+                    { const u32 fp = h & 0xffff0000u;
+                      u32 x = h & (BW_SL-1);
+                      for (u32 step = 0; ; step++)
+                        { if (step >= BK_PROBE) { *ovf = 1; break; }
+                          u32 v = ((volatile u32 *) slot)[x];
+                          if (v == 0u)
+                            { if (spare == 0xffffffffu)
+                                { spare = atomicAdd(&s_nk[warp],1u);
+                                  if (spare >= BW_KC) { *ovf = 1; spare = 0xffffffffu; break; }
+                                }
+                              k0[spare] = key.w[0];
+                              if (KW > 2) k1[spare] = key.w[1];
+                              __threadfence_block();
+                              const u32 old = atomicCAS(&slot[x],0u,fp | (spare + 1u));
+                              if (old == 0u) { atomicAdd(&cnt[spare],wsi); spare = 0xffffffffu; break; }
+                              v = old;
+                            }
+                          if ((v & 0xffff0000u) == fp)
+                            { const u32 ki = (v & 0xffffu) - 1u;
+                              bool eq = (((volatile u64 *) k0)[ki] == key.w[0]);
+                              if (KW > 2) eq = eq && (((volatile u64 *) k1)[ki] == key.w[1]);
+                              if (eq) { atomicAdd(&cnt[ki],wsi); break; }
+                            }
+                          x = (x+1) & (BW_SL-1);
+                        }
+                    }
+                }
+            }
+          __syncwarp();
+        }
+      for (u32 i = lane; i < (u32) BW_RT; i += 32) rt[i] = 0;
+      if (lane == 0) s_nrep[warp] = 0;
+      __syncwarp();
+    };
+
   long long g = (long long) blockIdx.x * BW_WARPS + warp;
   u64 r0 = 0, r1 = 0, r0n, r1n, r0nn, r1nn, sa = 0, sb = 0, san, sbn;
   u64 sann_ = 0, sbnn_ = 0, r0x_ = 0, r1x_ = 0;
@@ -384,121 +464,68 @@ __global__ void __launch_bounds__(BW_TPB,6) k_bucket_count3(BucketParams p, u32 
       bounds(g + 3*nwarps,r0x_,r1x_);
       if (r1 <= r0) continue;
       if (r1 - r0 > (u64) p.big) { spill_group(p,g,r0,r1,lane); continue; }
-      u32 R = 1, rd = 0;
+      R = 1; rd = 0;
       for (;;)
         { { uint4 *s4 = (uint4 *) slot;
             const uint4 z = make_uint4(0,0,0,0);
 #pragma unroll
             for (u32 i = 0; i < BW_SL/4/32; i++) s4[lane + i*32] = z;
           }
-          if (lane == 0) { s_nk[warp] = 0; s_ov[warp] = 0; }
+          for (u32 i = lane; i < (u32) BW_RT; i += 32) rt[i] = 0;
+          if (lane == 0) { s_nk[warp] = 0; s_ov[warp] = 0; s_nrep[warp] = 0; }
+          spare = 0xffffffffu;
           __syncwarp();
-          volatile u32 *ovf = &s_ov[warp];
 
-          u32 spare = 0xffffffffu;
           for (u64 q0 = r0; q0 < r1; q0 += 32)
             { if (*ovf) break;
               const u32 ns = (u32) ((r1 - q0 < 32ull) ? (r1 - q0) : 32ull);
               u32 l = 0, hs = 0;
-              u32 *row = rows + lane*BK_ROW;
-              ssl[lane] = 0; ssl[lane + 32] = 0;
-              wt[lane] = 1;
-              if (lane < ns)
+              u32 d[8];
+              bool pending = lane < ns;
+              if (pending)
                 { const u64 sm = (q0 == r0) ? sa : ((q0 == r0 + 32) ? sb : p.recs[q0 + lane]);
                   l = sm_len(sm,p.pbits);
-                  u32 d[8];
-                  load_supermer<PAY>(p,sm,pmask,l,true,d,row);
-                  ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
-                  ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
+                  load_supermer<PAY>(p,sm,pmask,l,true,d);
                   hs = d[0] * 0x9E3779B1u + d[1] * 0x85EBCA77u + d[2] * 0xC2B2AE3Du + d[3] * 0x27D4EB2Fu
                      + d[4] * 0x165667B1u + d[5] * 0xD3A2646Du + d[6] * 0xFD7046C5u + d[7] * 0xB55A4F09u + l * 0x2545F491u;
                   hs ^= hs >> 15; hs *= 0x2C1B3C6Du; hs ^= hs >> 13;
+                  if (R == 1) nsm++;
                 }
-              __threadfence_block();
-              __syncwarp();
-              /* ---- dedupe: a copy of a string another lane holds only adds to that lane's weight ---- */
-              if (lane < ns)
-                { const u32 tag = (hs & 0xffff8000u) | ((l - 1u) << 9);             /* fingerprint and length: both must agree */
-                  u32 x = hs & (BW_SS-1);
-                  for (;;)
-                    { u32 v = ((volatile u32 *) ssl)[x];
-                      if (v == 0u)
-                        { const u32 old = atomicCAS(&ssl[x],0u,tag | (lane + 1u));
-                          if (old == 0u) break;                                      /* first holder of this string */
-                          v = old;
-                        }
-                      if ((v & 0xfffffe00u) == tag)
-                        { const u32 o = (v & 63u) - 1u;
-                          const uint4 a0 = ((const uint4 *) (rows + o*BK_ROW))[0], a1 = ((const uint4 *) (rows + o*BK_ROW))[1];      /* rows are final since the barrier above */
-                          const uint4 b0 = ((const uint4 *) row)[0], b1 = ((const uint4 *) row)[1];
-                          if (((a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w)) == 0u)
-                            { atomicAdd(&wt[o],1u); l = 0; break; }
-                        }
-                      x = (x+1) & (BW_SS-1);
-                    }
-                  if (R == 1) { nsm++; nex += (l != 0u) ? 1u : 0u; }
-                }
-              __syncwarp();
-              const u32 w = wt[lane];
-              u32 incl = l;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1)
-                { const u32 y = __shfl_up_sync(0xffffffffu,incl,o);
-                  if ((int) lane >= o) incl += y;
-                }
-              const u32 T   = __shfl_sync(0xffffffffu,incl,31);
-              const u32 pre = incl - l;
-              /* the lanes that still hold a super-mer, compacted into the (now dead) dedupe table: the i-th holder's
-                 (first instance : 12+)(weight : 6)(lane : 6)                                                          */
-              { const u32 hmask = __ballot_sync(0xffffffffu,l != 0u);
-                if (l != 0u) ssl[__popc(hmask & ((1u << lane) - 1u))] = (pre << 12) | (w << 6) | lane;
-              }
-              __syncwarp();
-              u32 before = 0;
-              for (u32 g0 = 0; g0 < T; g0 += 32)
-                { const u32 rel = pre - g0;
-                  const u32 m   = __reduce_or_sync(0xffffffffu,(l != 0u && rel < 32u) ? (1u << rel) : 0u);
-                  const u32 ri  = before + __popc(m & (0xffffffffu >> (31u - lane))) - 1u;     /* my super-mer: the ri-th holder */
-                  before += __popc(m);
-                  if (g0 + lane < T)
-                    { const u32 hc_ = ssl[ri & 31u];
-                      const u32 si = hc_ & 63u, wsi = (hc_ >> 6) & 63u;
-                      const u32 j = g0 + lane - (hc_ >> 12);
-                      u32 F[KW], G[KW];
-                      supermer_strands<KW>(rows + si*BK_ROW,(int) j,p.k,klast,F,G);
-                      const Key<2> key = strands_canon<KW>(F,G);
-                      const u32 h = bucket_hash<KW>(key);
-                      if (((h >> 20) & (R-1)) == rd)
-                        { const u32 fp = h & 0xffff0000u;
-                          u32 x = h & (BW_SL-1);
-                          for (u32 step = 0; ; step++)
-                            { if (step >= BK_PROBE) { *ovf = 1; break; }
-                              u32 v = ((volatile u32 *) slot)[x];
-                              if (v == 0u)
-                                { if (spare == 0xffffffffu)
-                                    { spare = atomicAdd(&s_nk[warp],1u);
-                                      if (spare >= BW_KC) { *ovf = 1; spare = 0xffffffffu; break; }
-                                    }
-                                  k0[spare] = key.w[0];
-                                  if (KW > 2) k1[spare] = key.w[1];
-                                  __threadfence_block();
-                                  const u32 old = atomicCAS(&slot[x],0u,fp | (spare + 1u));
-                                  if (old == 0u) { atomicAdd(&cnt[spare],wsi); spare = 0xffffffffu; break; }
-                                  v = old;
-                                }
-                              if ((v & 0xffff0000u) == fp)
-                                { const u32 ki = (v & 0xffffu) - 1u;
-                                  bool eq = (((volatile u64 *) k0)[ki] == key.w[0]);
-                                  if (KW > 2) eq = eq && (((volatile u64 *) k1)[ki] == key.w[1]);
-                                  if (eq) { atomicAdd(&cnt[ki],wsi); break; }
-                                }
-                              x = (x+1) & (BW_SL-1);
+              /* ---- dedupe against the group's representatives; a string that finds the rows full waits for a flush ---- */
+              for (;;)                                    /* every flush empties the rows, so at least the winners of the next try get in */
+                { if (pending)
+                    { const u32 tag = (hs & 0xffff8000u) | ((l - 1u) << 9);           /* fingerprint and length: both must agree */
+                      u32 x = hs & (BW_RT-1);
+                      for (;;)
+                        { u32 v = ((volatile u32 *) rt)[x];
+                          if (v == 0u)
+                            { const u32 idx = atomicAdd(&s_nrep[warp],1u);
+                              if (idx >= (u32) BW_RP) break;                           /* rows full: stay pending */
+                              uint4 *r4 = (uint4 *) (rows + idx*BK_ROW);
+                              r4[0] = make_uint4(d[0],d[1],d[2],d[3]);
+                              r4[1] = make_uint4(d[4],d[5],d[6],d[7]);
+                              rm[idx] = (1u << 8) | l;
+                              __threadfence_block();
+                              const u32 old = atomicCAS(&rt[x],0u,tag | (idx + 1u));
+                              if (old == 0u) { pending = false; break; }               /* first holder of this string */
+                              rm[idx] = 0;                                             /* lost the race: the row stays unused */
+                              v = old;
                             }
+                          if ((v & 0xfffffe00u) == tag)
+                            { const u32 o = (v & 0xffu) - 1u;
+                              const volatile u32 *rr = rows + o*BK_ROW;
+                              if (((rr[0] ^ d[0]) | (rr[1] ^ d[1]) | (rr[2] ^ d[2]) | (rr[3] ^ d[3]) | (rr[4] ^ d[4]) | (rr[5] ^ d[5]) | (rr[6] ^ d[6]) | (rr[7] ^ d[7])) == 0u)
+                                { atomicAdd(&rm[o],1u << 8); pending = false; break; }
+                            }
+                          x = (x+1) & (BW_RT-1);
                         }
                     }
+                  if (!__any_sync(0xffffffffu,pending)) break;
+                  flush();
+                  if (*ovf) break;
                 }
-              __syncwarp();
             }
+          if (!*ovf) flush();
           __syncwarp();
           const u32 nkr = ((volatile u32 *) s_nk)[warp];
           const u32 nk  = (nkr < (u32) BW_KC) ? nkr : (u32) BW_KC;
@@ -592,7 +619,7 @@ __global__ void __launch_bounds__(256) k_spill_expand(BucketParams p, u32 klast,
           l = sm_len(sm,p.pbits);
           u32 d[8];
           u32 *row = rows + lane*BK_ROW;
-          load_supermer<PAY>(p,sm,pmask,l,false,d,row);
+          load_supermer<PAY>(p,sm,pmask,l,false,d);
           ((uint4 *) row)[0] = make_uint4(d[0],d[1],d[2],d[3]);
           ((uint4 *) row)[1] = make_uint4(d[4],d[5],d[6],d[7]);
         }

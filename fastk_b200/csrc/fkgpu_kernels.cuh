@@ -600,9 +600,13 @@ __global__ void __launch_bounds__(REF_TPB) k_refine(const Key<NW> *__restrict__ 
  *  the input is records rather than reads: the multi-GPU path after the exchange).                   */
 
 #define TP_TPB 256
-#define TP_RPT(NW) ((NW) == 3 ? 8 : 16)
+#define TP_RPT(NW) ((NW) == 3 ? 24 : 32)
 #define TP_TILE(NW) (TP_TPB*TP_RPT(NW))
 
+/*  One CTA per tile of TP_TILE records.  The tile is read twice -- once to rank every record inside its bucket (smem atomics;
+ *  only the 16-bit ranks stay in registers), once more (an L2 hit) to scatter -- so that a tile can be 8192 records without
+ *  holding them in registers: the global atomics that reserve a run per (tile, non-empty bucket) were what this kernel
+ *  waited for (ncu r2: long_scoreboard 22 of 47 stalled warps), and their number per record halves with the tile size.   */
 template<int NW, bool SCATTER>
 __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__ src, Key<NW> *__restrict__ dst,
                                                      u64 n, int nbits, u64 *hist)
@@ -614,20 +618,15 @@ __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__
   __syncthreads();
   constexpr int RPT = TP_RPT(NW);
   const u64 t0 = (u64) blockIdx.x * TP_TILE(NW);
-  Key<NW> r[RPT];
   u32 rk[RPT/2];
 #pragma unroll
   for (int u = 0; u < RPT/2; u++) rk[u] = 0;
 #pragma unroll
   for (int u = 0; u < RPT; u++)
     { u64 i = t0 + u*TP_TPB + threadIdx.x;
-      if (i < n) r[u] = src[i];
-    }
-#pragma unroll
-  for (int u = 0; u < RPT; u++)
-    { u64 i = t0 + u*TP_TPB + threadIdx.x;
       if (i < n)
-        { u32 rr = atomicAdd(&s_cnt[nbits ? key_digit<NW>(r[u],0,nbits) : 0u],1u);
+        { const Key<NW> r = src[i];
+          u32 rr = atomicAdd(&s_cnt[nbits ? key_digit<NW>(r,0,nbits) : 0u],1u);
           rk[u>>1] |= rr << (16*(u&1));
         }
     }
@@ -643,8 +642,9 @@ __global__ void __launch_bounds__(TP_TPB) k_tilepart(const Key<NW> *__restrict__
   for (int u = 0; u < RPT; u++)
     { u64 i = t0 + u*TP_TPB + threadIdx.x;
       if (i < n)
-        { u32 d = nbits ? key_digit<NW>(r[u],0,nbits) : 0u;
-          dst[s_base[d] + ((rk[u>>1] >> (16*(u&1))) & 0xffffu)] = r[u];
+        { const Key<NW> r = src[i];
+          u32 d = nbits ? key_digit<NW>(r,0,nbits) : 0u;
+          dst[s_base[d] + ((rk[u>>1] >> (16*(u&1))) & 0xffffu)] = r;
         }
     }
 }
@@ -719,7 +719,8 @@ template<int NW>
 __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
 { extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ u64 s_bar;
-  __shared__ u32 s_D, s_pass, s_or[2*NW];
+  __shared__ u32 s_D, s_pass;
+  __shared__ u64 s_mn, s_mx;
   __shared__ u32 s_hist[SC_SMALLHIST];
   __shared__ u32 s_bin[SC_NBIN], s_boff[SC_NBIN+1], s_wtot[SC_TPB/32];
 
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
     { mbar_init(&s_bar,1);
       s_D = 0; s_pass = 0;
     }
-  if (threadIdx.x < 2*NW) s_or[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_mn = ~0ull; s_mx = 0ull; }
   for (u32 i = threadIdx.x; i < SC_SMALLHIST; i += SC_TPB) s_hist[i] = 0;
   __syncthreads();
   if (threadIdx.x == 0)
@@ -786,39 +787,21 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
   __syncthreads();
   rec += shift;
 
+  /* the group's keys span [mn, mx] in their top 64 bits: they are ordered by the top 32 bits of (w0 - mn) scaled to that span,
+     so the bins below fill evenly whatever power-of-two boundary the key range straddles (ties fall back to a full compare) */
+  u64 mn = ~0ull, mx = 0ull;
   if (p.weighted)
     { /* every record is already a distinct key carrying its count: nothing to merge, only to order */
-      const Key<NW> k0 = rec[0];
-      u32 orw[2*NW];
-#pragma unroll
-      for (int m = 0; m < 2*NW; m++) orw[m] = 0;
       for (u32 i = threadIdx.x; i < n; i += SC_TPB)
-        { const Key<NW> key = rec[i];
-#pragma unroll
-          for (int m = 0; m < NW; m++)
-            { u64 x = key.w[m] ^ k0.w[m];
-              orw[2*m] |= (u32) (x >> 32); orw[2*m+1] |= (u32) x;
-            }
-        }
-#pragma unroll
-      for (int m = 0; m < 2*NW; m++)
-        { u32 x = __reduce_or_sync(0xffffffffu,orw[m]);
-          if ((threadIdx.x & 31) == 0 && x) atomicOr(&s_or[m],x);
+        { const u64 w0 = rec[i].w[0];
+          mn = w0 < mn ? w0 : mn; mx = w0 > mx ? w0 : mx;
         }
     }
   else
   /* hash count: table slot = (owner record index << 16) | multiplicity */
-  { const Key<NW> k0 = rec[0];
-    u32 orw[2*NW];
-#pragma unroll
-    for (int m = 0; m < 2*NW; m++) orw[m] = 0;
-    for (u32 i = threadIdx.x; i < n; i += SC_TPB)
+  { for (u32 i = threadIdx.x; i < n; i += SC_TPB)
       { const Key<NW> key = rec[i];
-#pragma unroll
-        for (int m = 0; m < NW; m++)
-          { u64 x = key.w[m] ^ k0.w[m];
-            orw[2*m] |= (u32) (x >> 32); orw[2*m+1] |= (u32) x;
-          }
+        mn = key.w[0] < mn ? key.w[0] : mn; mx = key.w[0] > mx ? key.w[0] : mx;
         u32 h = key_hash<NW>(key) & (H-1);
         for (;;)
           { u32 cur = ((volatile u32 *) table)[h];
@@ -834,31 +817,22 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
             h = (h+1) & (H-1);
           }
       }
-#pragma unroll
-    for (int m = 0; m < 2*NW; m++)
-      { u32 x = __reduce_or_sync(0xffffffffu,orw[m]);
-        if ((threadIdx.x & 31) == 0 && x) atomicOr(&s_or[m],x);
-      }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    { const u64 a = __shfl_xor_sync(0xffffffffu,mn,o), b = __shfl_xor_sync(0xffffffffu,mx,o);
+      mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_mn,mn); atomicMax(&s_mx,mx); }
   __syncthreads();
-
-  /* common prefix length of the item's keys -> sort on the 32 bits that follow it */
-  int pc = 0;
-  { bool done = false;
-#pragma unroll
-    for (int m = 0; m < 2*NW; m++)
-      if (!done)
-        { u32 x = s_or[m];
-          if (x) { pc += __clz(x); done = true; }
-          else pc += 32;
-        }
-    if (pc > 64*NW - 32) pc = 64*NW - 32;
-  }
+  mn = s_mn; mx = s_mx;
+  const int nsh = (mx > mn) ? __clzll((long long) (mx - mn)) : 0;
+#define SC_NORM32(w0) ((mx > mn) ? ((((w0) - mn) << nsh) >> 32) : 0ull)
 
   /* gather the distinct keys */
   if (p.weighted)
     { for (u32 i = threadIdx.x; i < n; i += SC_TPB)
-        srt[i] = ((key_bits64<NW>(rec[i],pc) >> 32) << 32) | ((u64) i << 16);
+        srt[i] = (SC_NORM32(rec[i].w[0]) << 32) | ((u64) i << 16);
       if (threadIdx.x == 0) s_D = n;
     }
   else
@@ -866,8 +840,7 @@ __global__ void __launch_bounds__(SC_TPB) k_sortcount(SortCountParams p)
     { u32 v = table[s];
       if (v != SC_EMPTY)
         { u32 ps = atomicAdd(&s_D,1u);
-          u64 pre = key_bits64<NW>(rec[v >> 16],pc) >> 32;
-          srt[ps] = (pre << 32) | v;
+          srt[ps] = (SC_NORM32(rec[v >> 16].w[0]) << 32) | v;
         }
     }
   __syncthreads();
