@@ -710,7 +710,9 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       CU(cudaMemcpyAsync(&hm,d_misc,sizeof(Misc),cudaMemcpyDeviceToHost,c->st));
       CU(cudaStreamSynchronize(c->st));
       const u64 U = hm.total_pass;
-      int B = ilog2_ceil(U + 1) - 2; if (B < 8) B = 8; if (B > 26) B = 26;
+      /* about one key per index slot: a lookup is the slot's two bounds (one sector), ~one key, its count (ncu r2: with 3.5 keys
+         per slot k_profile moved 294 B of DRAM per lookup at 75 % of the HBM peak)                                          */
+      int B = ilog2_ceil(U + 1); if (B < 8) B = 8; if (B > 28) B = 28;
       if (c->pkeys.ensure((size_t) (U + 1) * sizeof(K)) || c->pcnts.ensure((size_t) (U + 1) * 2) || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
         return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %llu k-mers)",U);
       CompactParams cp;
@@ -2445,7 +2447,7 @@ template<int NW>
 static int load_profile_table_t(fkgpu_ctx *c, const uint8_t *records, int64_t n)
 { const int tw = c->kbytes + 2;
   const u64 U = (u64) n;
-  int B = ilog2_ceil(U + 1) - 2; if (B < 8) B = 8; if (B > 26) B = 26;
+  int B = ilog2_ceil(U + 1); if (B < 8) B = 8; if (B > 28) B = 28;
   if (c->table.ensure((size_t) U * tw + 64) || c->pkeys.ensure((size_t) (U + 1) * sizeof(Key<NW>)) || c->pcnts.ensure((size_t) (U + 1) * 2)
       || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
     return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %lld k-mers)",(long long) n);
