@@ -93,13 +93,27 @@ def make_rows(a, rank, out=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md).  NVML in-process (one cheap query
+    every 20 ms from a thread); a polling nvidia-smi child was measured to stall the driver by tens of milliseconds per step on
+    some boxes.  Falls back to nvidia-smi when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows = []
-        self.p = None
+        self.rows, self.p, self.h, self.stopf = [], None, None, False
+        self.sm, self.mx, self.reasons = [], None, set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -109,11 +123,35 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+        getr = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stopf:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if getr is not None:
+                    r = getr(self.h)
+                    for nm, attr in names.items():
+                        bit = getattr(nv, attr, None) or getattr(nv, attr.replace("Event", "Throttle"), 0)
+                        if bit and (r & bit):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _pump(self):
         for line in self.p.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.h is not None:
+            self.stopf = True
+            self.t.join(timeout=1)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -137,7 +175,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------------
