@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <time.h>
 #include <vector>
 #include <atomic>
 #include <mutex>
@@ -2165,6 +2166,19 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   const bool want_entries = c->cfg.do_table > 0;
   memset(c->used,0,sizeof(c->used));
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES],c->st);
+  /* FKGPU_MG_TIMING=1: host wall clock of every phase, both streams drained at each mark (diagnostic: it serialises the overlap) */
+  static int tl_on = -1;
+  if (tl_on < 0) { const char *e = getenv("FKGPU_MG_TIMING"); tl_on = (e && atoi(e)) ? 1 : 0; }
+  struct timespec tl_t0; clock_gettime(CLOCK_MONOTONIC,&tl_t0);
+  char tl_buf[1024]; int tl_len = 0;
+  auto mark = [&](const char *name)
+    { if (!tl_on) return;
+      cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->cst);
+      struct timespec t; clock_gettime(CLOCK_MONOTONIC,&t);
+      const double ms = (t.tv_sec - tl_t0.tv_sec) * 1e3 + (t.tv_nsec - tl_t0.tv_nsec) * 1e-6;
+      tl_len += snprintf(tl_buf + tl_len,sizeof(tl_buf) - (size_t) tl_len," %s %.2f",name,ms);
+      tl_t0 = t;
+    };
 
   /* ---- global position space: rank r's stream starts at pos_base[r] (multiples of 64) */
   std::vector<u64> all;
@@ -2207,6 +2221,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     for (int r = 0; r < W; r++)
       if (!all[r]) return set_err(FKGPU_E_UNSUPPORTED,"multi-GPU count: rank %d produced more super-mers than its staging buffer holds",r);
   }
+  mark("scan");
   const long long S = (long long) hc.nrec;
   const int b1 = g.bbits ? g.P1 : 0, n1 = 1 << b1;
   stage_begin(c,FKGPU_ST_SUPERPART);
@@ -2229,6 +2244,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   rc = mg_plan(c,off,beg,pl);
   if (rc) return rc;
   m->sent_records = (int64_t) (pl.nsend - pl.scnt[me]);
+  mark("level1+plan");
 
   /* ---- the base string of every record travels beside it, compact: ceil((l + k - 1) / 16) words, back to back.
           Words per record -> exclusive scan -> strings + the records to send (position = word offset inside the slice)     */
@@ -2268,6 +2284,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     { k_materialise_compact<<<(unsigned) ((S + 255) / 256),256,0,c->st>>>((const u64 *) SB,S,g.pbits,0,g.k,d_seq,(const u64 *) c->poff.p,
                                                                         sst,(u64 *) SA,(u32 *) m->payload.p); KCHECK();
     }
+  mark("payload-build");
   /* the records go first, on the compute stream; their base strings follow on the copy stream, so that the larger payload
      crosses NVLink while this rank already partitions the records it received (the counting kernel waits for ev_pay)      */
   rc = mg_alltoall(c,SA,pl.soff,pl.scnt,m->rrec.p,pl.roff,pl.rcnt,8,c->st);
@@ -2286,6 +2303,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
       k_rebase_slices<<<(unsigned) ((nrecv + 255) / 256),256,0,c->st>>>((u64 *) m->rrec.p,nrecv,rst); KCHECK();
     }
 
+  mark("exchange");
   /* ---- count the owned buckets; the entries are bounded by the k-mers the received records cover */
   u64 nk = 0;
   { u64 *d_nk = (u64 *) m->small.p;
@@ -2310,6 +2328,7 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
   if (rc) return rc;
   const u64 nent = want_entries ? hc.nent : 0;
   bank_times(c);
+  mark("count");
 
   /* ---- table: distinct entries to the owners of their key range, key order there */
   res->ntable = 0; res->table = NULL; res->table_dev = NULL;
@@ -2337,15 +2356,18 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
       m->sent_entries = (int64_t) (p2.nsend - p2.scnt[me]);
       if (m->erecv.ensure((size_t) (p2.nrecv + 8) * EB) || c->bufA.ensure((size_t) (p2.nrecv + 8) * EB))
         return set_err(FKGPU_E_NOMEM,"out of device memory (%llu entries in)",p2.nrecv);
+      mark("entry-partition+plan");
       rc = mg_alltoall(c,m->epart.p,p2.soff,p2.scnt,m->erecv.p,p2.roff,p2.rcnt,EB,c->st);
       if (rc) return rc;
       bank_times(c);
+      mark("entry-exchange");
       fkgpu_result tr; memset(&tr,0,sizeof(tr));
       rc = entries_sort_stage(c,m->erecv.p,c->bufA.p,(long long) p2.nrecv,fetch_table,&tr);
       if (rc) return rc;
       rc = d2h_join(c);
       if (rc) return rc;
       res->ntable = tr.ntable; res->table = tr.table; res->table_dev = tr.table_dev;
+      mark("entry-sort+d2h");
     }
 
   /* ---- global histogram and scalars; table sizes in rank (= key) order */
@@ -2365,6 +2387,8 @@ static int count_packed_multi(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, 
     m->table_sizes.assign(W,0); m->global_ntable = 0;
     for (int r = 0; r < W; r++) { m->table_sizes[r] = (int64_t) all[r]; m->global_ntable += (int64_t) all[r]; }
   }
+  mark("reduce");
+  if (tl_on) fprintf(stderr,"[fkgpu mg rank %d]%s\n",me,tl_buf);
   cudaEventRecord(c->ev[2*FKGPU_NSTAGES+1],c->st);
   CU(cudaStreamSynchronize(c->st));
   collect_times(c,res);
