@@ -29,6 +29,22 @@ import tempfile
 import threading
 import time
 
+_OUT = None
+
+
+def emit(line):
+    """The JSON line goes to the process's ORIGINAL stdout; fd 1 itself is pointed at stderr from the start of main()
+    (NCCL prints its version banner on stdout, the reference FastK its -v chatter), so stdout carries the line only."""
+    print(json.dumps(line), file=_OUT or sys.stdout, flush=True)
+
+
+def claim_stdout():
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -242,7 +258,7 @@ def reference_arm(a, rank):
             "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": used, "kind": kind,
                              "sample": sample_text(a, used, " per step; FASTA parse and file writes included")},
             "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -296,6 +312,7 @@ def invariants(res_hist, max_inst, nkmers, ndistinct):
 
 def main():
     a = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -659,7 +676,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "parity_checked": bool(parity.get("checked") and parity.get("ok") and not problems), "parity": parity,
                 "invariant_violations": problems}
-        print(json.dumps(line), flush=True)
+        emit(line)
     fail = torch.tensor([1 if (rank == 0 and problems) else 0], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(fail, op=dist.ReduceOp.MAX)
