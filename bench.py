@@ -75,6 +75,9 @@ def parse():
     ap.add_argument("--cutoff", type=int, default=None, help="-t<cutoff>")
     ap.add_argument("--ingest-threads", type=int, default=0, help="e2e arm: ingest threads (0 = host cores, at most 16)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-feeder", default="c", choices=["c", "py"],
+                    help="e2e arm: the producer threads that call fkgpu_ingest per DATA_BLOCK: C pthreads (fastk_b200/host/fk_block_feeder.c, "
+                         "what a FastK host has) or Python threads")
     ap.add_argument("--e2e-order", default="rr", choices=["rr", "contig"], help="e2e arm: how DATA_BLOCKs are dealt to the ingest threads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference run: no cpu_baseline and NO parity check")
     ap.add_argument("--seed", type=int, default=1234)
@@ -449,6 +452,19 @@ def main():
                 r0, r1 = blocks[bi]
                 eng.ingest_ptr(base_ptr + r0 * (L + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
 
+        feed = None
+        if a.e2e_feeder == "c":
+            import ctypes as C
+            flib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fastk_b200", "lib", "libfk_feeder.so"))
+            flib.fk_feed_blocks.restype = C.c_int
+            flib.fk_feed_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int]
+            contig = 1 if (a.profile or a.e2e_order == "contig") else 0
+
+            def feed():
+                rc = flib.fk_feed_blocks(eng.h, nthr, base_ptr, nreads, L + 1, rows_per_block, contig)
+                if rc != 0:
+                    raise RuntimeError("fk_feed_blocks: %d: %s" % (rc, eng.lib.fkgpu_last_error().decode()))
+
         e2e_split = {"ingest_ms": 0.0, "finish_ms": 0.0, "profile_ms": 0.0}
 
         def e2e_step():
@@ -456,11 +472,14 @@ def main():
                 dist.barrier(device_ids=[local])
             ta = time.perf_counter()
             eng.reset()
-            th = [threading.Thread(target=worker, args=(t,)) for t in range(nthr)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
+            if feed is not None:
+                feed()
+            else:
+                th = [threading.Thread(target=worker, args=(t,)) for t in range(nthr)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
             tb = time.perf_counter()
             r = eng.finish(fetch_table=want_table, copy_table=False)      # collective when a communicator is attached
             tc = time.perf_counter()
@@ -497,7 +516,7 @@ def main():
                "profile_ms_per_step": e2e_split["profile_ms"] / a.steps,
                "finish_device_ms": r2.ms_total,
                "finish_stage_ms": {kn: round(v, 3) for kn, v in eng.stage_times().items() if v > 0},
-               "path": f"fkgpu_ingest ({nthr} threads, DATA_BLOCKs in pinned host memory; chunks packed + scanned on the device as "
+               "path": f"fkgpu_ingest ({nthr} {'C' if feed is not None else 'Python'} threads, DATA_BLOCKs in pinned host memory; chunks packed + scanned on the device as "
                        f"they land) -> fkgpu_finish(fetch_table={int(want_table)})" + (" -> fkgpu_profiles" if a.profile else "")}
         if not (r2.nkmers == res.nkmers and r2.ndistinct == res.ndistinct and np.array_equal(r2.hist, res.hist)):
             problems.append("e2e and device-resident arms disagree")
