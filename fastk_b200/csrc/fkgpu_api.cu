@@ -134,6 +134,9 @@ struct fkgpu_ctx
 
     /* profile lookup table built by finish when cfg.do_profile */
     DevBuf eprof, qoff, pkeys, pcnts, pidx, praw, pout, psrc, pdst, plen;
+    DevBuf phash, phcnt, vtsrc, vtplo, vtpend;     /* hash form of the lookup table; virtual tiles of an ordered profile run */
+    unsigned long long ph_nbuckets = 0; int ph_wide = 0; bool ph_on = false;
+    cudaEvent_t ev_prof = nullptr;
     long long ptab_n = 0; int ptab_B = 0; long long last_npos = 0;
     bool rel_table = false;     /* -p:<table>: the lookup table was loaded from an existing k-mer table, nothing is counted */
     MultiState *mg = nullptr;   /* multi-GPU: communicator + exchange buffers (fkgpu_comm_init) */
@@ -214,8 +217,10 @@ extern "C" void fkgpu_destroy(fkgpu_ctx *c)
   DevBuf *bufs[] = { &c->ctah,&c->ctao,&c->ascii,&c->seq,&c->val,&c->bufA,&c->bufB,&c->scnt,&c->hist1,&c->off1,&c->cur1,&c->off2,&c->gstart,
                      &c->eall,&c->epass,&c->poff,&c->bsum,&c->ghist,&c->misc,&c->table,&c->segs,&c->child,&c->pcl,
                      &c->sub_s,&c->sub_e,&c->sub_f,&c->sub_ea,&c->sub_ep,&c->sub_off,&c->sub_par,&c->sub_base,
-                     &c->rstart_d,&c->prof_d,&c->eprof,&c->qoff,&c->pkeys,&c->pcnts,&c->pidx,&c->praw,&c->pout,&c->psrc,&c->pdst,&c->plen };
+                     &c->rstart_d,&c->prof_d,&c->eprof,&c->qoff,&c->pkeys,&c->pcnts,&c->pidx,&c->praw,&c->pout,&c->psrc,&c->pdst,&c->plen,
+                     &c->phash,&c->phcnt,&c->vtsrc,&c->vtplo,&c->vtpend };
   for (auto b : bufs) b->release();
+  if (c->ev_prof) cudaEventDestroy(c->ev_prof);
   c->h_table.release(); c->h_misc.release(); c->h_prof.release(); c->h_poff.release();
   if (c->mg) mg_destroy(c);
   for (auto r : c->h_runs) { r->release(); delete r; }
@@ -478,6 +483,39 @@ static int ilog2_ceil(unsigned long long x) { int l = 0; while ((1ull << l) < x)
 #define KCHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
     return set_err(FKGPU_E_CUDA,"kernel launch failed at %s:%d: %s",__FILE__,__LINE__,cudaGetErrorString(e_)); c->launches++; } while (0)
 
+/*  FKGPU_PROF=legacy: profiles by binary search over the sorted keys behind a prefix index, one u16 per position, pieces
+ *  gathered afterwards (round 1 .. r2h).  Default: hash lookups, counts written straight to their place in the output, the
+ *  output copied to the host in slices while later tiles are looked up.                                                */
+static bool prof_legacy()
+{ static int v = -1;
+  if (v < 0) { const char *e = getenv("FKGPU_PROF"); v = (e && strcmp(e,"legacy") == 0) ? 1 : 0; }
+  return v == 1;
+}
+
+/*  (pkeys, pcnts)[0..U) hold the distinct k-mers in key order: build what k_profile looks them up with  */
+template<int NW>
+static int build_profile_lookup(fkgpu_ctx *c, u64 U)
+{ if (prof_legacy())
+    { int B = ilog2_ceil(U + 1); if (B < 8) B = 8; if (B > 28) B = 28;
+      if (c->pidx.ensure(((size_t) (1ull << B) + 2) * 8)) return set_err(FKGPU_E_NOMEM,"out of device memory (profile index of %llu k-mers)",U);
+      k_build_index<NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const Key<NW> *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
+      c->ptab_B = B; c->ph_on = false;
+      return FKGPU_OK;
+    }
+  const u64 nb = (U * 7) / 16 + 64;                  /* 4 slots per bucket: load 4/7 */
+  const int wide = (NW == 2 && c->cfg.kmer > 56) ? 1 : 0;
+  if (c->phash.ensure((size_t) nb * 64) || (wide && c->phcnt.ensure((size_t) nb * 8)))
+    return set_err(FKGPU_E_NOMEM,"out of device memory (profile hash table of %llu k-mers)",U);
+  CU(cudaMemsetAsync(c->phash.p,0,(size_t) nb * 64,c->st));
+  if (wide) CU(cudaMemsetAsync(c->phcnt.p,0,(size_t) nb * 8,c->st));
+  if (U > 0)
+    { k_hash_build<NW><<<(unsigned) ((U + 255) / 256),256,0,c->st>>>((const Key<NW> *) c->pkeys.p,(const uint16_t *) c->pcnts.p,U,(ulonglong2 *) c->phash.p,
+                                                                 (uint16_t *) c->phcnt.p,nb,wide); KCHECK();
+    }
+  c->ph_nbuckets = nb; c->ph_wide = wide; c->ph_on = true;
+  return FKGPU_OK;
+}
+
 static const u32 SC_CAP = 2048;      /* records one k_sortcount CTA can hold           */
 static const u32 SC_T   = 1024;      /* group packing target (fine buckets up to SC_CAP-SC_T+1 never overflow) */
 
@@ -713,8 +751,7 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
       const u64 U = hm.total_pass;
       /* about one key per index slot: a lookup is the slot's two bounds (one sector), ~one key, its count (ncu r2: with 3.5 keys
          per slot k_profile moved 294 B of DRAM per lookup at 75 % of the HBM peak)                                          */
-      int B = ilog2_ceil(U + 1); if (B < 8) B = 8; if (B > 28) B = 28;
-      if (c->pkeys.ensure((size_t) (U + 1) * sizeof(K)) || c->pcnts.ensure((size_t) (U + 1) * 2) || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
+      if (c->pkeys.ensure((size_t) (U + 1) * sizeof(K)) || c->pcnts.ensure((size_t) (U + 1) * 2))
         return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %llu k-mers)",U);
       CompactParams cp;
       cp.stage0 = Y; cp.stage1 = X; cp.stage_cnt = (const u32 *) c->scnt.p;
@@ -733,8 +770,9 @@ static int count_from_level1(fkgpu_ctx *c, long long nub, int P1, int P2, int fe
           k_compact_keys<NW><<<c->sms * 8,256,0,c->st>>>(cq,(PK *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
           CU(cudaStreamSynchronize(c->st));       /* hb is about to go out of scope */
         }
-      k_build_index<(NW == 3) ? 2 : NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const PK *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
-      c->ptab_n = (long long) U; c->ptab_B = B;
+      rc = build_profile_lookup<(NW == 3) ? 2 : NW>(c,U);
+      if (rc) return rc;
+      c->ptab_n = (long long) U;
     }
 
   /* ---- table: scan the per-item pass counts, compact ------------------------------------------- */
@@ -2409,38 +2447,104 @@ extern "C" int fkgpu_count_packed_multi(fkgpu_ctx *c, const uint32_t *d_seq, con
   return count_packed_multi(c,d_seq,d_val,npos,fetch_table,res);
 }
 
-/*  pieces: copy praw[src[i] .. src[i]+len[i]) to the output at dst[i]; offs = profile start of every read (+ total)  */
-struct ProfPieces { std::vector<long long> src, dst; std::vector<int> len; std::vector<int64_t> offs; long long run = 0; };
+/*  pieces: the counts of positions src[i] .. src[i]+len[i]) go to the output at dst[i]; offs = profile start of every read
+ *  (+ total).  segs (optional): the stretches of the read stream in the order of the output -- stretch s covers positions
+ *  [off, off+fill) and holds pieces [p0, p1), sorted by src -- which lets the lookup kernel write the output in place and in
+ *  order (k_profile<.,.,true>).  Without segs the pieces may lie anywhere: one u16 per position, then a gather.           */
+struct ProfSeg { long long off, fill; long long p0, p1; };
+struct ProfPieces { std::vector<long long> src, dst; std::vector<int> len; std::vector<int64_t> offs; long long run = 0; std::vector<ProfSeg> segs; };
+
+#define FKGPU_PROF_SLICES 16      /* an ordered profile run is launched and copied back in this many slices */
+
+template<int NW, bool HASH>
+static int profiles_launch(fkgpu_ctx *c, const ProfileParams &q, bool direct, long long ntiles)
+{ const size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW) * 4;
+  if (ntiles <= 0) return FKGPU_OK;
+  if (direct) k_profile<NW,HASH,true><<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(q);
+  else        k_profile<NW,HASH,false><<<(unsigned) ntiles,SCAN_TPB,sm,c->st>>>(q);
+  KCHECK();
+  return FKGPU_OK;
+}
 
 template<int NW>
 static int profiles_run(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long long npos, const ProfPieces &pp,
                         int64_t *nreads, const int64_t **off, const uint16_t **prof)
 { const size_t np = pp.src.size();
   const long long run = pp.run;
-  if (c->praw.ensure((size_t) (npos + 64) * 2) || c->pout.ensure((size_t) (run + 2) * 2) || c->psrc.ensure(np*8 + 8) || c->pdst.ensure(np*8 + 8)
-      || c->plen.ensure(np*4 + 8))
+  const bool hash = c->ph_on;
+  const bool direct = !prof_legacy() && !pp.segs.empty() && np < (size_t) 0x7fffffff;
+  if (c->pout.ensure((size_t) (run + 2) * 2) || c->psrc.ensure(np*8 + 8) || c->pdst.ensure(np*8 + 8) || c->plen.ensure(np*4 + 8)
+      || (!direct && c->praw.ensure((size_t) (npos + 64) * 2)))
     return set_err(FKGPU_E_NOMEM,"out of device memory (profiles of %lld positions)",npos);
   if (c->h_prof.ensure((size_t) (run + 2) * 2) || c->h_poff.ensure(pp.offs.size() * 8))
     return set_err(FKGPU_E_NOMEM,"out of pinned host memory (profiles)");
+  if (c->ev_prof == nullptr) CU(cudaEventCreateWithFlags(&c->ev_prof,cudaEventDisableTiming));
   stage_begin(c,FKGPU_ST_PROFILE);
   ProfileParams q;
+  memset(&q,0,sizeof(q));
   ScanGeom g = scan_geom(c,npos,0);
   fill_scan_params(c,q.sp,d_seq,d_val,npos,0,g);
   q.keys = c->pkeys.p; q.cnts = (const uint16_t *) c->pcnts.p; q.idx = (const u64 *) c->pidx.p; q.B = c->ptab_B;
+  q.H.slots = (const ulonglong2 *) c->phash.p; q.H.hcnt = (const uint16_t *) c->phcnt.p; q.H.nbuckets = c->ph_nbuckets; q.H.wide = c->ph_wide;
   q.raw = (uint16_t *) c->praw.p;
-  if (g.ntiles > 0)
-    { size_t sm = (size_t) (SCAN_SEQW + SCAN_VALW) * 4;
-      k_profile<NW><<<(unsigned) g.ntiles,SCAN_TPB,sm,c->st>>>(q); KCHECK();
-    }
+  q.psrc = (const long long *) c->psrc.p; q.pdst = (const long long *) c->pdst.p; q.plen = (const int *) c->plen.p;
+  q.out = (uint16_t *) c->pout.p;
   if (np > 0)
     { CU(cudaMemcpyAsync(c->psrc.p,pp.src.data(),np*8,cudaMemcpyHostToDevice,c->st));
       CU(cudaMemcpyAsync(c->pdst.p,pp.dst.data(),np*8,cudaMemcpyHostToDevice,c->st));
       CU(cudaMemcpyAsync(c->plen.p,pp.len.data(),np*4,cudaMemcpyHostToDevice,c->st));
-      k_gather_profile<<<c->sms * 8,256,0,c->st>>>((const uint16_t *) c->praw.p,(const long long *) c->psrc.p,(const long long *) c->pdst.p,
-                                                  (const int *) c->plen.p,(long long) np,(uint16_t *) c->pout.p); KCHECK();
     }
-  stage_end(c,FKGPU_ST_PROFILE);
-  if (run > 0) CU(cudaMemcpyAsync(c->h_prof.p,c->pout.p,(size_t) run * 2,cudaMemcpyDeviceToHost,c->st));
+  int rc = FKGPU_OK;
+  if (!direct)
+    { rc = hash ? profiles_launch<NW,true>(c,q,false,g.ntiles) : profiles_launch<NW,false>(c,q,false,g.ntiles);
+      if (rc) return rc;
+      if (np > 0)
+        { k_gather_profile<<<c->sms * 8,256,0,c->st>>>((const uint16_t *) c->praw.p,q.psrc,q.pdst,q.plen,(long long) np,(uint16_t *) c->pout.p); KCHECK(); }
+      stage_end(c,FKGPU_ST_PROFILE);
+      if (run > 0) CU(cudaMemcpyAsync(c->h_prof.p,c->pout.p,(size_t) run * 2,cudaMemcpyDeviceToHost,c->st));
+    }
+  else
+    { /* virtual tiles: the stretches cut into SCAN_TILE positions, with the pieces that meet each tile and the first output
+         index the tile (or a later one) writes                                                                          */
+      std::vector<long long> vsrc, vdst;
+      std::vector<int> vlo, vend;
+      for (const ProfSeg &sg : pp.segs)
+        { long long a = sg.p0, b = sg.p0;
+          for (long long P = sg.off; P < sg.off + sg.fill; P += SCAN_TILE)
+            { while (a < sg.p1 && pp.src[a] + pp.len[a] <= P) a++;
+              while (b < sg.p1 && pp.src[b] < P + SCAN_TILE) b++;
+              vsrc.push_back(P); vlo.push_back((int) a); vend.push_back((int) b);
+              long long d;
+              if (a < sg.p1) d = (pp.src[a] < P) ? pp.dst[a] + (P - pp.src[a]) : pp.dst[a];
+              else           d = ((size_t) sg.p1 < np) ? pp.dst[sg.p1] : run;
+              vdst.push_back(d);
+            }
+        }
+      const long long nt = (long long) vsrc.size();
+      if (c->vtsrc.ensure((size_t) nt * 8 + 8) || c->vtplo.ensure((size_t) nt * 4 + 8) || c->vtpend.ensure((size_t) nt * 4 + 8))
+        return set_err(FKGPU_E_NOMEM,"out of device memory (profile tiles)");
+      if (nt > 0)
+        { CU(cudaMemcpyAsync(c->vtsrc.p,vsrc.data(),(size_t) nt * 8,cudaMemcpyHostToDevice,c->st));
+          CU(cudaMemcpyAsync(c->vtplo.p,vlo.data(),(size_t) nt * 4,cudaMemcpyHostToDevice,c->st));
+          CU(cudaMemcpyAsync(c->vtpend.p,vend.data(),(size_t) nt * 4,cudaMemcpyHostToDevice,c->st));
+        }
+      q.vt_src = (const long long *) c->vtsrc.p; q.vt_plo = (const int *) c->vtplo.p; q.vt_pend = (const int *) c->vtpend.p;
+      for (int sl = 0; sl < FKGPU_PROF_SLICES; sl++)
+        { const long long t0 = nt * sl / FKGPU_PROF_SLICES, t1 = nt * (sl + 1) / FKGPU_PROF_SLICES;
+          if (t1 <= t0) continue;
+          q.vt0 = t0;
+          rc = hash ? profiles_launch<NW,true>(c,q,true,t1 - t0) : profiles_launch<NW,false>(c,q,true,t1 - t0);
+          if (rc) return rc;
+          const long long d0 = vdst[t0], d1 = (t1 < nt) ? vdst[t1] : run;
+          if (d1 > d0)
+            { CU(cudaEventRecord(c->ev_prof,c->st));
+              CU(cudaStreamWaitEvent(c->cst,c->ev_prof,0));
+              CU(cudaMemcpyAsync((uint16_t *) c->h_prof.p + d0,(const uint16_t *) c->pout.p + d0,(size_t) (d1 - d0) * 2,cudaMemcpyDeviceToHost,c->cst));
+            }
+        }
+      stage_end(c,FKGPU_ST_PROFILE);
+      CU(cudaStreamSynchronize(c->cst));
+    }
   CU(cudaStreamSynchronize(c->st));
   cudaEventElapsedTime(&c->ms[FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE],c->ev[2*FKGPU_ST_PROFILE+1]);
   memcpy(c->h_poff.p,pp.offs.data(),pp.offs.size()*8);
@@ -2455,15 +2559,32 @@ static int profiles_t(fkgpu_ctx *c, int64_t *nreads, const int64_t **off, const 
 { const int k = c->cfg.kmer, bc = c->cfg.bc_prefix;
   /* pieces in tid-major order; a continuation piece (rem carry) extends the previous read */
   ProfPieces pp;
+  bool ordered = true;
   for (auto &t : c->tids)
-    for (size_t i = 0; i < t.rstart.size(); i++)
-      { const int b = t.rcont[i] ? 0 : bc;
-        int pl = t.rlen[i] - b - k + 1; if (pl < 0) pl = 0;
-        if (!t.rcont[i]) pp.offs.push_back(pp.run);
-        pp.src.push_back(t.rstart[i] + b); pp.dst.push_back(pp.run); pp.len.push_back(pl);
-        pp.run += pl;
-      }
+    { size_t ch = 0;
+      long long last = -1;
+      for (size_t i = 0; i < t.rstart.size(); i++)
+        { const int b = t.rcont[i] ? 0 : bc;
+          int pl = t.rlen[i] - b - k + 1; if (pl < 0) pl = 0;
+          if (!t.rcont[i]) pp.offs.push_back(pp.run);
+          /* the chunk of this thread that holds the piece: chunks and pieces both come in arrival order */
+          while (ordered && ch < t.chunks.size() && !(t.rstart[i] >= t.chunks[ch].first && t.rstart[i] < t.chunks[ch].first + t.chunks[ch].second))
+            { ch++; last = -1; }
+          if (ordered && (ch >= t.chunks.size() || t.rstart[i] < last)) ordered = false;
+          if (ordered)
+            { if (pp.segs.empty() || pp.segs.back().off != t.chunks[ch].first || last < 0)
+                { ProfSeg sg; sg.off = t.chunks[ch].first; sg.fill = t.chunks[ch].second; sg.p0 = sg.p1 = (long long) pp.src.size();
+                  pp.segs.push_back(sg);
+                }
+              pp.segs.back().p1 = (long long) pp.src.size() + 1;
+              last = t.rstart[i] + t.rlen[i];
+            }
+          pp.src.push_back(t.rstart[i] + b); pp.dst.push_back(pp.run); pp.len.push_back(pl);
+          pp.run += pl;
+        }
+    }
   pp.offs.push_back(pp.run);
+  if (!ordered) pp.segs.clear();
   return profiles_run<NW>(c,(const u32 *) c->seq.p,(const u32 *) c->val.p,c->last_npos,pp,nreads,off,prof);
 }
 
@@ -2471,17 +2592,17 @@ template<int NW>
 static int load_profile_table_t(fkgpu_ctx *c, const uint8_t *records, int64_t n)
 { const int tw = c->kbytes + 2;
   const u64 U = (u64) n;
-  int B = ilog2_ceil(U + 1); if (B < 8) B = 8; if (B > 28) B = 28;
-  if (c->table.ensure((size_t) U * tw + 64) || c->pkeys.ensure((size_t) (U + 1) * sizeof(Key<NW>)) || c->pcnts.ensure((size_t) (U + 1) * 2)
-      || c->pidx.ensure(((size_t) (1ull << B) + 2) * 8))
+  if (c->table.ensure((size_t) U * tw + 64) || c->pkeys.ensure((size_t) (U + 1) * sizeof(Key<NW>)) || c->pcnts.ensure((size_t) (U + 1) * 2))
     return set_err(FKGPU_E_NOMEM,"out of device memory (profile lookup table of %lld k-mers)",(long long) n);
   if (U > 0)
     { CU(cudaMemcpyAsync(c->table.p,records,(size_t) U * tw,cudaMemcpyHostToDevice,c->st));
       k_records_to_keys<NW><<<(unsigned) ((U + 255) / 256),256,0,c->st>>>((const uint8_t *) c->table.p,U,c->kbytes,(Key<NW> *) c->pkeys.p,(uint16_t *) c->pcnts.p); KCHECK();
     }
-  k_build_index<NW><<<(unsigned) ((U + 1 + 255) / 256),256,0,c->st>>>((const Key<NW> *) c->pkeys.p,U,B,(u64 *) c->pidx.p); KCHECK();
+  { int rc = build_profile_lookup<NW>(c,U);
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(c->st));
-  c->ptab_n = (long long) U; c->ptab_B = B; c->res_nw = NW; c->rel_table = true;
+  c->ptab_n = (long long) U; c->res_nw = NW; c->rel_table = true;
   return FKGPU_OK;
 }
 
@@ -2587,6 +2708,12 @@ extern "C" int fkgpu_profiles_packed(fkgpu_ctx *c, const uint32_t *d_seq, const 
       pp.run += pl;
     }
   pp.offs.push_back(pp.run);
+  bool ordered = true;                 /* reads in stream order, not overlapping: the output can be written in place, in order */
+  for (int64_t i = 1; i < nreads_in && ordered; i++) ordered = (read_start[i] >= read_start[i-1] + read_len[i-1]);
+  if (ordered && nreads_in > 0)
+    { ProfSeg sg; sg.off = 0; sg.fill = npos; sg.p0 = 0; sg.p1 = (long long) nreads_in;
+      pp.segs.push_back(sg);
+    }
   return (c->res_nw == 1) ? profiles_run<1>(c,d_seq,d_val,npos,pp,nreads,off,prof) : profiles_run<2>(c,d_seq,d_val,npos,pp,nreads,off,prof);
 }
 

@@ -1590,26 +1590,130 @@ __global__ void k_build_index(const Key<NW> *keys, u64 n, int B, u64 *idx)
   for (u64 s = lo; s <= hi && s <= slots; s++) idx[s] = i;
 }
 
-struct ProfileParams
-  { ScanParams   sp;
-    const void  *keys; const uint16_t *cnts; const u64 *idx; int B;
-    uint16_t    *raw;            /* [npos] */
-  };
+/*  The lookup table of the profiles as a hash table: buckets of four 16-byte slots = one 64-byte line = two 32-byte sectors.
+ *  A key's home is one HALF (sector) of its bucket; it is stored in the first free slot of: home half, other half, next
+ *  bucket ...  A lookup reads the home half with ONE 256-bit load (LDG.E.256, new with sm_100) and in most cases is done:
+ *  one DRAM sector per lookup.  (History, ncu r2/r2n: sorted keys + prefix index + counts = 3 dependent random accesses,
+ *  294 B of DRAM per lookup; four 128-bit loads of a 64-byte bucket = 4 DRAM sectors, 128 B -- two loads that miss on the
+ *  same sector are both sent to DRAM.)
+ *  Slot = { key word 0, key word 1 | 0x8000 | count } when the key leaves the low 16 bits of word 1 free (k <= 56; for
+ *  k <= 32 word 1 is the count alone), empty = second word zero.  "wide" (k 57..64): the slot holds the two key words, the
+ *  count (| 0x8000) sits in hcnt[slot], empty = hcnt zero.  Keys are distinct, so building is claim-a-slot (one atomicCAS on
+ *  the word that holds the count), then a plain store of the rest; lookups run after the build.                          */
+struct ProfHash { const ulonglong2 *slots; const uint16_t *hcnt; u64 nbuckets; int wide; };
+
+__device__ __forceinline__ u64 fk_mix64(u64 x)
+{ x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
+
+template<int NW> __device__ __forceinline__ u64 fk_key_hash(const Key<NW> &k)
+{ u64 h = fk_mix64(k.w[0]);
+  if (NW > 1) h = fk_mix64(h ^ k.w[1]);
+  return h;
+}
 
 template<int NW>
+__global__ void __launch_bounds__(256) k_hash_build(const Key<NW> *keys, const uint16_t *cnts, u64 n, ulonglong2 *slots, uint16_t *hcnt,
+                                                    u64 nbuckets, int wide)
+{ const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Key<NW> key = keys[i];
+  const u64 c  = 0x8000ull | (u64) (cnts[i] & 0x7fffu);
+  const u64 k1 = (NW > 1) ? key.w[1] : 0ull;
+  const u64 h  = fk_key_hash<NW>(key);
+  u64 b = __umul64hi(h,nbuckets);
+  const u32 s0 = ((u32) h & 1u) << 1;                 /* home half: slots s0, s0+1; then s0^2, (s0^2)+1 */
+  for (;;)
+    { for (u32 t = 0; t < 4; t++)
+        { const u64 x = 4*b + (s0 ^ t);
+          if (wide)
+            { if (atomicCAS((unsigned short *) hcnt + x,(unsigned short) 0,(unsigned short) c) == 0)
+                { slots[x] = make_ulonglong2(key.w[0],k1); return; }
+            }
+          else if (atomicCAS((unsigned long long *) &slots[x].y,0ull,(unsigned long long) (k1 | c)) == 0ull)
+            { slots[x].x = key.w[0]; return; }
+        }
+      b = (b + 1 == nbuckets) ? 0 : b + 1;
+    }
+}
+
+/*  count of the key (k0,k1), 0 if absent (relative profiles look up k-mers the table never saw).  NOT inlined: k_profile
+ *  unrolls its 32 positions, and 32 copies of this loop made a 164 KB kernel (ncu r2n: no_instruction 31 warps per issue). */
+template<int NW>
+__device__ __noinline__ u32 hash_lookup(const ulonglong2 *slots, const uint16_t *hcnt, u64 nbuckets, int wide, u64 k0, u64 k1)
+{ if (NW == 1) k1 = 0ull;
+  Key<NW> key; key.w[0] = k0; if (NW > 1) key.w[NW-1] = k1;
+  const u64 h = fk_key_hash<NW>(key);
+  u64 b = __umul64hi(h,nbuckets);
+  const u32 s0 = ((u32) h & 1u) << 1;
+  for (;;)
+    {
+#pragma unroll
+      for (u32 half = 0; half < 2; half++)
+        { const u64 x = 4*b + (s0 ^ (half << 1));       /* slots x, x+1: one 32-byte sector */
+          u64 ax, ay, bx, by;
+          asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(ax), "=l"(ay), "=l"(bx), "=l"(by) : "l"(slots + x));
+          if (!wide)
+            { if (ax == k0 && (ay & ~0xffffull) == k1 && (ay & 0x8000ull)) return (u32) (ay & 0x7fffull);
+              if (ay == 0ull) return 0u;
+              if (bx == k0 && (by & ~0xffffull) == k1 && (by & 0x8000ull)) return (u32) (by & 0x7fffull);
+              if (by == 0ull) return 0u;
+            }
+          else
+            { if (ax == k0 && ay == k1) { const u32 c = hcnt[x]; return c & 0x7fffu; }       /* c == 0: the all-zero key met a free slot */
+              if ((ax | ay) == 0ull && hcnt[x] == 0) return 0u;
+              if (bx == k0 && by == k1) { const u32 c = hcnt[x+1]; return c & 0x7fffu; }
+              if ((bx | by) == 0ull && hcnt[x+1] == 0) return 0u;
+            }
+        }
+      b = (b + 1 == nbuckets) ? 0 : b + 1;
+    }
+}
+
+/*  k_profile<NW,HASH,DIRECT>.  DIRECT: the grid walks VIRTUAL tiles -- the tiles of the chunks of the read stream taken in
+ *  the order of the output (input thread by input thread, each thread's chunks as they arrived), tile t starting at position
+ *  vt_src[t] -- and every thread writes the counts of its 32 positions straight to their places in the output: pieces
+ *  [vt_plo[t], vt_pend[t]) are the reads (src, len -> dst) that meet the tile, sorted by src.  Output order = launch order, so
+ *  the host copies the output back in slices while later tiles are still being looked up.  !DIRECT: tile b = positions
+ *  [b*SCAN_TILE ..), one u16 per position into raw[] (k_gather_profile then moves the pieces).                            */
+struct ProfileParams
+  { ScanParams   sp;
+    const void  *keys; const uint16_t *cnts; const u64 *idx; int B;      /* !HASH: sorted keys, counts, 2^B-slot prefix index */
+    ProfHash     H;
+    uint16_t    *raw;            /* !DIRECT: [npos] */
+    const long long *vt_src; const int *vt_plo, *vt_pend; long long vt0;  /* DIRECT: virtual tiles, first tile of this launch */
+    const long long *psrc, *pdst; const int *plen;
+    uint16_t    *out;
+  };
+
+__device__ __forceinline__ void scan_load_at(const ScanParams &p, long long pos0, u32 *s_seq, u32 *s_val)   /* pos0 % 32 == 0 */
+{ const long long w0 = (pos0 >> 4) - SCAN_LHALO;
+  for (int i = threadIdx.x; i < SCAN_SEQW; i += SCAN_TPB)
+    { long long g = w0 + i;
+      s_seq[i] = (g >= 0 && g < p.nseqw) ? __ldg(p.seq+g) : 0u;
+    }
+  const long long v0 = pos0 >> 5;
+  for (int i = threadIdx.x; i < SCAN_VALW; i += SCAN_TPB)
+    { long long g = v0 + i;
+      s_val[i] = (g < p.nvalw) ? __ldg(p.val+g) : 0u;
+    }
+}
+
+template<int NW, bool HASH, bool DIRECT>
 __global__ void __launch_bounds__(SCAN_TPB) k_profile(ProfileParams q)
 { extern __shared__ u32 s_dyn[];
   u32 *s_seq = s_dyn;
   u32 *s_val = s_seq + SCAN_SEQW;
   constexpr int NW32 = 2*NW;
   const ScanParams &p = q.sp;
-  scan_load_tile(p,blockIdx.x,s_seq,s_val);
+  const long long vt = DIRECT ? q.vt0 + blockIdx.x : (long long) blockIdx.x;
+  const long long tile0 = DIRECT ? q.vt_src[vt] : vt * SCAN_TILE;
+  scan_load_at(p,tile0,s_seq,s_val);
   __syncthreads();
   Window w;
   load_window(w,s_seq,s_val,threadIdx.x,p.k);
   u32 km[4] = { p.kmask[0], p.kmask[1], p.kmask[2], p.kmask[3] };
   const Key<NW> *keys = (const Key<NW> *) q.keys;
-  const long long p0 = (long long) blockIdx.x * SCAN_TILE + (long long) threadIdx.x * SCAN_PPT;
+  const long long p0 = tile0 + (long long) threadIdx.x * SCAN_PPT;
   u32 res[SCAN_PPT/2];
 #pragma unroll
   for (int i = 0; i < SCAN_PPT/2; i++) res[i] = 0;
@@ -1617,23 +1721,67 @@ __global__ void __launch_bounds__(SCAN_TPB) k_profile(ProfileParams q)
     { Key<NW> key;
 #pragma unroll
       for (int m = 0; m < NW; m++) key.w[m] = ((u64) C[2*m] << 32) | C[2*m+1];
-      const u64 s = key.w[0] >> (64 - q.B);
-      u64 lo = q.idx[s], hi = q.idx[s+1];
       u32 c = 0;
-      while (lo < hi)
-        { u64 mid = (lo + hi) >> 1;
-          Key<NW> t = keys[mid];
-          if (key_eq<NW>(t,key)) { c = q.cnts[mid]; break; }
-          if (key_lt<NW>(t,key)) lo = mid+1; else hi = mid;
+      if (HASH) c = hash_lookup<NW>(q.H.slots,q.H.hcnt,q.H.nbuckets,q.H.wide,key.w[0],(NW > 1) ? key.w[NW-1] : 0ull);
+      else
+        { const u64 s = key.w[0] >> (64 - q.B);
+          u64 lo = q.idx[s], hi = q.idx[s+1];
+          while (lo < hi)
+            { u64 mid = (lo + hi) >> 1;
+              Key<NW> t = keys[mid];
+              if (key_eq<NW>(t,key)) { c = q.cnts[mid]; break; }
+              if (key_lt<NW>(t,key)) lo = mid+1; else hi = mid;
+            }
         }
       res[j>>1] |= c << (16*(j&1));
     };
-  KmerLoop<NW32,0>::run(w,km,fn);
-  if (p0 < p.npos)
-    { u32 *out = (u32 *) (q.raw + p0);            /* p0 is a multiple of 32: 4-byte aligned */
+  if (!DIRECT)
+    { KmerLoop<NW32,0>::run(w,km,fn);
+      if (p0 < p.npos)
+        { u32 *out = (u32 *) (q.raw + p0);            /* p0 is a multiple of 32: 4-byte aligned */
 #pragma unroll
-      for (int i = 0; i < SCAN_PPT/2; i++)
-        if (p0 + 2*i < p.npos) out[i] = res[i];
+          for (int i = 0; i < SCAN_PPT/2; i++)
+            if (p0 + 2*i < p.npos) out[i] = res[i];
+        }
+      return;
+    }
+  /* the first piece that ends beyond p0 */
+  int i = q.vt_plo[vt];
+  const int pe = q.vt_pend[vt];
+  { int lo = i, hi = pe;
+    while (lo < hi)
+      { const int mid = (lo + hi) >> 1;
+        if (q.psrc[mid] + q.plen[mid] > p0) hi = mid; else lo = mid + 1;
+      }
+    i = lo;
+  }
+  if (i >= pe || q.psrc[i] >= p0 + SCAN_PPT) return;          /* no read position among these 32: nothing to look up */
+  KmerLoop<NW32,0>::run(w,km,fn);
+  long long s = q.psrc[i], e = s + q.plen[i], db = q.pdst[i] - s;   /* output index of position x of piece i: db + x */
+  if (p0 >= s && p0 + SCAN_PPT <= e)
+    { uint16_t *d = q.out + (db + p0);
+      if ((((size_t) d) & 3) == 0)
+        { u32 *d32 = (u32 *) d;
+#pragma unroll
+          for (int x = 0; x < SCAN_PPT/2; x++) d32[x] = res[x];
+        }
+      else                                               /* odd output index: the pairs straddle the words */
+        { d[0] = (uint16_t) (res[0] & 0xffffu);
+          u32 *d32 = (u32 *) (d + 1);
+#pragma unroll
+          for (int x = 0; x + 1 < SCAN_PPT/2; x++) d32[x] = __funnelshift_r(res[x],res[x+1],16);
+          d[SCAN_PPT-1] = (uint16_t) (res[SCAN_PPT/2-1] >> 16);
+        }
+      return;
+    }
+#pragma unroll
+  for (int j = 0; j < SCAN_PPT; j++)
+    { const long long pos = p0 + j;
+      while (i < pe && pos >= e)
+        { i += 1;
+          if (i < pe) { s = q.psrc[i]; e = s + q.plen[i]; db = q.pdst[i] - s; }
+        }
+      if (i < pe && pos >= s) q.out[db + pos] = (uint16_t) ((res[j>>1] >> (16*(j&1))) & 0xffffu);
     }
 }
 

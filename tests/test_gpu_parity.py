@@ -221,6 +221,42 @@ def test_profiles_match_oracle(oracle_lib, k, bc, nthreads):
         assert np.array_equal(prof[off[r]:off[r + 1]], want["profiles"][r]), f"profile of read {r} differs"
 
 
+@pytest.mark.parametrize("k,reserve_frac", [(40, 1.3), (63, 0.0), (21, 0.3)])
+def test_profiles_with_interleaved_chunks(oracle_lib, monkeypatch, k, reserve_frac):
+    """The profile output is tid-major while the device read stream holds the chunks in arrival order: three threads whose
+    blocks arrive interleaved (so their 64 KB chunks alternate in the stream), ~150 tiles in 16 slices; streamed, plain and
+    abandoned-stream front ends.  Long and short reads, so tiles hold many pieces and pieces span many tiles."""
+    monkeypatch.setenv("FKGPU_CHUNK_BYTES", str(64 << 10))
+    genome = synth.random_genome(120_000, 81)
+    reads = synth.sample_reads(genome, 3000, 150, 0.003, 82, n_rate=0.002, len_jitter=100)
+    reads += synth.sample_reads(genome, 40, 12_000, 0.002, 83) + [b"", b"ACGT", b"N" * 70]
+    nthreads = 3
+    total = sum(len(r) + 1 for r in reads)
+    want = oracle_lib.count(reads, k, cutoff=1, profiles=True)
+    g = FastKGPU(k=k, table_cutoff=1, profile=True, nthreads=nthreads, reserve_bases=int(total * reserve_frac))
+    try:
+        its = []
+        for t in range(nthreads):                      # tid t owns a contiguous slice; blocks are handed over round-robin
+            mine = reads[len(reads) * t // nthreads: len(reads) * (t + 1) // nthreads]
+            its.append(iter(synth.blocks(mine, max_bytes=30_000)))
+        live = list(range(nthreads))
+        while live:
+            for t in list(live):
+                nxt = next(its[t], None)
+                if nxt is None:
+                    live.remove(t)
+                else:
+                    g.ingest(nxt[0], nxt[1].astype(np.int32), tid=t)
+        got = g.finish(fetch_table=True)
+        assert np.array_equal(got.table, want["table"])
+        off, prof = g.profiles()
+        assert len(off) == len(reads) + 1
+        for r in range(len(reads)):
+            assert np.array_equal(prof[off[r]:off[r + 1]], want["profiles"][r]), f"profile of read {r} differs"
+    finally:
+        g.close()
+
+
 def test_split_long_read_rem_semantics(oracle_lib):
     """A read delivered in pieces with rem > 0 and a k-1 overlap (io.c:296-333) counts and profiles as one read."""
     k = 40
