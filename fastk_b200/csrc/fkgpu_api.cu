@@ -2486,6 +2486,10 @@ static int profiles_run(fkgpu_ctx *c, const u32 *d_seq, const u32 *d_val, long l
   fill_scan_params(c,q.sp,d_seq,d_val,npos,0,g);
   q.keys = c->pkeys.p; q.cnts = (const uint16_t *) c->pcnts.p; q.idx = (const u64 *) c->pidx.p; q.B = c->ptab_B;
   q.H.slots = (const ulonglong2 *) c->phash.p; q.H.hcnt = (const uint16_t *) c->phcnt.p; q.H.nbuckets = c->ph_nbuckets; q.H.wide = c->ph_wide;
+  { static int ltc = -1;            /* L2::64B on the lookup loads: DRAM bytes per lookup 127 -> 67 (ncu r2q), same time; FKGPU_PROF_LTC=0 drops the hint */
+    if (ltc < 0) { const char *e = getenv("FKGPU_PROF_LTC"); ltc = e ? atoi(e) : 64; }
+    if (ltc == 64) q.H.wide |= 2;
+  }
   q.raw = (uint16_t *) c->praw.p;
   q.psrc = (const long long *) c->psrc.p; q.pdst = (const long long *) c->pdst.p; q.plen = (const int *) c->plen.p;
   q.out = (uint16_t *) c->pout.p;

@@ -1600,7 +1600,7 @@ __global__ void k_build_index(const Key<NW> *keys, u64 n, int B, u64 *idx)
  *  k <= 32 word 1 is the count alone), empty = second word zero.  "wide" (k 57..64): the slot holds the two key words, the
  *  count (| 0x8000) sits in hcnt[slot], empty = hcnt zero.  Keys are distinct, so building is claim-a-slot (one atomicCAS on
  *  the word that holds the count), then a plain store of the rest; lookups run after the build.                          */
-struct ProfHash { const ulonglong2 *slots; const uint16_t *hcnt; u64 nbuckets; int wide; };
+struct ProfHash { const ulonglong2 *slots; const uint16_t *hcnt; u64 nbuckets; int wide; };   /* wide: bit 0 = counts in hcnt, bit 1 = lookups carry the L2::64B hint */
 
 __device__ __forceinline__ u64 fk_mix64(u64 x)
 { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
@@ -1651,8 +1651,9 @@ __device__ __noinline__ u32 hash_lookup(const ulonglong2 *slots, const uint16_t 
       for (u32 half = 0; half < 2; half++)
         { const u64 x = 4*b + (s0 ^ (half << 1));       /* slots x, x+1: one 32-byte sector */
           u64 ax, ay, bx, by;
-          asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(ax), "=l"(ay), "=l"(bx), "=l"(by) : "l"(slots + x));
-          if (!wide)
+          if (wide & 2) asm volatile("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(ax), "=l"(ay), "=l"(bx), "=l"(by) : "l"(slots + x));
+          else          asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(ax), "=l"(ay), "=l"(bx), "=l"(by) : "l"(slots + x));
+          if (!(wide & 1))
             { if (ax == k0 && (ay & ~0xffffull) == k1 && (ay & 0x8000ull)) return (u32) (ay & 0x7fffull);
               if (ay == 0ull) return 0u;
               if (bx == k0 && (by & ~0xffffull) == k1 && (by & 0x8000ull)) return (u32) (by & 0x7fffull);
