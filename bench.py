@@ -113,7 +113,7 @@ def make_rows(a, rank, out=None):
 
 class ClockSampler:
     """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md).  NVML in-process (one cheap query
-    every 20 ms from a thread); a polling nvidia-smi child was measured to stall the driver by tens of milliseconds per step on
+    every 50 ms from a thread); a polling nvidia-smi child was measured to stall the driver by tens of milliseconds per step on
     some boxes.  Falls back to nvidia-smi when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -158,7 +158,7 @@ class ClockSampler:
                             self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)
 
     def _pump(self):
         for line in self.p.stdout:
@@ -641,6 +641,9 @@ def main():
                "sortcount": N * W + U * (W + 4),
                "compact": U * (W + 4) + ntab * (res.kmer_bytes + 2)}
     stage_ms["super_partition"] = stage_ms.get("super_partition", 0.0) + stage_ms.pop("super_refine", 0.0)   # both levels
+    if a.profile and stage_ms.get("profile", 0.0) > 0:
+        # -p: the packed reads once more, one 32-byte sector of the hash table per k-mer, one u16 out per k-mer
+        alg["profile"] = nbases * 0.375 + N * (32 + 2)
     per_stage = {}
     for s, b in alg.items():
         ms = stage_ms.get(s, 0.0) / a.steps
