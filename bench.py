@@ -453,9 +453,12 @@ def main():
                 eng.ingest_ptr(base_ptr + r0 * (L + 1), boff_full.ctypes.data, r1 - r0, tid=tid)
 
         feed = None
-        if a.e2e_feeder == "c":
+        feeder_so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fastk_b200", "lib", "libfk_feeder.so")
+        if a.e2e_feeder == "c" and not os.path.exists(feeder_so):
+            print("bench.py: %s is missing (run __graft_entry__.build()); the e2e arm uses Python producer threads" % feeder_so, file=sys.stderr)
+        if a.e2e_feeder == "c" and os.path.exists(feeder_so):
             import ctypes as C
-            flib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fastk_b200", "lib", "libfk_feeder.so"))
+            flib = C.CDLL(feeder_so)
             flib.fk_feed_blocks.restype = C.c_int
             flib.fk_feed_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int]
             contig = 1 if (a.profile or a.e2e_order == "contig") else 0

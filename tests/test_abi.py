@@ -57,3 +57,17 @@ def test_host_program_refuses_without_input():
     import subprocess
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and "Usage: FastK" in r.stderr
+
+
+def test_block_feeder_loads_and_rejects_bad_arguments():
+    """The producer-thread helper of bench.py's e2e arm (fastk_b200/host/fk_block_feeder.c) links against the library,
+    exports fk_feed_blocks and refuses a NULL context without touching the device."""
+    so = os.path.join(ROOT, "fastk_b200", "lib", "libfk_feeder.so")
+    if not os.path.exists(so):
+        pytest.skip("host helpers not built")
+    dll = ctypes.CDLL(so)
+    dll.fk_feed_blocks.restype = ctypes.c_int
+    dll.fk_feed_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int]
+    buf = ctypes.create_string_buffer(64)
+    assert dll.fk_feed_blocks(None, 4, buf, 1, 16, 1, 0) == -3          # FKGPU_E_ARG
+    assert dll.fk_feed_blocks(None, 0, buf, 1, 16, 1, 0) == -3
