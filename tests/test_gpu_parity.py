@@ -339,3 +339,20 @@ def test_relative_profiles_against_a_loaded_table(oracle_lib):
         assert np.array_equal(off, g["prof_off"]) and np.array_equal(prof, g["prof"])
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("env", [{"FKGPU_PROF": "legacy"}, {"FKGPU_PROF_LTC": "0"}])
+def test_profile_path_switches(env):
+    """The profile path has two process-wide switches (read once): FKGPU_PROF=legacy (sorted keys + prefix index + gather) and
+    FKGPU_PROF_LTC=0 (lookups without the L2::64B hint).  Each runs the oracle comparisons of this file in a child process."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "test_profiles_match_oracle or test_relative_profiles_against_a_loaded_table"],
+                       env=e, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(here)), timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
