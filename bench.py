@@ -75,6 +75,7 @@ def parse():
     ap.add_argument("--cutoff", type=int, default=None, help="-t<cutoff>")
     ap.add_argument("--ingest-threads", type=int, default=0, help="e2e arm: ingest threads (0 = host cores, at most 16)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the FASTA-on-disk -> files-on-disk run of fastk_b200/bin/FastK")
     ap.add_argument("--e2e-feeder", default="c", choices=["c", "py"],
                     help="e2e arm: the producer threads that call fkgpu_ingest per DATA_BLOCK: C pthreads (fastk_b200/host/fk_block_feeder.c, "
                          "what a FastK host has) or Python threads")
@@ -227,6 +228,32 @@ def run_reference_once(a, fasta, tmpdir, cores):
         subprocess.check_call([exe, f"-k{a.kmer}", f"-t{a.cutoff}", f"-N{out}", fasta],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return time.perf_counter() - t0, kind, cores
+
+
+def files_arm(a, fasta, tmpdir, cores, device, t_ref):
+    """SURVEY.md 8(d), reported separately: FASTA on disk -> .hist/.ktab(/.prof) on disk through OUR host program
+    (fastk_b200/bin/FastK, same options as the reference run beside it, process start and CUDA initialisation included),
+    and the two runs' files compared (tiers T0 / T1).  Never fails the bench: an error is reported in the object."""
+    exe = os.path.join(ROOT, "fastk_b200", "bin", "FastK")
+    if not os.path.exists(exe):
+        return {"error": "fastk_b200/bin/FastK not built"}
+    try:
+        from fastk_b200 import formats
+        out = os.path.join(tmpdir, "gpu_out")
+        cmd = [exe, f"-k{a.kmer}", f"-t{a.cutoff}", f"-T{cores}", f"-P{tmpdir}", f"-N{out}"] + (["-p"] if a.profile else []) + [fasta]
+        env = dict(os.environ, FASTK_GPU=str(device))
+        t0 = time.perf_counter()
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, timeout=900)
+        t = time.perf_counter() - t0
+        bad = formats.compare_fastk_outputs(tmpdir, "cpu_out", "gpu_out", table=a.cutoff > 0)
+        nb = a.nreads * a.read_len
+        return {"value": nb / t / 1e9, "unit": "Gbases/s", "wall_s": round(t, 3), "reference_wall_s": round(t_ref, 3),
+                "what": "FASTA on tmpfs -> .hist/.ktab" + ("/.prof" if a.profile else "") + " on tmpfs: " + " ".join(
+                    [os.path.relpath(cmd[0], ROOT)] + cmd[1:3] + [f"-T{cores}"] + (["-p"] if a.profile else [])) +
+                        "; one run, process start + CUDA initialisation included",
+                "files_equal_reference": not bad, "mismatches": bad}
+    except Exception as e:                                   # noqa: BLE001 -- a side measurement must not end the bench
+        return {"error": str(e)[:300]}
 
 
 def sample_text(a, cores, extra=""):
@@ -525,7 +552,7 @@ def main():
             problems.append("e2e and device-resident arms disagree")
 
     # ---- parity against the reference FastK on the FASTA of rank 0's reads, and the CPU baseline (the same run) --------
-    cpu, parity = None, {"checked": False}
+    cpu, parity, files = None, {"checked": False}, None
     if not a.no_cpu and ref_binary() is not None and host_ascii is not None:
         tmpdir = scratch_dir("fastk_cpu_") if rank == 0 else None
         try:
@@ -534,6 +561,8 @@ def main():
                 synth.write_rows_fasta(host_ascii.numpy(), fasta)
                 cores = os.cpu_count() or 1
                 t, kind, used = run_reference_once(a, fasta, tmpdir, cores)
+                if world == 1 and not a.no_files:
+                    files = files_arm(a, fasta, tmpdir, cores, local, t)
                 os.remove(fasta)
                 if world == 1:
                     cpu = {"value": nbases / t / 1e9, "unit": "Gbases/s", "cores": used, "kind": kind,
@@ -699,6 +728,7 @@ def main():
                            % (npos * 0.375 / 1e6, N * W / 1e9),
                            "parallelism": parallelism},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "files": files,
                 "parity_checked": bool(parity.get("checked") and parity.get("ok") and not problems), "parity": parity,
                 "invariant_violations": problems}
         emit(line)

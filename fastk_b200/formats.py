@@ -91,3 +91,25 @@ def compare_with_fastk_files(d, root, k, cutoff, hist, max_inst, table):
     if a != n:
         bad.append(".ktab parts hold a different number of entries")
     return bad
+
+
+def compare_fastk_outputs(d, root_a, root_b, table=True):
+    """Two FastK runs' files in directory d (tiers T0 / T1 of DESIGN.md §1): `.hist` byte-identical; `.ktab` stub
+    byte-identical and the concatenated payload of the hidden parts byte-identical.  -> list of mismatches."""
+    bad = []
+    ha, hb = (open(os.path.join(d, r + ".hist"), "rb").read() for r in (root_a, root_b))
+    if ha != hb:
+        bad.append(".hist files differ")
+    if not table:
+        return bad
+    sa, sb = (open(os.path.join(d, r + ".ktab"), "rb").read() for r in (root_a, root_b))
+    if sa != sb:
+        bad.append(".ktab stubs differ")
+        return bad
+    pa = [np.asarray(p) for p in ktab_parts(d, root_a, read_ktab_stub(d, root_a))]
+    pb = [np.asarray(p) for p in ktab_parts(d, root_b, read_ktab_stub(d, root_b))]
+    ca = np.concatenate(pa) if pa else np.zeros((0, 1), np.uint8)
+    cb = np.concatenate(pb) if pb else np.zeros((0, 1), np.uint8)
+    if ca.shape != cb.shape or not np.array_equal(ca, cb):
+        bad.append(f".ktab hidden-part payloads differ ({ca.shape[0]} vs {cb.shape[0]} records)")
+    return bad

@@ -181,3 +181,24 @@ def test_table_reader_round_trip(oracle_lib, fkfiles, name, tmp_path):
         back = np.ctypeslib.as_array(rec, shape=(n.value * tab.shape[1],)).reshape(n.value, tab.shape[1])
         assert np.array_equal(back, tab)
     assert fkfiles.fk_read_ktab(os.path.join(str(tmp_path), "missing").encode(), C.byref(k), C.byref(cut), C.byref(rec), C.byref(n)) != 0
+
+
+def test_compare_fastk_outputs_on_two_reference_runs(tmp_path):
+    """formats.compare_fastk_outputs (bench.py's files arm): two runs of the compiled reference on the same FASTA with
+    different -M (different hidden-part splits are allowed, T1) compare equal; a different cutoff does not."""
+    import subprocess
+    import numpy as np
+    from fastk_b200 import formats, synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "FastK")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/FastK not built")
+    genome = synth.random_genome(30_000, 5)
+    reads = synth.sample_reads(genome, 3000, 150, 0.005, 6)
+    fa = str(tmp_path / "r.fasta")
+    synth.write_fasta(reads, fa)
+    for name, extra in (("a", ["-t1", "-M1"]), ("b", ["-t1", "-M4"]), ("c", ["-t2", "-M1"])):
+        subprocess.check_call([ref, "-k40", "-T3", f"-P{tmp_path}", f"-N{tmp_path}/{name}"] + extra + [fa],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert formats.compare_fastk_outputs(str(tmp_path), "a", "b") == []
+    assert formats.compare_fastk_outputs(str(tmp_path), "a", "c") != []
+    assert formats.compare_fastk_outputs(str(tmp_path), "a", "c", table=False) == []
