@@ -351,7 +351,7 @@ int main(int argc, char *argv[])
 { int   i, nfiles = 0;
   char *files[4096];
   char *spath = NULL;
-  double t0 = now(), t1, t2, t3;
+  double t0 = now(), tc, t1, t2, t3, t4;
 
   for (i = 1; i < argc; i++)
     if (argv[i][0] == '-' && argv[i][1] != '\0')
@@ -474,6 +474,7 @@ int main(int argc, char *argv[])
     }
   have_out = 1;
   fk_remove_outputs(OUT_DIR,OUT_ROOT);
+  tc = now();
 
   if (VERBOSE)
     fprintf(stderr,"\nPhase 1: Reading %d file(s) with %d thread(s) into the GPU k-mer counter\n",nfiles,ITHREADS);
@@ -571,13 +572,14 @@ int main(int argc, char *argv[])
         { fprintf(stderr,"%s: Cannot write to %s/%s.prof.  Enough disk space?\n",Prog_Name,OUT_DIR,OUT_ROOT); Clean_Exit(1); }
     }
   t3 = now();
+  have_out = 0;
+  { int g; for (g = 0; g < NGPUS; g++) fkgpu_destroy(CTXS[g]); }
+  t4 = now();
   if (VERBOSE)
     { struct rusage ru;
       getrusage(RUSAGE_SELF,&ru);
-      fprintf(stderr,"\nTotal Resources:  %.3fs wall (read %.3f, count %.3f, write %.3f)  %ldMB\n",
-              t3-t0,t1-t0,t2-t1,t3-t2,ru.ru_maxrss/1024);
+      fprintf(stderr,"\nTotal Resources:  %.3fs wall (init %.3f, read %.3f, count %.3f, write %.3f, release %.3f)  %ldMB\n",
+              t4-t0,tc-t0,t1-tc,t2-t1,t3-t2,t4-t3,ru.ru_maxrss/1024);
     }
-  have_out = 0;
-  { int g; for (g = 0; g < NGPUS; g++) fkgpu_destroy(CTXS[g]); }
   return 0;
 }
