@@ -733,7 +733,7 @@ def main():
                            % (npos * 0.375 / 1e6, N * W / 1e9),
                            "parallelism": parallelism},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "files": files,
+                "e2e_files": files,
                 "parity_checked": bool(parity.get("checked") and parity.get("ok") and not problems), "parity": parity,
                 "invariant_violations": problems}
         emit(line)
