@@ -148,7 +148,9 @@ int  fkgpu_count_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d
 
 /*  Count profiles over a packed stream counted by fkgpu_count_packed on a context with do_profile (the device-resident
  *  form of fkgpu_profiles; count.c:817-1181): read i occupies positions [read_start[i], read_start[i] + read_len[i]) of
- *  the stream (host arrays).  Outputs as fkgpu_profiles.                                                          */
+ *  the stream (host arrays).  Outputs as fkgpu_profiles.  Reads given in stream order without overlap take the fast
+ *  path (counts written in output order, copied to the host in slices under the lookups); any other order is served
+ *  through a per-position array and a gather.                                                                     */
 int  fkgpu_profiles_packed(fkgpu_ctx *ctx, const uint32_t *d_seq, const uint32_t *d_val, int64_t npos,
                            const int64_t *read_start, const int32_t *read_len, int64_t nreads_in,
                            int64_t *nreads, const int64_t **off, const uint16_t **prof);
